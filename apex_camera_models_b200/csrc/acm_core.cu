@@ -1,0 +1,601 @@
+// Context, memory, point buffers (AoS <-> SoA), camera parameter blocks, NCCL plumbing.
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include <new>
+
+#include "acm_internal.cuh"
+
+// ---------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+void acm_set_global_error(const char* msg) { g_last_error = msg; }
+
+int32_t acm_fail(acm_ctx* ctx, int32_t code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    g_last_error = buf;
+    return code;
+}
+
+extern "C" const char* acm_last_error(const acm_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+extern "C" int32_t acm_abi_version(void) { return ACM_ABI_VERSION; }
+
+// ---------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------
+extern "C" int32_t acm_ctx_create(int32_t device, void* cuda_stream, acm_ctx** out) {
+    if (!out) return acm_fail(nullptr, ACM_ERR_INVALID_ARG, "acm_ctx_create: null output");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return acm_fail(nullptr, ACM_ERR_NO_DEVICE, "no CUDA device available (%s); libacm has no CPU fallback",
+                        e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= count) return acm_fail(nullptr, ACM_ERR_INVALID_ARG, "device %d out of range [0,%d)", device, count);
+    acm_ctx* ctx = new (std::nothrow) acm_ctx();
+    if (!ctx) return acm_fail(nullptr, ACM_ERR_INVALID_ARG, "out of host memory");
+    ctx->device = device;
+    ctx->comm = nullptr; ctx->n_ranks = 1; ctx->rank = 0;
+    ctx->launches = 0;
+    ctx->d_partials = nullptr; ctx->partials_cap = 0; ctx->d_reduce = nullptr; ctx->d_ticket = nullptr; ctx->h_reduce = nullptr;
+    ctx->d_lm = nullptr; ctx->h_lm = nullptr; ctx->d_stage[0] = ctx->d_stage[1] = nullptr; ctx->stage_cap = 0;
+    ctx->h_stage = nullptr; ctx->h_stage_cap = 0;
+#define CREATE_CUDA(call)                                                                                     \
+    do { cudaError_t _e = (call); if (_e != cudaSuccess) { int32_t rc = acm_fail(nullptr, ACM_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(_e)); delete ctx; return rc; } } while (0)
+    CREATE_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CREATE_CUDA(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->l2_bytes = (size_t)prop.l2CacheSize;
+    ctx->cc = prop.major * 10 + prop.minor;
+    if (cuda_stream) { ctx->stream = (cudaStream_t)cuda_stream; ctx->owns_stream = false; }
+    else { CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->owns_stream = true; }
+    CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    CREATE_CUDA(cudaEventCreate(&ctx->t0));
+    CREATE_CUDA(cudaEventCreate(&ctx->t1));
+    for (int i = 0; i < 4; ++i) CREATE_CUDA(cudaEventCreateWithFlags(&ctx->chunk_ev[i], cudaEventDisableTiming));
+    CREATE_CUDA(cudaMalloc(&ctx->d_reduce, 1024 * sizeof(double)));
+    CREATE_CUDA(cudaMalloc(&ctx->d_ticket, 64 * sizeof(unsigned int)));
+    CREATE_CUDA(cudaMemset(ctx->d_ticket, 0, 64 * sizeof(unsigned int)));
+    CREATE_CUDA(cudaMallocHost(&ctx->h_reduce, 1024 * sizeof(double)));
+    CREATE_CUDA(cudaMalloc(&ctx->d_lm, 4096));
+    CREATE_CUDA(cudaMemset(ctx->d_lm, 0, 4096));
+    CREATE_CUDA(cudaMallocHost(&ctx->h_lm, 4096));
+#undef CREATE_CUDA
+    *out = ctx;
+    return ACM_OK;
+}
+
+extern "C" int32_t acm_ctx_destroy(acm_ctx* ctx) {
+    if (!ctx) return ACM_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    acm_comm_destroy(ctx);
+    cudaFree(ctx->d_partials); cudaFree(ctx->d_reduce); cudaFree(ctx->d_ticket); cudaFreeHost(ctx->h_reduce);
+    cudaFree(ctx->d_lm); cudaFreeHost(ctx->h_lm);
+    cudaFree(ctx->d_stage[0]); cudaFree(ctx->d_stage[1]); cudaFreeHost(ctx->h_stage);
+    for (int i = 0; i < 4; ++i) cudaEventDestroy(ctx->chunk_ev[i]);
+    cudaEventDestroy(ctx->t0); cudaEventDestroy(ctx->t1);
+    cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return ACM_OK;
+}
+
+extern "C" int32_t acm_ctx_sync(acm_ctx* ctx) {
+    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ACM_OK;
+}
+
+extern "C" int32_t acm_ctx_device_info(const acm_ctx* ctx, int64_t info[4]) {
+    if (!ctx || !info) return ACM_ERR_INVALID_ARG;
+    info[0] = ctx->sm_count; info[1] = (int64_t)ctx->l2_bytes; info[2] = 0; info[3] = ctx->cc;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess) info[2] = (int64_t)prop.sharedMemPerBlockOptin;
+    return ACM_OK;
+}
+
+extern "C" int32_t acm_timer_start(acm_ctx* ctx) {
+    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_CUDA(ctx, cudaEventRecord(ctx->t0, ctx->stream));
+    return ACM_OK;
+}
+extern "C" int32_t acm_timer_stop(acm_ctx* ctx, float* elapsed_ms) {
+    if (!ctx || !elapsed_ms) return ACM_ERR_INVALID_ARG;
+    ACM_CUDA(ctx, cudaEventRecord(ctx->t1, ctx->stream));
+    ACM_CUDA(ctx, cudaEventSynchronize(ctx->t1));
+    ACM_CUDA(ctx, cudaEventElapsedTime(elapsed_ms, ctx->t0, ctx->t1));
+    return ACM_OK;
+}
+extern "C" uint64_t acm_ctx_kernel_launches(const acm_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---------------------------------------------------------------------------------------
+// camera parameter blocks (host logic; mirrors `new` and `validate_params` of every model)
+// ---------------------------------------------------------------------------------------
+static const int kNParams[7] = {4, 9, 8, 5, 6, 6, 5};
+static const char* kExpect[7] = {
+    "Expected 4 parameters (fx, fy, cx, cy), got %zu",                      // pinhole.rs:82-87
+    "Expected 9 parameters (fx, fy, cx, cy, k1, k2, p1, p2, k3), got %zu",  // rad_tan.rs:108-113
+    "Expected 8 parameters, got %zu",                                       // kannala_brandt.rs:123-128
+    "Expected 5 parameters (fx, fy, cx, cy, alpha), got %zu",               // ucm.rs:114-119
+    "Expected 6 parameters (fx, fy, cx, cy, alpha, beta), got %zu",         // eucm.rs
+    "Expected 6 parameters (fx, fy, cx, cy, alpha, xi), got %zu",           // double_sphere.rs:134-139
+    "Expected 5 parameters (fx, fy, cx, cy, w), got %zu"};                  // fov.rs:114-119
+
+extern "C" int32_t acm_n_params(int32_t model) { return (model >= 0 && model < 7) ? kNParams[model] : ACM_ERR_INVALID_ARG; }
+
+static void put_msg(char* msg, size_t len, const char* text) {
+    if (msg && len) { strncpy(msg, text, len - 1); msg[len - 1] = 0; }
+}
+
+extern "C" int32_t acm_validate_params(const acm_camera* cam, char* msg, size_t msg_len) {
+    put_msg(msg, msg_len, "");
+    if (!cam || cam->model < 0 || cam->model > 6 || cam->n_params != kNParams[cam->model]) {
+        put_msg(msg, msg_len, "invalid camera block");
+        return ACM_ERR_INVALID_ARG;
+    }
+    const double* p = cam->params;
+    // validation::validate_intrinsics (mod.rs:362-370)
+    if (p[0] <= 0.0 || p[1] <= 0.0) { put_msg(msg, msg_len, "Focal length must be positive"); return ACM_ERR_FOCAL_LENGTH; }
+    if (!isfinite(p[2]) || !isfinite(p[3])) { put_msg(msg, msg_len, "Principal point must be finite"); return ACM_ERR_PRINCIPAL_POINT; }
+    char buf[128];
+    switch (cam->model) {
+        case ACM_MODEL_UCM:  // ucm.rs:467-477
+            if (!isfinite(p[4])) { put_msg(msg, msg_len, "alpha must be finite"); return ACM_ERR_INVALID_PARAMS; }
+            break;
+        case ACM_MODEL_EUCM:  // eucm.rs:501-517
+            if (!isfinite(p[4])) { put_msg(msg, msg_len, "alpha must be finite"); return ACM_ERR_INVALID_PARAMS; }
+            if (!isfinite(p[5])) { put_msg(msg, msg_len, "beta must be finite"); return ACM_ERR_INVALID_PARAMS; }
+            break;
+        case ACM_MODEL_DOUBLE_SPHERE:  // double_sphere.rs:592-608
+            if (p[4] <= 0.0 || p[4] > 1.0) { put_msg(msg, msg_len, "alpha must be in (0, 1]"); return ACM_ERR_INVALID_PARAMS; }
+            if (!isfinite(p[5])) { put_msg(msg, msg_len, "xi must be finite"); return ACM_ERR_INVALID_PARAMS; }
+            break;
+        case ACM_MODEL_FOV:  // fov.rs:457-468
+            if (!isfinite(p[4]) || p[4] <= 2.220446049250313e-16 || p[4] > 3.0) {
+                snprintf(buf, sizeof(buf), "w must be in range (epsilon, 3.0], got %g", p[4]);
+                put_msg(msg, msg_len, buf);
+                return ACM_ERR_INVALID_PARAMS;
+            }
+            break;
+        default: break;  // pinhole / rad_tan / kannala_brandt: intrinsics only
+    }
+    return ACM_OK;
+}
+
+extern "C" int32_t acm_camera_new(int32_t model, const double* params, size_t n, acm_camera* out, char* msg, size_t msg_len) {
+    put_msg(msg, msg_len, "");
+    if (!out || model < 0 || model > 6 || (!params && n)) { put_msg(msg, msg_len, "invalid argument"); return ACM_ERR_INVALID_ARG; }
+    if ((int)n != kNParams[model]) {
+        char buf[128];
+        snprintf(buf, sizeof(buf), kExpect[model], n);
+        put_msg(msg, msg_len, buf);
+        return ACM_ERR_INVALID_PARAMS;
+    }
+    memset(out, 0, sizeof(*out));
+    out->model = model; out->width = 0; out->height = 0; out->n_params = (int32_t)n;
+    for (size_t i = 0; i < n; ++i) out->params[i] = params[i];
+    // only Pinhole and RadTan validate inside `new` (pinhole.rs:101, rad_tan.rs:135)
+    if (model == ACM_MODEL_PINHOLE || model == ACM_MODEL_RADTAN) return acm_validate_params(out, msg, msg_len);
+    return ACM_OK;
+}
+
+int32_t acm_make_cam_params(acm_ctx* ctx, const acm_camera* cam, CamParams* c) {
+    if (!cam || cam->model < 0 || cam->model > 6) return acm_fail(ctx, ACM_ERR_INVALID_ARG, "invalid camera model id");
+    if (cam->n_params != kNParams[cam->model])
+        return acm_fail(ctx, ACM_ERR_INVALID_PARAMS, "model %d expects %d parameters, got %d", cam->model, kNParams[cam->model], cam->n_params);
+    memset(c, 0, sizeof(*c));
+    c->fx = cam->params[0]; c->fy = cam->params[1]; c->cx = cam->params[2]; c->cy = cam->params[3];
+    for (int i = 4; i < cam->n_params; ++i) c->d[i - 4] = cam->params[i];
+    c->W = (double)cam->width; c->H = (double)cam->height;
+    c->has_resolution = (cam->width > 0 && cam->height > 0) ? 1 : 0;
+    c->model = cam->model;
+    // per-model constants, in the reference's operation order (volatile: no host-side contraction)
+    volatile double alpha = c->d[0];
+    switch (cam->model) {
+        case ACM_MODEL_UCM: {  // ucm.rs:154-161, :177-184, :346-347
+            volatile double gamma = 1.0 - alpha;
+            c->k0 = (alpha <= 0.5) ? alpha / (1.0 - alpha) : (1.0 - alpha) / alpha;
+            volatile double g2 = gamma * gamma;
+            volatile double den = 2.0 * alpha - 1.0;
+            c->k1 = g2 / den;
+            c->k2 = alpha / gamma;
+            break;
+        }
+        case ACM_MODEL_EUCM: {  // eucm.rs:171, :196
+            volatile double beta = c->d[1];
+            volatile double t = 2.0 * alpha - 1.0;
+            c->k0 = (alpha - 1.0) / t;
+            volatile double ib = 1.0 / beta;
+            c->k1 = ib * t;
+            break;
+        }
+        case ACM_MODEL_DOUBLE_SPHERE: {  // double_sphere.rs:177-184, :204
+            volatile double xi = c->d[1];
+            volatile double w1 = (alpha <= 0.5) ? alpha / (1.0 - alpha) : (1.0 - alpha) / alpha;
+            volatile double a = 2.0 * w1;
+            volatile double b = a * xi;
+            volatile double cc = xi * xi;
+            volatile double s = b + cc;
+            volatile double s1 = s + 1.0;
+            c->k0 = (w1 + xi) / sqrt(s1);
+            volatile double t = 2.0 * alpha - 1.0;
+            c->k1 = 1.0 / t;
+            break;
+        }
+        case ACM_MODEL_FOV: {  // fov.rs:296, :340
+            c->k0 = tan(c->d[0] / 2.0);
+            break;
+        }
+        default: break;
+    }
+    return ACM_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// raw memory
+// ---------------------------------------------------------------------------------------
+extern "C" int32_t acm_device_alloc(acm_ctx* ctx, size_t bytes, void** out) {
+    if (!ctx || !out) return ACM_ERR_INVALID_ARG;
+    ACM_CUDA(ctx, cudaSetDevice(ctx->device));
+    ACM_CUDA(ctx, cudaMalloc(out, bytes ? bytes : 1));
+    return ACM_OK;
+}
+extern "C" int32_t acm_device_free(acm_ctx* ctx, void* p) {
+    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_CUDA(ctx, cudaFree(p));
+    return ACM_OK;
+}
+extern "C" int32_t acm_host_alloc_pinned(acm_ctx* ctx, size_t bytes, void** out) {
+    if (!ctx || !out) return ACM_ERR_INVALID_ARG;
+    ACM_CUDA(ctx, cudaSetDevice(ctx->device));
+    ACM_CUDA(ctx, cudaMallocHost(out, bytes ? bytes : 1));
+    return ACM_OK;
+}
+extern "C" int32_t acm_host_free_pinned(acm_ctx* ctx, void* p) {
+    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_CUDA(ctx, cudaFreeHost(p));
+    return ACM_OK;
+}
+extern "C" int32_t acm_memcpy_h2d(acm_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return ACM_OK;
+}
+extern "C" int32_t acm_memcpy_d2h(acm_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return ACM_OK;
+}
+extern "C" int32_t acm_memset_d(acm_ctx* ctx, void* dst, int value, size_t bytes) {
+    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_CUDA(ctx, cudaMemsetAsync(dst, value, bytes, ctx->stream));
+    return ACM_OK;
+}
+
+int32_t acm_ensure_stage(acm_ctx* ctx, size_t bytes) {
+    if (ctx->stage_cap >= bytes) return ACM_OK;
+    ACM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ACM_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    for (int i = 0; i < 2; ++i) { cudaFree(ctx->d_stage[i]); ctx->d_stage[i] = nullptr; }
+    ctx->stage_cap = 0;
+    for (int i = 0; i < 2; ++i) ACM_CUDA(ctx, cudaMalloc(&ctx->d_stage[i], bytes));
+    ctx->stage_cap = bytes;
+    return ACM_OK;
+}
+
+int32_t acm_ensure_host_stage(acm_ctx* ctx, size_t bytes) {
+    if (ctx->h_stage_cap >= bytes) return ACM_OK;
+    ACM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFreeHost(ctx->h_stage); ctx->h_stage = nullptr; ctx->h_stage_cap = 0;
+    ACM_CUDA(ctx, cudaMallocHost(&ctx->h_stage, bytes));
+    ctx->h_stage_cap = bytes;
+    return ACM_OK;
+}
+
+int32_t acm_ensure_partials(acm_ctx* ctx, size_t doubles) {
+    if (ctx->partials_cap >= doubles) return ACM_OK;
+    ACM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->d_partials); ctx->d_partials = nullptr; ctx->partials_cap = 0;
+    ACM_CUDA(ctx, cudaMalloc(&ctx->d_partials, doubles * sizeof(double)));
+    ctx->partials_cap = doubles;
+    return ACM_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// point buffers
+// ---------------------------------------------------------------------------------------
+extern "C" int32_t acm_points_create(acm_ctx* ctx, int32_t dim, size_t n, int32_t dtype, acm_points** out) {
+    if (!ctx || !out) return ACM_ERR_INVALID_ARG;
+    *out = nullptr;
+    ACM_REQUIRE(ctx, dim == 2 || dim == 3, "points: dim must be 2 or 3");
+    ACM_REQUIRE(ctx, dtype == ACM_F64 || dtype == ACM_F32, "points: dtype must be ACM_F64 or ACM_F32");
+    acm_points* p = new (std::nothrow) acm_points();
+    if (!p) return acm_fail(ctx, ACM_ERR_INVALID_ARG, "out of host memory");
+    size_t es = dtype == ACM_F64 ? 8 : 4;
+    p->dim = dim; p->dtype = dtype; p->n = n;
+    p->stride_bytes = ((n * es + 255) / 256) * 256;
+    if (p->stride_bytes == 0) p->stride_bytes = 256;
+    p->base = nullptr;
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e == cudaSuccess) e = cudaMalloc(&p->base, p->stride_bytes * (size_t)dim);
+    if (e != cudaSuccess) { delete p; return acm_fail(ctx, ACM_ERR_CUDA, "cudaMalloc of %zu bytes failed: %s", p->stride_bytes * (size_t)dim, cudaGetErrorString(e)); }
+    *out = p;
+    return ACM_OK;
+}
+
+extern "C" int32_t acm_points_destroy(acm_ctx* ctx, acm_points* p) {
+    if (!p) return ACM_OK;
+    if (ctx) cudaStreamSynchronize(ctx->stream);
+    cudaFree(p->base);
+    delete p;
+    return ACM_OK;
+}
+extern "C" size_t acm_points_len(const acm_points* p) { return p ? p->n : 0; }
+extern "C" int32_t acm_points_dim(const acm_points* p) { return p ? p->dim : 0; }
+extern "C" int32_t acm_points_dtype(const acm_points* p) { return p ? p->dtype : -1; }
+extern "C" void* acm_points_component(const acm_points* p, int32_t c) {
+    if (!p || c < 0 || c >= p->dim) return nullptr;
+    return static_cast<char*>(p->base) + (size_t)c * p->stride_bytes;
+}
+
+// AoS (xyzxyz...) f64 staging -> SoA components of type T.  A block stages 256 points through
+// shared memory so that both the global read and the global writes are fully coalesced.
+template <int DIM, typename T>
+__global__ void __launch_bounds__(256) aos_to_soa_kernel(const double* __restrict__ aos, T* __restrict__ c0, T* __restrict__ c1,
+                                                         T* __restrict__ c2, size_t n) {
+    __shared__ double tile[256 * DIM];
+    const size_t nblk = (n + 255) / 256;
+    for (size_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const size_t base = blk * 256;
+        const size_t cnt = (n - base < 256) ? n - base : 256;
+        for (size_t j = threadIdx.x; j < cnt * DIM; j += 256) tile[j] = __ldcs(aos + base * DIM + j);
+        __syncthreads();
+        if (threadIdx.x < cnt) {
+            c0[base + threadIdx.x] = (T)tile[threadIdx.x * DIM];
+            c1[base + threadIdx.x] = (T)tile[threadIdx.x * DIM + 1];
+            if (DIM == 3) c2[base + threadIdx.x] = (T)tile[threadIdx.x * DIM + 2];
+        }
+        __syncthreads();
+    }
+}
+
+template <int DIM, typename T>
+__global__ void __launch_bounds__(256) soa_to_aos_kernel(const T* __restrict__ c0, const T* __restrict__ c1, const T* __restrict__ c2,
+                                                         double* __restrict__ aos, size_t n) {
+    __shared__ double tile[256 * DIM];
+    const size_t nblk = (n + 255) / 256;
+    for (size_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const size_t base = blk * 256;
+        const size_t cnt = (n - base < 256) ? n - base : 256;
+        if (threadIdx.x < cnt) {
+            tile[threadIdx.x * DIM] = (double)c0[base + threadIdx.x];
+            tile[threadIdx.x * DIM + 1] = (double)c1[base + threadIdx.x];
+            if (DIM == 3) tile[threadIdx.x * DIM + 2] = (double)c2[base + threadIdx.x];
+        }
+        __syncthreads();
+        for (size_t j = threadIdx.x; j < cnt * DIM; j += 256) aos[base * DIM + j] = tile[j];
+        __syncthreads();
+    }
+}
+
+template <typename T>
+static void launch_a2s(acm_ctx* ctx, const acm_points* p, const double* d_aos, size_t off, size_t cnt) {
+    int grid = grid_for(ctx, cnt, 256, 8);
+    T* c0 = comp<T>(p, 0) + off; T* c1 = comp<T>(p, 1) + off; T* c2 = p->dim == 3 ? comp<T>(p, 2) + off : nullptr;
+    if (p->dim == 3) aos_to_soa_kernel<3, T><<<grid, 256, 0, ctx->stream>>>(d_aos, c0, c1, c2, cnt);
+    else aos_to_soa_kernel<2, T><<<grid, 256, 0, ctx->stream>>>(d_aos, c0, c1, c2, cnt);
+}
+template <typename T>
+static void launch_s2a(acm_ctx* ctx, const acm_points* p, double* d_aos, size_t off, size_t cnt) {
+    int grid = grid_for(ctx, cnt, 256, 8);
+    const T* c0 = comp<T>(p, 0) + off; const T* c1 = comp<T>(p, 1) + off; const T* c2 = p->dim == 3 ? comp<T>(p, 2) + off : nullptr;
+    if (p->dim == 3) soa_to_aos_kernel<3, T><<<grid, 256, 0, ctx->stream>>>(c0, c1, c2, d_aos, cnt);
+    else soa_to_aos_kernel<2, T><<<grid, 256, 0, ctx->stream>>>(c0, c1, c2, d_aos, cnt);
+}
+
+static const size_t kChunkPoints = (size_t)4 << 20;  // 4 Mi points per staged chunk (96 MiB for xyz)
+
+// Chunked, double-buffered: H2D of chunk k+1 (copy stream) overlaps the AoS->SoA kernel of
+// chunk k (compute stream).  Asynchronous w.r.t. the host only when the source is pinned.
+int32_t acm_points_upload_any(acm_ctx* ctx, acm_points* p, const double* host_aos, size_t n, size_t dst_offset) {
+    ACM_REQUIRE(ctx, p && (host_aos || n == 0), "upload: null argument");
+    ACM_REQUIRE(ctx, dst_offset + n <= p->n, "upload: more points than the buffer holds");
+    if (n == 0) return ACM_OK;
+    const size_t dim = (size_t)p->dim;
+    const size_t chunk = n < kChunkPoints ? n : kChunkPoints;
+    int32_t rc = acm_ensure_stage(ctx, chunk * 3 * sizeof(double));
+    if (rc) return rc;
+    // staging buffers may still be read by kernels enqueued earlier on the compute stream
+    ACM_CUDA(ctx, cudaEventRecord(ctx->chunk_ev[2], ctx->stream));
+    ACM_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[2], 0));
+    size_t done = 0; int k = 0;
+    while (done < n) {
+        size_t cnt = (n - done < chunk) ? n - done : chunk;
+        int b = k & 1;
+        if (k >= 2) ACM_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[2 + b], 0));  // kernel of chunk k-2 done
+        ACM_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage[b], host_aos + done * dim, cnt * dim * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_stream));
+        ACM_CUDA(ctx, cudaEventRecord(ctx->chunk_ev[b], ctx->copy_stream));
+        ACM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[b], 0));
+        if (p->dtype == ACM_F64) launch_a2s<double>(ctx, p, (const double*)ctx->d_stage[b], dst_offset + done, cnt);
+        else launch_a2s<float>(ctx, p, (const double*)ctx->d_stage[b], dst_offset + done, cnt);
+        ACM_CHECK_LAUNCH(ctx);
+        ACM_CUDA(ctx, cudaEventRecord(ctx->chunk_ev[2 + b], ctx->stream));
+        done += cnt; ++k;
+    }
+    return ACM_OK;
+}
+
+extern "C" int32_t acm_points_upload_aos_f64(acm_ctx* ctx, acm_points* p, const double* host_aos, size_t n) {
+    if (!ctx) return ACM_ERR_INVALID_ARG;
+    return acm_points_upload_any(ctx, p, host_aos, n, 0);
+}
+
+extern "C" int32_t acm_points_download_aos_f64(acm_ctx* ctx, const acm_points* p, double* host_aos, size_t n) {
+    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_REQUIRE(ctx, p && (host_aos || n == 0), "download: null argument");
+    ACM_REQUIRE(ctx, n <= p->n, "download: more points than the buffer holds");
+    if (n == 0) return ACM_OK;
+    const size_t dim = (size_t)p->dim;
+    const size_t chunk = n < kChunkPoints ? n : kChunkPoints;
+    int32_t rc = acm_ensure_stage(ctx, chunk * 3 * sizeof(double));
+    if (rc) return rc;
+    size_t done = 0;
+    while (done < n) {  // simple: kernel then copy on the same stream
+        size_t cnt = (n - done < chunk) ? n - done : chunk;
+        if (p->dtype == ACM_F64) launch_s2a<double>(ctx, p, (double*)ctx->d_stage[0], done, cnt);
+        else launch_s2a<float>(ctx, p, (double*)ctx->d_stage[0], done, cnt);
+        ACM_CHECK_LAUNCH(ctx);
+        ACM_CUDA(ctx, cudaMemcpyAsync(host_aos + done * dim, ctx->d_stage[0], cnt * dim * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        done += cnt;
+    }
+    ACM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ACM_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// host-buffer project / unproject (what `CameraModel::project` over nalgebra data binds)
+// ---------------------------------------------------------------------------------------
+static int32_t host_map(acm_ctx* ctx, const acm_camera* cam, const double* in_aos, size_t n, double* out_aos, uint8_t* status, bool is_project) {
+    ACM_REQUIRE(ctx, cam && (n == 0 || (in_aos && out_aos)), "host map: null argument");
+    if (n == 0) return ACM_OK;
+    acm_points *in = nullptr, *out = nullptr;
+    uint8_t* d_st = nullptr;
+    int32_t rc = acm_points_create(ctx, is_project ? 3 : 2, n, ACM_F64, &in);
+    if (!rc) rc = acm_points_create(ctx, is_project ? 2 : 3, n, ACM_F64, &out);
+    if (!rc && cudaMalloc(&d_st, n) != cudaSuccess) rc = acm_fail(ctx, ACM_ERR_CUDA, "cudaMalloc status failed");
+    if (!rc) rc = acm_points_upload_aos_f64(ctx, in, in_aos, n);
+    if (!rc) rc = is_project ? acm_project(ctx, cam, in, out, d_st) : acm_unproject(ctx, cam, in, out, d_st);
+    if (!rc) rc = acm_points_download_aos_f64(ctx, out, out_aos, n);
+    if (!rc && status) {
+        cudaError_t e = cudaMemcpyAsync(status, d_st, n, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = acm_fail(ctx, ACM_ERR_CUDA, "status download failed: %s", cudaGetErrorString(e));
+    }
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_st);
+    acm_points_destroy(ctx, in);
+    acm_points_destroy(ctx, out);
+    return rc;
+}
+
+extern "C" int32_t acm_project_host(acm_ctx* ctx, const acm_camera* cam, const double* xyz_aos, size_t n, double* uv_aos, uint8_t* status) {
+    if (!ctx) return ACM_ERR_INVALID_ARG;
+    return host_map(ctx, cam, xyz_aos, n, uv_aos, status, true);
+}
+extern "C" int32_t acm_unproject_host(acm_ctx* ctx, const acm_camera* cam, const double* uv_aos, size_t n, double* xyz_aos, uint8_t* status) {
+    if (!ctx) return ACM_ERR_INVALID_ARG;
+    return host_map(ctx, cam, uv_aos, n, xyz_aos, status, false);
+}
+
+extern "C" int32_t acm_undistort_rgb8_host(acm_ctx* ctx, const acm_camera* cam, const double* target_intrinsics, const uint8_t* frames_in,
+                                           uint8_t* frames_out, size_t n_frames, int32_t interpolation) {
+    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_REQUIRE(ctx, cam && (n_frames == 0 || (frames_in && frames_out)), "undistort_host: null argument");
+    if (n_frames == 0) return ACM_OK;
+    size_t fb = (size_t)cam->width * cam->height * 3;
+    uint8_t *d_in = nullptr, *d_out = nullptr;
+    ACM_CUDA(ctx, cudaMalloc(&d_in, fb * n_frames));
+    if (cudaMalloc(&d_out, fb * n_frames) != cudaSuccess) { cudaFree(d_in); return acm_fail(ctx, ACM_ERR_CUDA, "cudaMalloc failed"); }
+    int32_t rc = ACM_OK;
+    cudaError_t e = cudaMemcpyAsync(d_in, frames_in, fb * n_frames, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) rc = acm_fail(ctx, ACM_ERR_CUDA, "H2D failed: %s", cudaGetErrorString(e));
+    if (!rc) rc = acm_undistort_rgb8(ctx, cam, target_intrinsics, d_in, d_out, n_frames, interpolation);
+    if (!rc) {
+        e = cudaMemcpyAsync(frames_out, d_out, fb * n_frames, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = acm_fail(ctx, ACM_ERR_CUDA, "D2H failed: %s", cudaGetErrorString(e));
+    }
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_in); cudaFree(d_out);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------
+// NCCL (loaded at run time so that single-GPU use has no NCCL dependency)
+// ---------------------------------------------------------------------------------------
+struct NcclId { char internal[128]; };
+struct NcclApi {
+    void* handle;
+    int (*GetUniqueId)(void*);
+    int (*CommInitRank)(void**, int, /*ncclUniqueId by value*/ NcclId, int);
+    int (*CommDestroy)(void*);
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+    const char* (*GetErrorString)(int);
+};
+static NcclApi g_nccl = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+
+static int32_t load_nccl(acm_ctx* ctx) {
+    if (g_nccl.handle) return ACM_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so", "/usr/lib/x86_64-linux-gnu/libnccl.so.2"};
+    void* h = nullptr;
+    const char* env = getenv("ACM_NCCL_LIB");
+    if (env) h = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+    for (int i = 0; !h && i < 3; ++i) h = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return acm_fail(ctx, ACM_ERR_NCCL, "cannot load libnccl.so.2: %s", dlerror());
+    g_nccl.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(h, "ncclCommInitRank");
+    g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+    g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce)
+        return acm_fail(ctx, ACM_ERR_NCCL, "libnccl is missing a required symbol");
+    g_nccl.handle = h;
+    return ACM_OK;
+}
+
+static const char* nccl_err(int r) { return g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "nccl error"; }
+
+extern "C" int32_t acm_comm_get_unique_id(uint8_t id[128]) {
+    if (!id) return ACM_ERR_INVALID_ARG;
+    int32_t rc = load_nccl(nullptr);
+    if (rc) return rc;
+    int r = g_nccl.GetUniqueId(id);
+    if (r != 0) return acm_fail(nullptr, ACM_ERR_NCCL, "ncclGetUniqueId: %s", nccl_err(r));
+    return ACM_OK;
+}
+
+extern "C" int32_t acm_comm_init_rank(acm_ctx* ctx, int32_t n_ranks, int32_t rank, const uint8_t id[128]) {
+    if (!ctx || !id) return ACM_ERR_INVALID_ARG;
+    ACM_REQUIRE(ctx, n_ranks >= 1 && rank >= 0 && rank < n_ranks, "comm_init_rank: bad rank / size");
+    ACM_REQUIRE(ctx, ctx->comm == nullptr, "comm_init_rank: communicator already attached");
+    int32_t rc = load_nccl(ctx);
+    if (rc) return rc;
+    ACM_CUDA(ctx, cudaSetDevice(ctx->device));
+    NcclId nid;
+    memcpy(nid.internal, id, 128);
+    void* comm = nullptr;
+    int r = g_nccl.CommInitRank(&comm, n_ranks, nid, rank);
+    if (r != 0) return acm_fail(ctx, ACM_ERR_NCCL, "ncclCommInitRank: %s", nccl_err(r));
+    ctx->comm = comm; ctx->n_ranks = n_ranks; ctx->rank = rank;
+    return ACM_OK;
+}
+
+extern "C" int32_t acm_comm_destroy(acm_ctx* ctx) {
+    if (!ctx) return ACM_ERR_INVALID_ARG;
+    if (ctx->comm && g_nccl.CommDestroy) { cudaStreamSynchronize(ctx->stream); g_nccl.CommDestroy(ctx->comm); }
+    ctx->comm = nullptr; ctx->n_ranks = 1; ctx->rank = 0;
+    return ACM_OK;
+}
+
+extern "C" int32_t acm_comm_size(const acm_ctx* ctx) { return ctx ? ctx->n_ranks : 0; }
+
+// Sum a small f64 vector over all ranks on the compute stream (no-op without a communicator).
+int32_t acm_allreduce_sum_f64(acm_ctx* ctx, double* d_buf, size_t count) {
+    if (!ctx->comm || ctx->n_ranks == 1) return ACM_OK;
+    int r = g_nccl.AllReduce(d_buf, d_buf, count, /*ncclFloat64*/ 8, /*ncclSum*/ 0, ctx->comm, ctx->stream);
+    if (r != 0) return acm_fail(ctx, ACM_ERR_NCCL, "ncclAllReduce: %s", nccl_err(r));
+    return ACM_OK;
+}

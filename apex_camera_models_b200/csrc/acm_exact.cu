@@ -1,0 +1,441 @@
+// Batched project / unproject / undistort / synthetic-input kernels.
+// Compiled with -fmad=false so that every +,-,*,/,sqrt is a separately rounded IEEE binary64
+// operation exactly as in the reference (Rust never fuses): status masks and remap indices
+// are bit-exact, f64 coordinates differ from the reference only through the <= 2 ulp device
+// atan2 / sin / cos.
+//
+// Data movement (HBM-bound kernels): SoA components, one 16-byte vector load per component
+// per thread (2 f64 or 4 f32 points), grid-stride loop over a grid of sm_count * k blocks.
+#include "acm_models.cuh"
+
+// ---------------------------------------------------------------------------------------
+// 16-byte packets of points
+// ---------------------------------------------------------------------------------------
+template <typename T> struct Vec;
+template <> struct Vec<double> {
+    static constexpr int N = 2;
+    using type = double2;
+    static __device__ __forceinline__ void unpack(const double2& v, double* o) { o[0] = v.x; o[1] = v.y; }
+    static __device__ __forceinline__ double2 pack(const double* o) { return make_double2(o[0], o[1]); }
+};
+template <> struct Vec<float> {
+    static constexpr int N = 4;
+    using type = float4;
+    static __device__ __forceinline__ void unpack(const float4& v, double* o) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+    static __device__ __forceinline__ float4 pack(const double* o) { return make_float4((float)o[0], (float)o[1], (float)o[2], (float)o[3]); }
+};
+
+template <typename V> __device__ __forceinline__ V ld_stream(const V* p) { return __ldcs(p); }
+template <typename V> __device__ __forceinline__ void st_stream(V* p, const V& v) { __stcs(p, v); }
+
+template <int NV> struct StatusVec;
+template <> struct StatusVec<2> {
+    static __device__ __forceinline__ void store(uint8_t* p, const int* s) {
+        __stcs(reinterpret_cast<uchar2*>(p), make_uchar2((uint8_t)s[0], (uint8_t)s[1]));
+    }
+};
+template <> struct StatusVec<4> {
+    static __device__ __forceinline__ void store(uint8_t* p, const int* s) {
+        __stcs(reinterpret_cast<uchar4*>(p), make_uchar4((uint8_t)s[0], (uint8_t)s[1], (uint8_t)s[2], (uint8_t)s[3]));
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// project: xyz -> uv + status
+// ---------------------------------------------------------------------------------------
+template <int M, typename T, bool BOUNDS>
+__global__ void __launch_bounds__(256) project_kernel(const __grid_constant__ CamParams c, const T* __restrict__ X,
+                                                      const T* __restrict__ Y, const T* __restrict__ Z, T* __restrict__ U,
+                                                      T* __restrict__ V, uint8_t* __restrict__ S, size_t n) {
+    using VT = typename Vec<T>::type;
+    constexpr int NV = Vec<T>::N;
+    const size_t npk = n / NV;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npk; p += stride) {
+        double x[NV], y[NV], z[NV], u[NV], v[NV];
+        int s[NV];
+        Vec<T>::unpack(ld_stream(reinterpret_cast<const VT*>(X) + p), x);
+        Vec<T>::unpack(ld_stream(reinterpret_cast<const VT*>(Y) + p), y);
+        Vec<T>::unpack(ld_stream(reinterpret_cast<const VT*>(Z) + p), z);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            u[k] = v[k] = acm_nan();
+            double uu, vv;
+            s[k] = CamModel<M>::template project<BOUNDS>(c, x[k], y[k], z[k], uu, vv);
+            if (s[k] == ACM_POINT_OK) { u[k] = uu; v[k] = vv; }
+        }
+        st_stream(reinterpret_cast<VT*>(U) + p, Vec<T>::pack(u));
+        st_stream(reinterpret_cast<VT*>(V) + p, Vec<T>::pack(v));
+        if (S) StatusVec<NV>::store(S + p * NV, s);
+    }
+    // ragged tail (n not a multiple of the packet width)
+    const size_t t = npk * NV + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) {
+        double uu, vv;
+        int st = CamModel<M>::template project<BOUNDS>(c, (double)X[t], (double)Y[t], (double)Z[t], uu, vv);
+        if (st != ACM_POINT_OK) uu = vv = acm_nan();
+        U[t] = (T)uu; V[t] = (T)vv;
+        if (S) S[t] = (uint8_t)st;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// unproject: uv -> ray + status
+// ---------------------------------------------------------------------------------------
+template <int M, typename T>
+__global__ void __launch_bounds__(256) unproject_kernel(const __grid_constant__ CamParams c, const T* __restrict__ U,
+                                                        const T* __restrict__ V, T* __restrict__ X, T* __restrict__ Y,
+                                                        T* __restrict__ Z, uint8_t* __restrict__ S, size_t n) {
+    using VT = typename Vec<T>::type;
+    constexpr int NV = Vec<T>::N;
+    const size_t npk = n / NV;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npk; p += stride) {
+        double u[NV], v[NV], x[NV], y[NV], z[NV];
+        int s[NV];
+        Vec<T>::unpack(ld_stream(reinterpret_cast<const VT*>(U) + p), u);
+        Vec<T>::unpack(ld_stream(reinterpret_cast<const VT*>(V) + p), v);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            x[k] = y[k] = z[k] = acm_nan();
+            double rx, ry, rz;
+            s[k] = CamModel<M>::unproject(c, u[k], v[k], rx, ry, rz);
+            if (s[k] == ACM_POINT_OK) { x[k] = rx; y[k] = ry; z[k] = rz; }
+        }
+        st_stream(reinterpret_cast<VT*>(X) + p, Vec<T>::pack(x));
+        st_stream(reinterpret_cast<VT*>(Y) + p, Vec<T>::pack(y));
+        st_stream(reinterpret_cast<VT*>(Z) + p, Vec<T>::pack(z));
+        if (S) StatusVec<NV>::store(S + p * NV, s);
+    }
+    const size_t t = npk * NV + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) {
+        double rx, ry, rz;
+        int st = CamModel<M>::unproject(c, (double)U[t], (double)V[t], rx, ry, rz);
+        if (st != ACM_POINT_OK) rx = ry = rz = acm_nan();
+        X[t] = (T)rx; Y[t] = (T)ry; Z[t] = (T)rz;
+        if (S) S[t] = (uint8_t)st;
+    }
+}
+
+template <int M, typename T>
+static int32_t launch_project(acm_ctx* ctx, const CamParams& c, const acm_points* xyz, acm_points* uv, uint8_t* st) {
+    const size_t n = xyz->n;
+    if (n == 0) return ACM_OK;
+    constexpr int NV = Vec<T>::N;
+    int grid = grid_for(ctx, n / NV + NV, 256, 8);
+    project_kernel<M, T, true><<<grid, 256, 0, ctx->stream>>>(c, comp<T>(xyz, 0), comp<T>(xyz, 1), comp<T>(xyz, 2),
+                                                                comp<T>(uv, 0), comp<T>(uv, 1), st, n);
+    ACM_CHECK_LAUNCH(ctx);
+    return ACM_OK;
+}
+
+template <int M, typename T>
+static int32_t launch_unproject(acm_ctx* ctx, const CamParams& c, const acm_points* uv, acm_points* xyz, uint8_t* st) {
+    const size_t n = uv->n;
+    if (n == 0) return ACM_OK;
+    constexpr int NV = Vec<T>::N;
+    int grid = grid_for(ctx, n / NV + NV, 256, 8);
+    unproject_kernel<M, T><<<grid, 256, 0, ctx->stream>>>(c, comp<T>(uv, 0), comp<T>(uv, 1), comp<T>(xyz, 0),
+                                                           comp<T>(xyz, 1), comp<T>(xyz, 2), st, n);
+    ACM_CHECK_LAUNCH(ctx);
+    return ACM_OK;
+}
+
+extern "C" int32_t acm_project(acm_ctx* ctx, const acm_camera* cam, const acm_points* xyz, acm_points* uv, uint8_t* d_status) {
+    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_REQUIRE(ctx, cam && xyz && uv, "acm_project: null argument");
+    ACM_REQUIRE(ctx, xyz->dim == 3 && uv->dim == 2, "acm_project: xyz must have dim 3 and uv dim 2");
+    ACM_REQUIRE(ctx, xyz->n == uv->n, "acm_project: point counts differ");
+    ACM_REQUIRE(ctx, xyz->dtype == uv->dtype, "acm_project: dtypes of input and output differ");
+    CamParams c;
+    int32_t rc = acm_make_cam_params(ctx, cam, &c);
+    if (rc) return rc;
+    if (xyz->dtype == ACM_F64) { ACM_DISPATCH_MODEL(cam->model, return (launch_project<M, double>(ctx, c, xyz, uv, d_status))) }
+    else { ACM_DISPATCH_MODEL(cam->model, return (launch_project<M, float>(ctx, c, xyz, uv, d_status))) }
+    return ACM_OK;
+}
+
+extern "C" int32_t acm_unproject(acm_ctx* ctx, const acm_camera* cam, const acm_points* uv, acm_points* xyz, uint8_t* d_status) {
+    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_REQUIRE(ctx, cam && xyz && uv, "acm_unproject: null argument");
+    ACM_REQUIRE(ctx, xyz->dim == 3 && uv->dim == 2, "acm_unproject: xyz must have dim 3 and uv dim 2");
+    ACM_REQUIRE(ctx, xyz->n == uv->n, "acm_unproject: point counts differ");
+    ACM_REQUIRE(ctx, xyz->dtype == uv->dtype, "acm_unproject: dtypes of input and output differ");
+    CamParams c;
+    int32_t rc = acm_make_cam_params(ctx, cam, &c);
+    if (rc) return rc;
+    if (uv->dtype == ACM_F64) { ACM_DISPATCH_MODEL(cam->model, return (launch_unproject<M, double>(ctx, c, uv, xyz, d_status))) }
+    else { ACM_DISPATCH_MODEL(cam->model, return (launch_unproject<M, float>(ctx, c, uv, xyz, d_status))) }
+    return ACM_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// undistort_image: per output pixel  ray = ((u-cx_t)/fx_t, (v-cy_t)/fy_t, 1) -> project ->
+// bilinear / nearest sample (undistort.rs:33-46, :51-105).  One thread owns 4 horizontally
+// adjacent output pixels: it evaluates their source coordinates once, then loops over the
+// frames of the batch (the map is never stored), gathers the taps through the read-only
+// path and stages the 12 output bytes in shared memory so that the block writes the row
+// segment with 16-byte coalesced stores.
+// ---------------------------------------------------------------------------------------
+struct Tap {
+    int ok;        // sample exists
+    int off00;     // byte offset of p00 in a frame
+    double wx, wy; // bilinear weights (unused for nearest)
+};
+
+__device__ __forceinline__ Tap make_tap(double sx, double sy, int status, int W, int H, int interp) {
+    Tap t; t.ok = 0; t.off00 = 0; t.wx = 0.0; t.wy = 0.0;
+    if (status != ACM_POINT_OK) return t;
+    if (isnan(sx) || isnan(sy)) return t;
+    if (interp == ACM_INTERP_NEAREST) {
+        double rx = round(sx), ry = round(sy);
+        // `as i32` saturates; anything outside [0,W) fails the guard either way
+        if (rx >= 0.0 && rx < (double)W && ry >= 0.0 && ry < (double)H) { t.ok = 1; t.off00 = 3 * ((int)ry * W + (int)rx); }
+        return t;
+    }
+    double x0 = floor(sx), y0 = floor(sy);
+    double x1 = x0 + 1.0, y1 = y0 + 1.0;
+    if (x0 < 0.0 || x1 >= (double)W || y0 < 0.0 || y1 >= (double)H) return t;
+    t.ok = 1;
+    t.off00 = 3 * ((int)y0 * W + (int)x0);
+    t.wx = sx - x0; t.wy = sy - y0;
+    return t;
+}
+
+__device__ __forceinline__ uint8_t blend(uint8_t p00, uint8_t p10, uint8_t p01, uint8_t p11, double wx, double wy, double wxi, double wyi) {
+    double val = (double)p00 * wxi * wyi + (double)p10 * wx * wyi + (double)p01 * wxi * wy + (double)p11 * wx * wy;
+    double r = round(val);  // f64::round: half away from zero
+    r = fmin(fmax(r, 0.0), 255.0);
+    return (uint8_t)r;
+}
+
+template <int M>
+__global__ void __launch_bounds__(256) undistort_kernel(const __grid_constant__ CamParams c, double tfx, double tfy, double tcx,
+                                                        double tcy, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
+                                                        int W, int H, size_t n_frames, int interp) {
+    // block = 256 threads x 4 pixels = 1024 pixels of one image row (W is padded by the guard)
+    __shared__ __align__(16) uint8_t sm[256 * 12];
+    const int row = blockIdx.y;
+    const int px0 = (blockIdx.x * 256 + threadIdx.x) * 4;
+    const size_t frame_bytes = (size_t)W * H * 3;
+    Tap taps[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int uo = px0 + k;
+        double sx = 0.0, sy = 0.0;
+        int st = ACM_POINT_IS_OUTSIDE_IMAGE;
+        if (uo < W) {
+            double xn = ((double)uo - tcx) / tfx;
+            double yn = ((double)row - tcy) / tfy;
+            st = CamModel<M>::template project<true>(c, xn, yn, 1.0, sx, sy);
+        }
+        taps[k] = make_tap(sx, sy, st, W, H, interp);
+    }
+    const int row_stride = 3 * W;
+    const int seg_px = min(1024, W - blockIdx.x * 1024);  // pixels of this block's segment
+    const int seg_bytes = seg_px * 3;
+    const size_t seg_off = ((size_t)row * W + (size_t)blockIdx.x * 1024) * 3;
+    const bool vec_ok = ((seg_off & 15) == 0) && ((frame_bytes & 15) == 0);
+    for (size_t f = 0; f < n_frames; ++f) {
+        const uint8_t* src = in + f * frame_bytes;
+        uint8_t o[12];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint8_t r = 0, g = 0, b = 0;
+            if (taps[k].ok) {
+                const uint8_t* p = src + taps[k].off00;
+                if (interp == ACM_INTERP_NEAREST) { r = __ldg(p); g = __ldg(p + 1); b = __ldg(p + 2); }
+                else {
+                    const uint8_t* q = p + row_stride;
+                    double wx = taps[k].wx, wy = taps[k].wy, wxi = 1.0 - wx, wyi = 1.0 - wy;
+                    r = blend(__ldg(p), __ldg(p + 3), __ldg(q), __ldg(q + 3), wx, wy, wxi, wyi);
+                    g = blend(__ldg(p + 1), __ldg(p + 4), __ldg(q + 1), __ldg(q + 4), wx, wy, wxi, wyi);
+                    b = blend(__ldg(p + 2), __ldg(p + 5), __ldg(q + 2), __ldg(q + 5), wx, wy, wxi, wyi);
+                }
+            }
+            o[3 * k] = r; o[3 * k + 1] = g; o[3 * k + 2] = b;
+        }
+        uint32_t* smw = reinterpret_cast<uint32_t*>(sm) + threadIdx.x * 3;
+        smw[0] = o[0] | (o[1] << 8) | (o[2] << 16) | ((uint32_t)o[3] << 24);
+        smw[1] = o[4] | (o[5] << 8) | (o[6] << 16) | ((uint32_t)o[7] << 24);
+        smw[2] = o[8] | (o[9] << 8) | (o[10] << 16) | ((uint32_t)o[11] << 24);
+        __syncthreads();
+        uint8_t* dst = out + f * frame_bytes + seg_off;
+        if (vec_ok) {
+            const int nvec = seg_bytes >> 4;
+            if ((int)threadIdx.x < nvec) __stcs(reinterpret_cast<uint4*>(dst) + threadIdx.x, reinterpret_cast<const uint4*>(sm)[threadIdx.x]);
+            for (int b = (nvec << 4) + threadIdx.x; b < seg_bytes; b += 256) dst[b] = sm[b];
+        } else {
+            for (int b = threadIdx.x; b < seg_bytes; b += 256) dst[b] = sm[b];
+        }
+        __syncthreads();
+    }
+}
+
+template <int M>
+__global__ void __launch_bounds__(256) undistort_map_kernel(const __grid_constant__ CamParams c, double tfx, double tfy, double tcx,
+                                                            double tcy, double* __restrict__ src_xy, int W, int H) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)W * H) return;
+    int uo = (int)(i % W), vo = (int)(i / W);
+    double xn = ((double)uo - tcx) / tfx, yn = ((double)vo - tcy) / tfy;
+    double sx, sy;
+    int st = CamModel<M>::template project<true>(c, xn, yn, 1.0, sx, sy);
+    if (st != ACM_POINT_OK) sx = sy = acm_nan();
+    reinterpret_cast<double2*>(src_xy)[i] = make_double2(sx, sy);
+}
+
+static int32_t check_undistort_args(acm_ctx* ctx, const acm_camera* cam, const double* target, double t[4]) {
+    ACM_REQUIRE(ctx, cam, "undistort: null camera");
+    ACM_REQUIRE(ctx, cam->width > 0 && cam->height > 0, "undistort: camera resolution must be set (image must match model resolution)");
+    ACM_REQUIRE(ctx, (uint64_t)cam->width * cam->height * 3 < 0x7fffffffULL, "undistort: frame larger than 2 GiB is not supported");
+    for (int i = 0; i < 4; ++i) t[i] = target ? target[i] : cam->params[i];
+    return ACM_OK;
+}
+
+extern "C" int32_t acm_undistort_rgb8(acm_ctx* ctx, const acm_camera* cam, const double* target_intrinsics, const uint8_t* d_in,
+                                      uint8_t* d_out, size_t n_frames, int32_t interpolation) {
+    if (!ctx) return ACM_ERR_INVALID_ARG;
+    double t[4];
+    int32_t rc = check_undistort_args(ctx, cam, target_intrinsics, t);
+    if (rc) return rc;
+    ACM_REQUIRE(ctx, d_in && d_out, "undistort: null frame buffer");
+    ACM_REQUIRE(ctx, interpolation == ACM_INTERP_NEAREST || interpolation == ACM_INTERP_BILINEAR, "undistort: unknown interpolation");
+    if (n_frames == 0) return ACM_OK;
+    CamParams c;
+    rc = acm_make_cam_params(ctx, cam, &c);
+    if (rc) return rc;
+    const int W = (int)cam->width, H = (int)cam->height;
+    dim3 grid((W + 1023) / 1024, H);
+    ACM_DISPATCH_MODEL(cam->model, (undistort_kernel<M><<<grid, 256, 0, ctx->stream>>>(c, t[0], t[1], t[2], t[3], d_in, d_out, W, H, n_frames, interpolation)))
+    ACM_CHECK_LAUNCH(ctx);
+    return ACM_OK;
+}
+
+extern "C" int32_t acm_undistort_map(acm_ctx* ctx, const acm_camera* cam, const double* target_intrinsics, double* d_src_xy) {
+    if (!ctx) return ACM_ERR_INVALID_ARG;
+    double t[4];
+    int32_t rc = check_undistort_args(ctx, cam, target_intrinsics, t);
+    if (rc) return rc;
+    ACM_REQUIRE(ctx, d_src_xy, "undistort_map: null output");
+    CamParams c;
+    rc = acm_make_cam_params(ctx, cam, &c);
+    if (rc) return rc;
+    const int W = (int)cam->width, H = (int)cam->height;
+    size_t n = (size_t)W * H;
+    int grid = (int)((n + 255) / 256);
+    ACM_DISPATCH_MODEL(cam->model, (undistort_map_kernel<M><<<grid, 256, 0, ctx->stream>>>(c, t[0], t[1], t[2], t[3], d_src_xy, W, H)))
+    ACM_CHECK_LAUNCH(ctx);
+    return ACM_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Synthetic inputs: counter-based splitmix64, transcendental-free so
+// that the host oracle reproduces them bit for bit.
+// ---------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    uint64_t z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ double unit01(uint64_t seed, uint64_t i, uint64_t k) {
+    return (double)(splitmix64(seed + 3ULL * i + k) >> 11) * 0x1.0p-53;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) synth_points3_kernel(uint64_t seed, uint64_t i0, double cos_max, int adversarial,
+                                                            T* __restrict__ X, T* __restrict__ Y, T* __restrict__ Z, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        uint64_t i = i0 + k;
+        double u0 = unit01(seed, i, 0), u1 = unit01(seed, i, 1), u2 = unit01(seed, i, 2);
+        double c = 1.0 - u0 * (1.0 - cos_max);
+        double s = sqrt((1.0 - c) * (1.0 + c));
+        double t = 4.0 * u1;
+        int q = (int)t;
+        double f = t - (double)q;
+        double a = 1.0 - f, b = f;
+        double nrm = sqrt(a * a + b * b);
+        a = a / nrm; b = b / nrm;
+        double ca, sa;
+        switch (q & 3) { case 0: ca = a; sa = b; break; case 1: ca = -b; sa = a; break; case 2: ca = -a; sa = -b; break; default: ca = b; sa = -a; break; }
+        double rho = 0.5 + 9.5 * u2;
+        double rs = rho * s;
+        double x = rs * ca, y = rs * sa, z = rho * c;
+        if (adversarial && (i & 63ULL) == 63ULL) {
+            switch ((i >> 6) % 6ULL) {
+                case 0: x = 0.0; y = 0.0; z = 0.0; break;
+                case 1: x = 0.1; y = 0.2; z = -1.0; break;
+                case 2: x = 0.0; y = 0.0; z = 1e-9; break;
+                case 3: x = 0.0; y = 0.0; z = 1.0; break;
+                case 4: x = 1e-3; y = 0.0; z = 0x1.0p-26; break;
+                default: x = 1e-3; y = 0.0; z = 0x1.fffffffffffffp-27; break;
+            }
+        }
+        X[k] = (T)x; Y[k] = (T)y; Z[k] = (T)z;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) synth_pixels_kernel(uint64_t seed, uint64_t i0, double W, double H, T* __restrict__ U,
+                                                           T* __restrict__ V, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        uint64_t i = i0 + k;
+        U[k] = (T)(W * unit01(seed, i, 0));
+        V[k] = (T)(H * unit01(seed, i, 1));
+    }
+}
+
+__global__ void __launch_bounds__(256) synth_bytes_kernel(uint64_t seed, uint64_t i0, uint8_t* __restrict__ out, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    // 4 bytes per thread-iteration when aligned
+    const size_t n4 = n / 4;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n4; k += stride) {
+        uint64_t i = i0 + 4 * k;
+        uint32_t w = (uint32_t)(splitmix64(seed + i) & 0xFF) | ((uint32_t)(splitmix64(seed + i + 1) & 0xFF) << 8) |
+                     ((uint32_t)(splitmix64(seed + i + 2) & 0xFF) << 16) | ((uint32_t)(splitmix64(seed + i + 3) & 0xFF) << 24);
+        reinterpret_cast<uint32_t*>(out)[k] = w;
+    }
+    size_t t = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) out[t] = (uint8_t)(splitmix64(seed + i0 + t) & 0xFF);
+}
+
+extern "C" int32_t acm_synth_points3(acm_ctx* ctx, uint64_t seed, size_t first_index, double cos_theta_max, int32_t adversarial, acm_points* xyz) {
+    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_REQUIRE(ctx, xyz && xyz->dim == 3, "synth_points3: need a dim-3 buffer");
+    if (xyz->n == 0) return ACM_OK;
+    int grid = grid_for(ctx, xyz->n, 256, 8);
+    if (xyz->dtype == ACM_F64)
+        synth_points3_kernel<double><<<grid, 256, 0, ctx->stream>>>(seed, first_index, cos_theta_max, adversarial, comp<double>(xyz, 0), comp<double>(xyz, 1), comp<double>(xyz, 2), xyz->n);
+    else
+        synth_points3_kernel<float><<<grid, 256, 0, ctx->stream>>>(seed, first_index, cos_theta_max, adversarial, comp<float>(xyz, 0), comp<float>(xyz, 1), comp<float>(xyz, 2), xyz->n);
+    ACM_CHECK_LAUNCH(ctx);
+    return ACM_OK;
+}
+
+extern "C" int32_t acm_synth_pixels(acm_ctx* ctx, uint64_t seed, size_t first_index, double width, double height, acm_points* uv) {
+    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_REQUIRE(ctx, uv && uv->dim == 2, "synth_pixels: need a dim-2 buffer");
+    if (uv->n == 0) return ACM_OK;
+    int grid = grid_for(ctx, uv->n, 256, 8);
+    if (uv->dtype == ACM_F64)
+        synth_pixels_kernel<double><<<grid, 256, 0, ctx->stream>>>(seed, first_index, width, height, comp<double>(uv, 0), comp<double>(uv, 1), uv->n);
+    else
+        synth_pixels_kernel<float><<<grid, 256, 0, ctx->stream>>>(seed, first_index, width, height, comp<float>(uv, 0), comp<float>(uv, 1), uv->n);
+    ACM_CHECK_LAUNCH(ctx);
+    return ACM_OK;
+}
+
+extern "C" int32_t acm_synth_bytes(acm_ctx* ctx, uint64_t seed, size_t first_index, uint8_t* d_out, size_t n) {
+    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_REQUIRE(ctx, d_out || n == 0, "synth_bytes: null output");
+    if (n == 0) return ACM_OK;
+    ACM_REQUIRE(ctx, ((uintptr_t)d_out & 3) == 0, "synth_bytes: output must be 4-byte aligned");
+    int grid = grid_for(ctx, n / 4 + 4, 256, 8);
+    synth_bytes_kernel<<<grid, 256, 0, ctx->stream>>>(seed, first_index, d_out, n);
+    ACM_CHECK_LAUNCH(ctx);
+    return ACM_OK;
+}

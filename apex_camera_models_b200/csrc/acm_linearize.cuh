@@ -1,0 +1,298 @@
+// Fused residual + analytic Jacobian + J^T J / J^T r accumulation (one streaming pass).
+//
+// This replaces `*CameraParamsFactor::linearize` + the solver's J^T J of apex-solver at the
+// call sites reference bin/camera_converter.rs:378-420 (and clones).  The Jacobian is never
+// materialised: every thread keeps the normal equations of its points in registers.
+//
+// Sparsity: the u-row touches only {fx, cx, dist..}, the v-row only
+// {fy, cy, dist..}.  Per row we therefore carry a short vector a = [a_f, a_c, a_d0, a_d1, ..].
+// For the PIXEL residual a_c == 1 exactly, so H[c,c] is the valid-point count and every
+// product with a_c is a plain add (UNIT_C = true).
+//
+// Accumulator layout (flat, all indices compile-time => registers):
+//   HFF[2]  H[fx,fx], H[fy,fy]          HFC[2]  H[fx,cx], H[fy,cy]      HCC[2] H[cx,cx], H[cy,cy]
+//   HFD[2][ND]  H[f*,d_k]               HCD[2][ND]  H[c*,d_k]           HDD[ND(ND+1)/2]
+//   GF[2] GC[2] GD[ND]   COST   COUNT
+#pragma once
+#include "acm_internal.cuh"
+
+#define LIN_EPS 2.220446049250313e-16
+#define LIN_SQRT_EPS 1.4901161193847656e-08
+#define LIN_PRECISION 1e-3
+
+template <int ND> struct AccLayout {
+    static constexpr int HFF = 0, HFC = 2, HCC = 4, HFD = 6, HCD = 6 + 2 * ND, HDD = 6 + 4 * ND;
+    static constexpr int GF = HDD + ND * (ND + 1) / 2, GC = GF + 2, GD = GC + 2, COST = GD + ND, COUNT = COST + 1;
+    static constexpr int N = COUNT + 1;
+    __host__ __device__ static constexpr int tri(int j, int k) { return j * ND - j * (j - 1) / 2 + (k - j); }  // j <= k
+};
+
+// Parameters as the kernels see them (plain doubles; derived constants recomputed on device
+// when the parameters come from the device-resident LM state).
+struct LinParams {
+    double fx, fy, cx, cy;
+    double d[5];
+    double k0;  // validity constant: UCM w, EUCM (a-1)/(2a-1), DS w2, FOV tan(w/2)
+};
+
+__host__ __device__ inline void lin_derive(int model, LinParams& p) {
+    const double alpha = p.d[0];
+    switch (model) {
+        case ACM_MODEL_UCM: p.k0 = (alpha <= 0.5) ? alpha / (1.0 - alpha) : (1.0 - alpha) / alpha; break;
+        case ACM_MODEL_EUCM: p.k0 = (alpha - 1.0) / (2.0 * alpha - 1.0); break;
+        case ACM_MODEL_DOUBLE_SPHERE: {
+            const double xi = p.d[1];
+            double w1 = (alpha <= 0.5) ? alpha / (1.0 - alpha) : (1.0 - alpha) / alpha;
+            p.k0 = (w1 + xi) / sqrt(2.0 * w1 * xi + xi * xi + 1.0);
+            break;
+        }
+        case ACM_MODEL_FOV: p.k0 = tan(p.d[0] / 2.0); break;
+        default: p.k0 = 0.0; break;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Per-model residual + Jacobian rows.  eval() returns validity (the model's geometric test,
+// no image-bounds test: the factor has no resolution) and fills
+//   ru, rv            residuals
+//   au[2+ND], av[2+ND] non-zero Jacobian entries of the two rows (a[1] ignored when UNIT_C)
+// ---------------------------------------------------------------------------------------
+template <int M, int KIND> struct Lin;
+
+template <> struct Lin<ACM_MODEL_PINHOLE, ACM_RESIDUAL_PIXEL> {
+    static constexpr int ND = 0; static constexpr bool UNIT_C = true;
+    static __device__ __forceinline__ bool eval(const LinParams& p, double x, double y, double z, double u, double v,
+                                                double& ru, double& rv, double* au, double* av) {
+        if (!(z >= LIN_SQRT_EPS)) return false;
+        double iz = 1.0 / z;
+        double mx = x * iz, my = y * iz;
+        ru = fma(p.fx, mx, p.cx) - u; rv = fma(p.fy, my, p.cy) - v;
+        au[0] = mx; av[0] = my; au[1] = av[1] = 1.0;
+        return true;
+    }
+};
+
+template <> struct Lin<ACM_MODEL_RADTAN, ACM_RESIDUAL_PIXEL> {
+    static constexpr int ND = 5; static constexpr bool UNIT_C = true;
+    static __device__ __forceinline__ bool eval(const LinParams& p, double x, double y, double z, double u, double v,
+                                                double& ru, double& rv, double* au, double* av) {
+        if (!(z >= LIN_SQRT_EPS)) return false;
+        const double k1 = p.d[0], k2 = p.d[1], p1 = p.d[2], p2 = p.d[3], k3 = p.d[4];
+        double iz = 1.0 / z;
+        double xp = x * iz, yp = y * iz;
+        double rho = xp * xp + yp * yp, rho2 = rho * rho, rho3 = rho2 * rho;
+        double rad = 1.0 + k1 * rho + k2 * rho2 + k3 * rho3;
+        double xy2 = 2.0 * xp * yp;
+        double tx = rho + 2.0 * xp * xp, ty = rho + 2.0 * yp * yp;
+        double mx = xp * rad + p1 * xy2 + p2 * tx;
+        double my = yp * rad + p1 * ty + p2 * xy2;
+        ru = fma(p.fx, mx, p.cx) - u; rv = fma(p.fy, my, p.cy) - v;
+        double fxx = p.fx * xp, fyy = p.fy * yp;
+        au[0] = mx; av[0] = my; au[1] = av[1] = 1.0;
+        au[2] = fxx * rho;  av[2] = fyy * rho;    // k1
+        au[3] = fxx * rho2; av[3] = fyy * rho2;   // k2
+        au[4] = p.fx * xy2; av[4] = p.fy * ty;    // p1
+        au[5] = p.fx * tx;  av[5] = p.fy * xy2;   // p2
+        au[6] = fxx * rho3; av[6] = fyy * rho3;   // k3
+        return true;
+    }
+};
+
+template <> struct Lin<ACM_MODEL_KANNALA_BRANDT, ACM_RESIDUAL_PIXEL> {
+    static constexpr int ND = 4; static constexpr bool UNIT_C = true;
+    static __device__ __forceinline__ bool eval(const LinParams& p, double x, double y, double z, double u, double v,
+                                                double& ru, double& rv, double* au, double* av) {
+        if (!(z >= LIN_EPS)) return false;  // z < 0 and 0 <= z < EPS both fail (kannala_brandt.rs:345-351)
+        double r = sqrt(x * x + y * y);
+        double th = atan2(r, z);
+        double xr = 0.0, yr = 0.0;
+        if (r >= LIN_EPS) { double ir = 1.0 / r; xr = x * ir; yr = y * ir; }
+        double t2 = th * th, t3 = t2 * th, t5 = t3 * t2, t7 = t5 * t2, t9 = t7 * t2;
+        double thd = th + p.d[0] * t3 + p.d[1] * t5 + p.d[2] * t7 + p.d[3] * t9;
+        double mx = thd * xr, my = thd * yr;
+        ru = fma(p.fx, mx, p.cx) - u; rv = fma(p.fy, my, p.cy) - v;
+        double fxr = p.fx * xr, fyr = p.fy * yr;
+        au[0] = mx; av[0] = my; au[1] = av[1] = 1.0;
+        au[2] = fxr * t3; av[2] = fyr * t3;
+        au[3] = fxr * t5; av[3] = fyr * t5;
+        au[4] = fxr * t7; av[4] = fyr * t7;
+        au[5] = fxr * t9; av[5] = fyr * t9;
+        return true;
+    }
+};
+
+// Unified family: den and d(den)/d(dist) are shared by both residual kinds.
+template <int M> struct Unified;
+template <> struct Unified<ACM_MODEL_UCM> {
+    static constexpr int ND = 1;
+    static __device__ __forceinline__ bool den(const LinParams& p, double x, double y, double z, double& den, double* dd) {
+        const double alpha = p.d[0];
+        double d = sqrt(x * x + y * y + z * z);
+        den = alpha * d + (1.0 - alpha) * z;
+        dd[0] = d - z;
+        return (den >= LIN_PRECISION) && (z > -p.k0 * d);
+    }
+};
+template <> struct Unified<ACM_MODEL_EUCM> {
+    static constexpr int ND = 2;
+    static __device__ __forceinline__ bool den(const LinParams& p, double x, double y, double z, double& den, double* dd) {
+        const double alpha = p.d[0], beta = p.d[1];
+        double rr = x * x + y * y;
+        double q = beta * rr + z * z;
+        double id = rsqrt(q);
+        double d = q * id;
+        den = alpha * d + (1.0 - alpha) * z;
+        dd[0] = d - z;
+        dd[1] = 0.5 * alpha * rr * id;
+        bool cond = true;
+        if (alpha > 0.5) cond = !(z < den * p.k0);
+        return (den >= LIN_PRECISION) && cond && (q > 0.0);
+    }
+};
+template <> struct Unified<ACM_MODEL_DOUBLE_SPHERE> {
+    static constexpr int ND = 2;
+    static __device__ __forceinline__ bool den(const LinParams& p, double x, double y, double z, double& den, double* dd) {
+        const double alpha = p.d[0], xi = p.d[1];
+        double rr = x * x + y * y;
+        double d1 = sqrt(rr + z * z);
+        double g = fma(xi, d1, z);
+        double q = fma(g, g, rr);
+        double id2 = rsqrt(q);
+        double d2 = q * id2;
+        double oma = 1.0 - alpha;
+        den = alpha * d2 + oma * g;
+        dd[0] = d2 - g;
+        dd[1] = d1 * fma(alpha * g, id2, oma);
+        return (den >= LIN_PRECISION) && (z > -p.k0 * d1) && (q > 0.0);
+    }
+};
+
+template <int M> struct LinUnifiedPixel {
+    static constexpr int ND = Unified<M>::ND; static constexpr bool UNIT_C = true;
+    static __device__ __forceinline__ bool eval(const LinParams& p, double x, double y, double z, double u, double v,
+                                                double& ru, double& rv, double* au, double* av) {
+        double den, dd[2];
+        if (!Unified<M>::den(p, x, y, z, den, dd)) return false;
+        double inv = 1.0 / den;
+        double mx = x * inv, my = y * inv;
+        ru = fma(p.fx, mx, p.cx) - u; rv = fma(p.fy, my, p.cy) - v;
+        double cu = -(p.fx * mx) * inv, cv = -(p.fy * my) * inv;  // d(u)/d(den), d(v)/d(den)
+        au[0] = mx; av[0] = my; au[1] = av[1] = 1.0;
+#pragma unroll
+        for (int k = 0; k < ND; ++k) { au[2 + k] = cu * dd[k]; av[2 + k] = cv * dd[k]; }
+        return true;
+    }
+};
+template <int M> struct LinUnifiedAlgebraic {
+    static constexpr int ND = Unified<M>::ND; static constexpr bool UNIT_C = false;
+    static __device__ __forceinline__ bool eval(const LinParams& p, double x, double y, double z, double u, double v,
+                                                double& ru, double& rv, double* au, double* av) {
+        double den, dd[2];
+        if (!Unified<M>::den(p, x, y, z, den, dd)) return false;
+        double du = u - p.cx, dv = v - p.cy;
+        ru = p.fx * x - du * den; rv = p.fy * y - dv * den;
+        au[0] = x; av[0] = y; au[1] = den; av[1] = den;
+#pragma unroll
+        for (int k = 0; k < ND; ++k) { au[2 + k] = -du * dd[k]; av[2 + k] = -dv * dd[k]; }
+        return true;
+    }
+};
+template <> struct Lin<ACM_MODEL_UCM, ACM_RESIDUAL_PIXEL> : LinUnifiedPixel<ACM_MODEL_UCM> {};
+template <> struct Lin<ACM_MODEL_EUCM, ACM_RESIDUAL_PIXEL> : LinUnifiedPixel<ACM_MODEL_EUCM> {};
+template <> struct Lin<ACM_MODEL_DOUBLE_SPHERE, ACM_RESIDUAL_PIXEL> : LinUnifiedPixel<ACM_MODEL_DOUBLE_SPHERE> {};
+template <> struct Lin<ACM_MODEL_UCM, ACM_RESIDUAL_ALGEBRAIC> : LinUnifiedAlgebraic<ACM_MODEL_UCM> {};
+template <> struct Lin<ACM_MODEL_EUCM, ACM_RESIDUAL_ALGEBRAIC> : LinUnifiedAlgebraic<ACM_MODEL_EUCM> {};
+template <> struct Lin<ACM_MODEL_DOUBLE_SPHERE, ACM_RESIDUAL_ALGEBRAIC> : LinUnifiedAlgebraic<ACM_MODEL_DOUBLE_SPHERE> {};
+
+template <> struct Lin<ACM_MODEL_FOV, ACM_RESIDUAL_PIXEL> {
+    static constexpr int ND = 1; static constexpr bool UNIT_C = true;
+    static __device__ __forceinline__ bool eval(const LinParams& p, double x, double y, double z, double u, double v,
+                                                double& ru, double& rv, double* au, double* av) {
+        if (!(z >= LIN_SQRT_EPS)) return false;
+        const double w = p.d[0], t = p.k0;
+        double r2 = x * x + y * y;
+        double rd, drd;
+        double iw = 1.0 / w;
+        if (r2 < LIN_SQRT_EPS) {
+            rd = 2.0 * t * iw;
+            drd = (1.0 + t * t) * iw - 2.0 * t * iw * iw;
+        } else {
+            double r = sqrt(r2);
+            double a = atan2(2.0 * t * r, z);
+            double da = z * r * (1.0 + t * t) / (4.0 * t * t * r2 + z * z);
+            double irw = iw / r;
+            rd = a * irw;
+            drd = (da - a * iw) * irw;
+        }
+        double mx = x * rd, my = y * rd;
+        ru = fma(p.fx, mx, p.cx) - u; rv = fma(p.fy, my, p.cy) - v;
+        au[0] = mx; av[0] = my; au[1] = av[1] = 1.0;
+        au[2] = p.fx * x * drd; av[2] = p.fy * y * drd;
+        return true;
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// rank-2 update of the packed normal equations with the two sparse rows
+// ---------------------------------------------------------------------------------------
+template <int ND, bool UNIT_C>
+__device__ __forceinline__ void lin_accumulate(double* acc, double ru, double rv, const double* au, const double* av) {
+    using L = AccLayout<ND>;
+    acc[L::HFF + 0] = fma(au[0], au[0], acc[L::HFF + 0]);
+    acc[L::HFF + 1] = fma(av[0], av[0], acc[L::HFF + 1]);
+    acc[L::GF + 0] = fma(au[0], ru, acc[L::GF + 0]);
+    acc[L::GF + 1] = fma(av[0], rv, acc[L::GF + 1]);
+    if (UNIT_C) {
+        acc[L::HFC + 0] += au[0];
+        acc[L::HFC + 1] += av[0];
+        acc[L::GC + 0] += ru;
+        acc[L::GC + 1] += rv;
+    } else {
+        acc[L::HFC + 0] = fma(au[0], au[1], acc[L::HFC + 0]);
+        acc[L::HFC + 1] = fma(av[0], av[1], acc[L::HFC + 1]);
+        acc[L::HCC + 0] = fma(au[1], au[1], acc[L::HCC + 0]);
+        acc[L::HCC + 1] = fma(av[1], av[1], acc[L::HCC + 1]);
+        acc[L::GC + 0] = fma(au[1], ru, acc[L::GC + 0]);
+        acc[L::GC + 1] = fma(av[1], rv, acc[L::GC + 1]);
+    }
+#pragma unroll
+    for (int k = 0; k < ND; ++k) {
+        acc[L::HFD + k] = fma(au[0], au[2 + k], acc[L::HFD + k]);
+        acc[L::HFD + ND + k] = fma(av[0], av[2 + k], acc[L::HFD + ND + k]);
+        if (UNIT_C) {
+            acc[L::HCD + k] += au[2 + k];
+            acc[L::HCD + ND + k] += av[2 + k];
+        } else {
+            acc[L::HCD + k] = fma(au[1], au[2 + k], acc[L::HCD + k]);
+            acc[L::HCD + ND + k] = fma(av[1], av[2 + k], acc[L::HCD + ND + k]);
+        }
+        acc[L::GD + k] = fma(au[2 + k], ru, fma(av[2 + k], rv, acc[L::GD + k]));
+#pragma unroll
+        for (int j = 0; j <= k; ++j)
+            acc[L::HDD + L::tri(j, k)] = fma(au[2 + j], au[2 + k], fma(av[2 + j], av[2 + k], acc[L::HDD + L::tri(j, k)]));
+    }
+    acc[L::COST] = fma(ru, ru, fma(rv, rv, acc[L::COST]));
+    acc[L::COUNT] += 1.0;
+}
+
+// Reduced accumulator vector -> dense symmetric H (P x P), g, cost, count.
+template <int ND, bool UNIT_C>
+__host__ __device__ inline void lin_unpack(const double* r, double* H, double* g, double* cost, double* count) {
+    using L = AccLayout<ND>;
+    constexpr int P = 4 + ND;
+    for (int i = 0; i < P * P; ++i) H[i] = 0.0;
+    const double cnt = r[L::COUNT];
+    H[0 * P + 0] = r[L::HFF]; H[1 * P + 1] = r[L::HFF + 1];
+    H[0 * P + 2] = r[L::HFC]; H[1 * P + 3] = r[L::HFC + 1];
+    H[2 * P + 2] = UNIT_C ? cnt : r[L::HCC]; H[3 * P + 3] = UNIT_C ? cnt : r[L::HCC + 1];
+    for (int k = 0; k < ND; ++k) {
+        H[0 * P + 4 + k] = r[L::HFD + k]; H[1 * P + 4 + k] = r[L::HFD + ND + k];
+        H[2 * P + 4 + k] = r[L::HCD + k]; H[3 * P + 4 + k] = r[L::HCD + ND + k];
+        for (int j = 0; j <= k; ++j) H[(4 + j) * P + 4 + k] = r[L::HDD + L::tri(j, k)];
+        g[4 + k] = r[L::GD + k];
+    }
+    g[0] = r[L::GF]; g[1] = r[L::GF + 1]; g[2] = r[L::GC]; g[3] = r[L::GC + 1];
+    for (int a = 0; a < P; ++a) for (int b = 0; b < a; ++b) H[a * P + b] = H[b * P + a];
+    *cost = 0.5 * r[L::COST];
+    *count = cnt;
+}

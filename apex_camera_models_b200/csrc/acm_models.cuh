@@ -1,0 +1,299 @@
+// Device math of the seven camera models: project / unproject with the reference's validity
+// tests, evaluated in IEEE binary64 in the reference's operation order.  The translation
+// unit that includes this header for the project / unproject / undistort kernels is compiled
+// with -fmad=false: Rust never contracts a*b+c, and the status masks (and remap indices) must
+// be bit-exact.  Per-model line references are to /root/reference/src/camera/<model>.rs.
+#pragma once
+#include "acm_internal.cuh"
+
+#define ACM_EPS 2.220446049250313e-16        // f64::EPSILON
+#define ACM_SQRT_EPS 1.4901161193847656e-08  // f64::EPSILON.sqrt() == 2^-26
+#define ACM_PRECISION 1e-3
+
+__device__ __forceinline__ double acm_nan() { return __longlong_as_double(0x7ff8000000000000LL); }
+
+__device__ __forceinline__ bool acm_outside(const CamParams& c, double u, double v) {
+    // mod.rs:157-166, :194-206 -- half-open [0,W) x [0,H)
+    return u < 0.0 || u >= c.W || v < 0.0 || v >= c.H;
+}
+
+// nalgebra normalize(): n = sqrt((x*x + y*y) + z*z), each component divided by n
+__device__ __forceinline__ void acm_normalize(double x, double y, double z, double& ox, double& oy, double& oz) {
+    double n = sqrt(x * x + y * y + z * z);
+    ox = x / n; oy = y / n; oz = z / n;
+}
+
+template <int M> struct CamModel;
+
+// ---- Pinhole (pinhole.rs:165-182, :228-246) ----------------------------------------------
+template <> struct CamModel<ACM_MODEL_PINHOLE> {
+    template <bool BOUNDS>
+    static __device__ __forceinline__ int project(const CamParams& c, double x, double y, double z, double& u, double& v) {
+        if (z < ACM_SQRT_EPS) return ACM_POINT_AT_CAMERA_CENTER;
+        u = c.fx * x / z + c.cx;
+        v = c.fy * y / z + c.cy;
+        if (BOUNDS && acm_outside(c, u, v)) return ACM_PROJECTION_OUTSIDE_IMAGE;
+        return ACM_POINT_OK;
+    }
+    static __device__ __forceinline__ int unproject(const CamParams& c, double u, double v, double& rx, double& ry, double& rz) {
+        if (acm_outside(c, u, v)) return ACM_POINT_IS_OUTSIDE_IMAGE;
+        double mx = (u - c.cx) / c.fx, my = (v - c.cy) / c.fy;
+        double r2 = mx * mx + my * my;
+        double ninv = 1.0 / sqrt(1.0 + r2);
+        rx = mx * ninv; ry = my * ninv; rz = ninv;
+        return ACM_POINT_OK;
+    }
+};
+
+// ---- RadTan (rad_tan.rs:302-348, :401-524), d = [k1,k2,p1,p2,k3] ---------------------------
+template <> struct CamModel<ACM_MODEL_RADTAN> {
+    template <bool BOUNDS>
+    static __device__ __forceinline__ int project(const CamParams& c, double x, double y, double z, double& u, double& v) {
+        if (z < ACM_SQRT_EPS) return ACM_POINT_AT_CAMERA_CENTER;
+        const double k1 = c.d[0], k2 = c.d[1], p1 = c.d[2], p2 = c.d[3], k3 = c.d[4];
+        double xp = x / z, yp = y / z;
+        double r2 = xp * xp + yp * yp;
+        double r4 = r2 * r2;
+        double r6 = r4 * r2;
+        double rad = 1.0 + k1 * r2 + k2 * r4 + k3 * r6;
+        double xd = xp * rad + 2.0 * p1 * xp * yp + p2 * (r2 + 2.0 * xp * xp);
+        double yd = yp * rad + p1 * (r2 + 2.0 * yp * yp) + 2.0 * p2 * xp * yp;
+        u = c.fx * xd + c.cx;
+        v = c.fy * yd + c.cy;
+        if (BOUNDS && acm_outside(c, u, v)) return ACM_PROJECTION_OUTSIDE_IMAGE;
+        return ACM_POINT_OK;
+    }
+    static __device__ int unproject(const CamParams& c, double u, double v, double& rx, double& ry, double& rz) {
+        if (acm_outside(c, u, v)) return ACM_POINT_IS_OUTSIDE_IMAGE;
+        const double k1 = c.d[0], k2 = c.d[1], p1 = c.d[2], p2 = c.d[3], k3 = c.d[4];
+        const double tx = (u - c.cx) / c.fx, ty = (v - c.cy) / c.fy;
+        double px = tx, py = ty;
+        for (int it = 0; it < 100; ++it) {
+            double x = px, y = py;
+            double r2 = x * x + y * y;
+            double r4 = r2 * r2;
+            double r6 = r4 * r2;
+            double rad = 1.0 + k1 * r2 + k2 * r4 + k3 * r6;
+            double xe = x * rad + 2.0 * p1 * x * y + p2 * (r2 + 2.0 * x * x);
+            double ye = y * rad + p1 * (r2 + 2.0 * y * y) + 2.0 * p2 * x * y;
+            double ex = xe - tx, ey = ye - ty;
+            if (sqrt(ex * ex + ey * ey) < 1e-6) break;
+            double dr_dx = 2.0 * x, dr_dy = 2.0 * y;
+            double common = k1 + 2.0 * k2 * r2 + 3.0 * k3 * r4;
+            double drad_dx = common * dr_dx, drad_dy = common * dr_dy;
+            double j00 = rad + x * drad_dx + 2.0 * p1 * y + p2 * (dr_dx + 4.0 * x);
+            double j01 = x * drad_dy + 2.0 * p1 * x + p2 * (dr_dy);
+            double j10 = y * drad_dx + p1 * (dr_dx) + 2.0 * p2 * y;
+            double j11 = rad + y * drad_dy + p1 * (dr_dy + 4.0 * y) + 2.0 * p2 * x;
+            double det = j00 * j11 - j10 * j01;   // nalgebra Matrix2::try_inverse
+            if (det == 0.0) return ACM_POINT_NUMERICAL_ERROR;
+            double i00 = j11 / det, i01 = -j01 / det, i10 = -j10 / det, i11 = j00 / det;
+            double dx = i00 * ex + i01 * ey;
+            double dy = i10 * ex + i11 * ey;
+            px -= dx; py -= dy;
+            if (sqrt(dx * dx + dy * dy) < 1e-6) break;
+            if (it == 99) return ACM_POINT_NUMERICAL_ERROR;
+        }
+        acm_normalize(px, py, 1.0, rx, ry, rz);
+        return ACM_POINT_OK;
+    }
+};
+
+// ---- Kannala-Brandt (kannala_brandt.rs:340-394, :445-562), d = [k1..k4] ---------------------
+template <> struct CamModel<ACM_MODEL_KANNALA_BRANDT> {
+    template <bool BOUNDS>
+    static __device__ __forceinline__ int project(const CamParams& c, double x, double y, double z, double& u, double& v) {
+        if (z < 0.0) return ACM_POINT_IS_OUTSIDE_IMAGE;
+        else if (z < ACM_EPS) return ACM_POINT_AT_CAMERA_CENTER;
+        double r = sqrt(x * x + y * y);
+        double th = atan2(r, z);
+        double t2 = th * th;
+        double t3 = t2 * th;
+        double t5 = t3 * t2;
+        double t7 = t5 * t2;
+        double t9 = t7 * t2;
+        double thd = th + c.d[0] * t3 + c.d[1] * t5 + c.d[2] * t7 + c.d[3] * t9;
+        double xr, yr;
+        if (r < ACM_EPS) { xr = 0.0; yr = 0.0; } else { xr = x / r; yr = y / r; }
+        u = c.fx * thd * xr + c.cx;
+        v = c.fy * thd * yr + c.cy;
+        return ACM_POINT_OK;  // no image-bounds test in the reference
+    }
+    static __device__ int unproject(const CamParams& c, double u, double v, double& rx, double& ry, double& rz) {
+        if (c.has_resolution && acm_outside(c, u, v)) return ACM_POINT_IS_OUTSIDE_IMAGE;
+        const double k1 = c.d[0], k2 = c.d[1], k3 = c.d[2], k4 = c.d[3];
+        double mx = (u - c.cx) / c.fx, my = (v - c.cy) / c.fy;
+        double ru = sqrt(mx * mx + my * my);
+        ru = fmin(ru, 3.14159265358979323846 / 2.0);
+        double th = ru;
+        bool converged = true;
+        if (ru > 1e-6) {
+            for (int i = 0; i < 10; ++i) {
+                double t2 = th * th, t4 = t2 * t2, t6 = t4 * t2, t8 = t4 * t4;
+                double a1 = k1 * t2, a2 = k2 * t4, a3 = k3 * t6, a4 = k4 * t8;
+                double f = th * (1.0 + a1 + a2 + a3 + a4) - ru;
+                double fp = 1.0 + (3.0 * a1) + (5.0 * a2) + (7.0 * a3) + (9.0 * a4);
+                if (fabs(fp) < ACM_EPS) { converged = false; break; }
+                double delta = f / fp;
+                th -= delta;
+                if (fabs(delta) < 1e-6) break;
+                if (i == 9) converged = false;
+            }
+        } else {
+            if (ru > 0.0) converged = false; else th = 0.0;
+        }
+        if (!converged) return ACM_POINT_NUMERICAL_ERROR;
+        double xc, yc;
+        if (fabs(ru) < ACM_EPS) { xc = 0.0; yc = 0.0; } else { xc = mx / ru; yc = my / ru; }
+        double st, ct;
+        sincos(th, &st, &ct);
+        acm_normalize(st * xc, st * yc, ct, rx, ry, rz);
+        return ACM_POINT_OK;
+    }
+};
+
+// ---- UCM (ucm.rs:297-316, :337-367, :154-161, :177-184), d = [alpha] -------------------------
+// k0 = w of check_proj_condition, k1 = gamma*gamma/(2*alpha-1), k2 = xi = alpha/gamma
+template <> struct CamModel<ACM_MODEL_UCM> {
+    template <bool BOUNDS>
+    static __device__ __forceinline__ int project(const CamParams& c, double x, double y, double z, double& u, double& v) {
+        const double alpha = c.d[0];
+        double d = sqrt(x * x + y * y + z * z);
+        double den = alpha * d + (1.0 - alpha) * z;
+        bool cond = z > -c.k0 * d;
+        if (den < ACM_PRECISION || !cond) return ACM_POINT_IS_OUTSIDE_IMAGE;
+        u = c.fx * (x / den) + c.cx;
+        v = c.fy * (y / den) + c.cy;
+        return ACM_POINT_OK;
+    }
+    static __device__ __forceinline__ int unproject(const CamParams& c, double u, double v, double& rx, double& ry, double& rz) {
+        const double alpha = c.d[0];
+        double gamma = 1.0 - alpha;
+        double xi = c.k2;
+        double mx = (u - c.cx) / c.fx * gamma, my = (v - c.cy) / c.fy * gamma;
+        double r2 = mx * mx + my * my;
+        double num = xi + sqrt(1.0 + (1.0 - xi * xi) * r2);
+        double den = 1.0 - r2;
+        bool cond = (alpha > 0.5) ? (r2 <= c.k1) : true;
+        if (den < ACM_PRECISION || !cond) return ACM_POINT_IS_OUTSIDE_IMAGE;
+        double coeff = num / den;
+        acm_normalize(coeff * mx, coeff * my, coeff - xi, rx, ry, rz);
+        return ACM_POINT_OK;
+    }
+};
+
+// ---- EUCM (eucm.rs:328-347, :368-398, :167-177, :194-200), d = [alpha,beta] -------------------
+// k0 = (alpha-1)/(2*alpha-1), k1 = 1/beta*(2*alpha-1)  (the reference's precedence, kept)
+template <> struct CamModel<ACM_MODEL_EUCM> {
+    template <bool BOUNDS>
+    static __device__ __forceinline__ int project(const CamParams& c, double x, double y, double z, double& u, double& v) {
+        const double alpha = c.d[0], beta = c.d[1];
+        double d = sqrt(beta * (x * x + y * y) + z * z);
+        double den = alpha * d + (1.0 - alpha) * z;
+        bool cond = true;
+        if (alpha > 0.5) { if (z < den * c.k0) cond = false; }
+        if (den < ACM_PRECISION || !cond) return ACM_POINT_IS_OUTSIDE_IMAGE;
+        u = c.fx * (x / den) + c.cx;
+        v = c.fy * (y / den) + c.cy;
+        return ACM_POINT_OK;
+    }
+    static __device__ __forceinline__ int unproject(const CamParams& c, double u, double v, double& rx, double& ry, double& rz) {
+        const double alpha = c.d[0], beta = c.d[1];
+        double mx = (u - c.cx) / c.fx, my = (v - c.cy) / c.fy;
+        double r2 = mx * mx + my * my;
+        double gamma = 1.0 - alpha;
+        double num = 1.0 - r2 * alpha * alpha * beta;
+        double det = 1.0 - (alpha - gamma) * beta * r2;
+        double den = gamma + alpha * sqrt(det);
+        bool cond = !(alpha > 0.5 && r2 > c.k1);
+        if (det < ACM_PRECISION || !cond) return ACM_POINT_IS_OUTSIDE_IMAGE;
+        double mz = num / den;
+        double norm = sqrt(mx * mx + my * my + mz * mz);
+        rx = mx / norm; ry = my / norm; rz = mz / norm;
+        return ACM_POINT_OK;
+    }
+};
+
+// ---- Double Sphere (double_sphere.rs:361-390, :436-476, :177-184, :200-209), d = [alpha,xi] ---
+// k0 = w2, k1 = 1/(2*alpha-1)
+template <> struct CamModel<ACM_MODEL_DOUBLE_SPHERE> {
+    template <bool BOUNDS>
+    static __device__ __forceinline__ int project(const CamParams& c, double x, double y, double z, double& u, double& v) {
+        const double alpha = c.d[0], xi = c.d[1];
+        double r2 = (x * x) + (y * y);
+        double d1 = sqrt(r2 + (z * z));
+        double g = xi * d1 + z;
+        double d2 = sqrt(r2 + g * g);
+        double den = alpha * d2 + (1.0 - alpha) * g;
+        bool cond = z > -c.k0 * d1;
+        if (den < ACM_PRECISION || !cond) return ACM_POINT_IS_OUTSIDE_IMAGE;
+        u = c.fx * (x / den) + c.cx;
+        v = c.fy * (y / den) + c.cy;
+        return ACM_POINT_OK;
+    }
+    static __device__ __forceinline__ int unproject(const CamParams& c, double u, double v, double& rx, double& ry, double& rz) {
+        const double alpha = c.d[0], xi = c.d[1];
+        double gamma = 1.0 - alpha;
+        double mx = (u - c.cx) / c.fx, my = (v - c.cy) / c.fy;
+        double r2 = (mx * mx) + (my * my);
+        bool cond = true;
+        if (alpha > 0.5) { if (r2 > c.k1) cond = false; }
+        if (alpha != 0.0 && !cond) return ACM_POINT_IS_OUTSIDE_IMAGE;
+        double mz = (1.0 - alpha * alpha * r2) / (alpha * sqrt(1.0 - (2.0 * alpha - 1.0) * r2) + gamma);
+        double mz2 = mz * mz;
+        double num = mz * xi + sqrt(mz2 + (1.0 - xi * xi) * r2);
+        double den = mz2 + r2;
+        if (den < ACM_PRECISION) return ACM_POINT_IS_OUTSIDE_IMAGE;
+        double coeff = num / den;
+        acm_normalize(coeff * mx, coeff * my, coeff * mz - xi, rx, ry, rz);
+        return ACM_POINT_OK;
+    }
+};
+
+// ---- FOV (fov.rs:284-316, :336-363), d = [w]; k0 = tan(w/2) from the host's libm -------------
+template <> struct CamModel<ACM_MODEL_FOV> {
+    template <bool BOUNDS>
+    static __device__ __forceinline__ int project(const CamParams& c, double x, double y, double z, double& u, double& v) {
+        const double w = c.d[0];
+        if (z < ACM_SQRT_EPS) return ACM_POINT_AT_CAMERA_CENTER;
+        double r2 = x * x + y * y;
+        double r = sqrt(r2);
+        double t = c.k0;
+        double rd;
+        if (r2 < ACM_SQRT_EPS) rd = 2.0 * t / w;
+        else rd = atan2(2.0 * t * r, z) / (r * w);
+        double mx = x * rd, my = y * rd;
+        u = c.fx * mx + c.cx;
+        v = c.fy * my + c.cy;
+        return ACM_POINT_OK;
+    }
+    static __device__ __forceinline__ int unproject(const CamParams& c, double u, double v, double& rx, double& ry, double& rz) {
+        const double w = c.d[0];
+        double mul2 = c.k0 * 2.0;
+        double mx = (u - c.cx) / c.fx, my = (v - c.cy) / c.fy;
+        double r2 = mx * mx + my * my;
+        double rd = sqrt(r2);
+        double x, y;
+        if (mul2 > ACM_SQRT_EPS && rd > ACM_SQRT_EPS) {
+            double s, co;
+            sincos(rd * w, &s, &co);
+            double ru = s / (rd * mul2);
+            x = mx * ru / co; y = my * ru / co;
+        } else { x = mx; y = my; }
+        acm_normalize(x, y, 1.0, rx, ry, rz);
+        return ACM_POINT_OK;
+    }
+};
+
+// Runtime model id -> compile-time specialisation.
+#define ACM_DISPATCH_MODEL(model_id, ...)                                                     \
+    switch (model_id) {                                                                       \
+        case ACM_MODEL_PINHOLE: { constexpr int M = ACM_MODEL_PINHOLE; __VA_ARGS__; break; }  \
+        case ACM_MODEL_RADTAN: { constexpr int M = ACM_MODEL_RADTAN; __VA_ARGS__; break; }    \
+        case ACM_MODEL_KANNALA_BRANDT: { constexpr int M = ACM_MODEL_KANNALA_BRANDT; __VA_ARGS__; break; } \
+        case ACM_MODEL_UCM: { constexpr int M = ACM_MODEL_UCM; __VA_ARGS__; break; }          \
+        case ACM_MODEL_EUCM: { constexpr int M = ACM_MODEL_EUCM; __VA_ARGS__; break; }        \
+        case ACM_MODEL_DOUBLE_SPHERE: { constexpr int M = ACM_MODEL_DOUBLE_SPHERE; __VA_ARGS__; break; } \
+        case ACM_MODEL_FOV: { constexpr int M = ACM_MODEL_FOV; __VA_ARGS__; break; }          \
+        default: return acm_fail(ctx, ACM_ERR_INVALID_ARG, "unknown camera model id %d", (int)(model_id)); \
+    }

@@ -1,0 +1,403 @@
+// Fused linearisation kernel, deterministic reduction, device-resident Levenberg-Marquardt.
+//
+// One LM iteration = one streaming pass (linearize_kernel at the trial point: cost, H and g
+// together, "speculative linearisation") + an all-reduce of <= 54 doubles when a communicator
+// is attached + one single-thread step kernel (accept / reject, damping update, P x P
+// Cholesky with Jacobi scaling, next trial point).  The host only polls a done flag every
+// `check_every` iterations; kernels launched after convergence exit on their first load.
+//
+// Determinism: fixed grid, per-thread sequential accumulation over a grid-stride range,
+// fixed shuffle tree, per-block partials, the last block to finish sums the partials in
+// block order.  No floating-point atomics.  The result depends on the grid size only.
+#include "acm_linearize.cuh"
+
+#include <chrono>
+
+struct LmState {
+    double x[ACM_MAX_PARAMS], xt[ACM_MAX_PARAMS];
+    double H[ACM_MAX_PARAMS * ACM_MAX_PARAMS], g[ACM_MAX_PARAMS];
+    double lower[ACM_MAX_PARAMS], upper[ACM_MAX_PARAMS];
+    double cost, lambda, nu;
+    double pred, dnorm, xnorm;
+    double cost_tol, param_tol, grad_tol;
+    double initial_cost, n_valid;
+    int32_t max_iter, iterations, passes, status, done, first, P, pad;
+};
+static_assert(sizeof(LmState) <= 4096, "LmState must fit the context's 4 KiB slot");
+
+// ---------------------------------------------------------------------------------------
+// linearize kernel
+// ---------------------------------------------------------------------------------------
+template <int M, int KIND>
+__global__ void __launch_bounds__(256) linearize_kernel(LinParams hp, const LmState* __restrict__ lm, const double2* __restrict__ X,
+                                                        const double2* __restrict__ Y, const double2* __restrict__ Z,
+                                                        const double2* __restrict__ U, const double2* __restrict__ V, size_t n,
+                                                        double pen2x2, double* __restrict__ partials, double* __restrict__ out,
+                                                        unsigned int* __restrict__ ticket) {
+    using LM_ = Lin<M, KIND>;
+    constexpr int ND = LM_::ND;
+    constexpr bool UNIT_C = LM_::UNIT_C;
+    using L = AccLayout<ND>;
+    constexpr int NACC = L::N;
+    static_assert(NACC <= 64, "final-pass layout assumes <= 64 accumulators");
+
+    LinParams p = hp;
+    if (lm) {
+        if (lm->done) return;  // converged earlier in this enqueue batch
+        p.fx = lm->xt[0]; p.fy = lm->xt[1]; p.cx = lm->xt[2]; p.cy = lm->xt[3];
+#pragma unroll
+        for (int k = 0; k < ND; ++k) p.d[k] = lm->xt[4 + k];
+        lin_derive(M, p);
+    }
+
+    double acc[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
+
+    const size_t npairs = n >> 1;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += stride) {
+        const double2 x = __ldcs(X + i), y = __ldcs(Y + i), z = __ldcs(Z + i), u = __ldcs(U + i), v = __ldcs(V + i);
+        double ru, rv, au[2 + ND], av[2 + ND];
+        if (LM_::eval(p, x.x, y.x, z.x, u.x, v.x, ru, rv, au, av)) lin_accumulate<ND, UNIT_C>(acc, ru, rv, au, av);
+        if (LM_::eval(p, x.y, y.y, z.y, u.y, v.y, ru, rv, au, av)) lin_accumulate<ND, UNIT_C>(acc, ru, rv, au, av);
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const size_t t = n - 1;
+        const double* Xs = reinterpret_cast<const double*>(X); const double* Ys = reinterpret_cast<const double*>(Y);
+        const double* Zs = reinterpret_cast<const double*>(Z); const double* Us = reinterpret_cast<const double*>(U);
+        const double* Vs = reinterpret_cast<const double*>(V);
+        double ru, rv, au[2 + ND], av[2 + ND];
+        if (LM_::eval(p, Xs[t], Ys[t], Zs[t], Us[t], Vs[t], ru, rv, au, av)) lin_accumulate<ND, UNIT_C>(acc, ru, rv, au, av);
+    }
+
+    // warp tree -> shared -> block partial
+    __shared__ double sm[8][NACC];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) {
+        double v = acc[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) sm[warp][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NACC) {
+        double s = sm[0][threadIdx.x];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) s += sm[w][threadIdx.x];
+        partials[(size_t)blockIdx.x * NACC + threadIdx.x] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = atomicAdd(ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // final pass: 4 contiguous block ranges x NACC accumulators, combined in fixed order
+    {
+        const int a = threadIdx.x & 63, sub = threadIdx.x >> 6;
+        const unsigned int nb = gridDim.x;
+        const unsigned int b0 = (unsigned int)(((size_t)nb * sub) / 4), b1 = (unsigned int)(((size_t)nb * (sub + 1)) / 4);
+        double s = 0.0;
+        if (a < NACC)
+            for (unsigned int b = b0; b < b1; ++b) s += __ldcg(partials + (size_t)b * NACC + a);
+        __shared__ double fin4[4][64];
+        fin4[sub][a] = s;
+        __syncthreads();
+        if (threadIdx.x < NACC) {
+            double tot = ((fin4[0][threadIdx.x] + fin4[1][threadIdx.x]) + fin4[2][threadIdx.x]) + fin4[3][threadIdx.x];
+            if (threadIdx.x == L::COST) {
+                double cnt = ((fin4[0][L::COUNT] + fin4[1][L::COUNT]) + fin4[2][L::COUNT]) + fin4[3][L::COUNT];
+                tot += pen2x2 * ((double)n - cnt);  // invalid points carry residual (pen, pen)
+            }
+            out[threadIdx.x] = tot;
+        }
+        if (threadIdx.x == 0) *ticket = 0;  // re-arm for the next launch on this stream
+    }
+}
+
+template <int M, int KIND>
+static int32_t launch_linearize(acm_ctx* ctx, const LinParams& hp, const LmState* d_lm, const acm_points* xyz, const acm_points* uv,
+                                double invalid_penalty) {
+    using L = AccLayout<Lin<M, KIND>::ND>;
+    static int blocks_per_sm = 0;
+    if (!blocks_per_sm) {
+        int b = 0;
+        ACM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, linearize_kernel<M, KIND>, 256, 0));
+        blocks_per_sm = b > 0 ? b : 1;
+    }
+    const size_t n = xyz->n;
+    int grid = grid_for(ctx, (n >> 1) + 1, 256, blocks_per_sm);
+    int32_t rc = acm_ensure_partials(ctx, (size_t)ctx->sm_count * 32 * 64);
+    if (rc) return rc;
+    linearize_kernel<M, KIND><<<grid, 256, 0, ctx->stream>>>(
+        hp, d_lm, comp<double2>(xyz, 0), comp<double2>(xyz, 1), comp<double2>(xyz, 2), comp<double2>(uv, 0), comp<double2>(uv, 1), n,
+        2.0 * invalid_penalty * invalid_penalty, ctx->d_partials, ctx->d_reduce, ctx->d_ticket);
+    ACM_CHECK_LAUNCH(ctx);
+    (void)sizeof(L);
+    return ACM_OK;
+}
+
+#define ACM_DISPATCH_LIN(model, kind, ...)                                                                       \
+    do {                                                                                                         \
+        if ((kind) == ACM_RESIDUAL_ALGEBRAIC) {                                                                  \
+            constexpr int KIND = ACM_RESIDUAL_ALGEBRAIC;                                                         \
+            switch (model) {                                                                                     \
+                case ACM_MODEL_UCM: { constexpr int M = ACM_MODEL_UCM; __VA_ARGS__; break; }                     \
+                case ACM_MODEL_EUCM: { constexpr int M = ACM_MODEL_EUCM; __VA_ARGS__; break; }                   \
+                case ACM_MODEL_DOUBLE_SPHERE: { constexpr int M = ACM_MODEL_DOUBLE_SPHERE; __VA_ARGS__; break; } \
+                default: return acm_fail(ctx, ACM_ERR_INVALID_ARG, "the algebraic residual exists only for UCM, EUCM and Double Sphere"); \
+            }                                                                                                    \
+        } else if ((kind) == ACM_RESIDUAL_PIXEL) {                                                               \
+            constexpr int KIND = ACM_RESIDUAL_PIXEL;                                                             \
+            switch (model) {                                                                                     \
+                case ACM_MODEL_PINHOLE: { constexpr int M = ACM_MODEL_PINHOLE; __VA_ARGS__; break; }             \
+                case ACM_MODEL_RADTAN: { constexpr int M = ACM_MODEL_RADTAN; __VA_ARGS__; break; }               \
+                case ACM_MODEL_KANNALA_BRANDT: { constexpr int M = ACM_MODEL_KANNALA_BRANDT; __VA_ARGS__; break; } \
+                case ACM_MODEL_UCM: { constexpr int M = ACM_MODEL_UCM; __VA_ARGS__; break; }                     \
+                case ACM_MODEL_EUCM: { constexpr int M = ACM_MODEL_EUCM; __VA_ARGS__; break; }                   \
+                case ACM_MODEL_DOUBLE_SPHERE: { constexpr int M = ACM_MODEL_DOUBLE_SPHERE; __VA_ARGS__; break; } \
+                case ACM_MODEL_FOV: { constexpr int M = ACM_MODEL_FOV; __VA_ARGS__; break; }                     \
+                default: return acm_fail(ctx, ACM_ERR_INVALID_ARG, "unknown camera model id %d", (int)(model));  \
+            }                                                                                                    \
+        } else return acm_fail(ctx, ACM_ERR_INVALID_ARG, "unknown residual kind %d", (int)(kind));              \
+    } while (0)
+
+static int32_t check_lin_args(acm_ctx* ctx, const acm_camera* cam, const acm_points* xyz, const acm_points* uv) {
+    ACM_REQUIRE(ctx, cam && xyz && uv, "linearize: null argument");
+    ACM_REQUIRE(ctx, xyz->dim == 3 && uv->dim == 2, "linearize: xyz must have dim 3 and uv dim 2");
+    ACM_REQUIRE(ctx, xyz->dtype == ACM_F64 && uv->dtype == ACM_F64, "linearize: f64 point buffers required");
+    if (xyz->n != uv->n) return acm_fail(ctx, ACM_ERR_INVALID_PARAMS, "Number of 2D and 3D points must match");
+    ACM_REQUIRE(ctx, cam->model >= 0 && cam->model <= 6 && cam->n_params == acm_n_params(cam->model), "linearize: bad camera block");
+    return ACM_OK;
+}
+
+static void make_lin_params(const acm_camera* cam, LinParams* p) {
+    memset(p, 0, sizeof(*p));
+    p->fx = cam->params[0]; p->fy = cam->params[1]; p->cx = cam->params[2]; p->cy = cam->params[3];
+    for (int i = 4; i < cam->n_params; ++i) p->d[i - 4] = cam->params[i];
+    lin_derive(cam->model, *p);
+}
+
+static int32_t enqueue_linearize(acm_ctx* ctx, const acm_camera* cam, int32_t kind, const LmState* d_lm, const acm_points* xyz,
+                                 const acm_points* uv, double invalid_penalty, int* nacc) {
+    LinParams hp;
+    make_lin_params(cam, &hp);
+    ACM_DISPATCH_LIN(cam->model, kind, {
+        int32_t rc = launch_linearize<M, KIND>(ctx, hp, d_lm, xyz, uv, invalid_penalty);
+        if (rc) return rc;
+        *nacc = AccLayout<Lin<M, KIND>::ND>::N;
+    });
+    return acm_allreduce_sum_f64(ctx, ctx->d_reduce, (size_t)*nacc);
+}
+
+static int32_t unpack_host(acm_ctx* ctx, const acm_camera* cam, int32_t kind, const double* r, acm_normal_equations* out) {
+    memset(out, 0, sizeof(*out));
+    out->n_params = cam->n_params;
+    double cnt = 0.0;
+    ACM_DISPATCH_LIN(cam->model, kind, (lin_unpack<Lin<M, KIND>::ND, Lin<M, KIND>::UNIT_C>(r, out->H, out->g, &out->cost, &cnt)));
+    out->n_valid = (uint64_t)cnt;
+    return ACM_OK;
+}
+
+extern "C" int32_t acm_linearize_async(acm_ctx* ctx, const acm_camera* cam, int32_t residual_kind, const acm_points* xyz, const acm_points* uv) {
+    if (!ctx) return ACM_ERR_INVALID_ARG;
+    int32_t rc = check_lin_args(ctx, cam, xyz, uv);
+    if (rc) return rc;
+    int nacc = 0;
+    return enqueue_linearize(ctx, cam, residual_kind, nullptr, xyz, uv, 0.0, &nacc);
+}
+
+extern "C" int32_t acm_linearize(acm_ctx* ctx, const acm_camera* cam, int32_t residual_kind, const acm_points* xyz, const acm_points* uv,
+                                 acm_normal_equations* out) {
+    if (!ctx || !out) return ACM_ERR_INVALID_ARG;
+    int32_t rc = check_lin_args(ctx, cam, xyz, uv);
+    if (rc) return rc;
+    int nacc = 0;
+    rc = enqueue_linearize(ctx, cam, residual_kind, nullptr, xyz, uv, 0.0, &nacc);
+    if (rc) return rc;
+    ACM_CUDA(ctx, cudaMemcpyAsync(ctx->h_reduce, ctx->d_reduce, nacc * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    ACM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return unpack_host(ctx, cam, residual_kind, ctx->h_reduce, out);
+}
+
+extern "C" int32_t acm_linearize_host(acm_ctx* ctx, const acm_camera* cam, int32_t residual_kind, const double* xyz_aos, const double* uv_aos,
+                                      size_t n, acm_normal_equations* out) {
+    if (!ctx || !out) return ACM_ERR_INVALID_ARG;
+    ACM_REQUIRE(ctx, cam && (n == 0 || (xyz_aos && uv_aos)), "linearize_host: null argument");
+    acm_points *xyz = nullptr, *uv = nullptr;
+    int32_t rc = acm_points_create(ctx, 3, n, ACM_F64, &xyz);
+    if (!rc) rc = acm_points_create(ctx, 2, n, ACM_F64, &uv);
+    if (!rc) rc = acm_points_upload_any(ctx, xyz, xyz_aos, n, 0);
+    if (!rc) rc = acm_points_upload_any(ctx, uv, uv_aos, n, 0);
+    if (!rc) rc = acm_linearize(ctx, cam, residual_kind, xyz, uv, out);
+    cudaStreamSynchronize(ctx->stream);
+    acm_points_destroy(ctx, xyz);
+    acm_points_destroy(ctx, uv);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------
+// LM step (single thread; P <= 9)
+// ---------------------------------------------------------------------------------------
+__device__ inline bool chol_solve_dev(int P, const double* A, const double* b, double* x) {
+    double Lm[ACM_MAX_PARAMS * ACM_MAX_PARAMS];
+    for (int i = 0; i < P; ++i) {
+        for (int j = 0; j <= i; ++j) {
+            double s = A[i * P + j];
+            for (int k = 0; k < j; ++k) s -= Lm[i * P + k] * Lm[j * P + k];
+            if (i == j) { if (!(s > 0.0)) return false; Lm[i * P + i] = sqrt(s); }
+            else Lm[i * P + j] = s / Lm[j * P + j];
+        }
+    }
+    double yv[ACM_MAX_PARAMS];
+    for (int i = 0; i < P; ++i) { double s = b[i]; for (int k = 0; k < i; ++k) s -= Lm[i * P + k] * yv[k]; yv[i] = s / Lm[i * P + i]; }
+    for (int i = P - 1; i >= 0; --i) { double s = yv[i]; for (int k = i + 1; k < P; ++k) s -= Lm[k * P + i] * x[k]; x[i] = s / Lm[i * P + i]; }
+    return true;
+}
+
+__device__ inline double clampd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+template <int ND, bool UNIT_C>
+__global__ void lm_step_kernel(LmState* __restrict__ s, const double* __restrict__ red) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (s->done) return;
+    constexpr int P = 4 + ND;
+    double Ht[P * P], gt[P], cost_t, cnt;
+    lin_unpack<ND, UNIT_C>(red, Ht, gt, &cost_t, &cnt);
+    s->passes++;
+    bool accepted = false;
+    if (s->first) {
+        s->first = 0;
+        s->initial_cost = cost_t;
+        accepted = true;
+    } else {
+        const bool small_step = s->dnorm <= s->param_tol * (s->xnorm + s->param_tol);
+        if (s->pred > 0.0 && cost_t < s->cost) {
+            const double rho = (s->cost - cost_t) / s->pred;
+            const double dcost = s->cost - cost_t, cost_old = s->cost;
+            const double q = 2.0 * rho - 1.0, f = 1.0 - q * q * q;
+            s->lambda *= (f > 1.0 / 3.0) ? f : 1.0 / 3.0;
+            s->nu = 2.0;
+            if (s->lambda < 1e-15) s->lambda = 1e-15;
+            accepted = true;
+            double gmax = 0.0;
+            for (int i = 0; i < P; ++i) gmax = fmax(gmax, fabs(gt[i]));
+            if (dcost <= s->cost_tol * cost_old) { s->status = 0; s->done = 1; }
+            else if (small_step) { s->status = 1; s->done = 1; }
+            else if (gmax <= s->grad_tol) { s->status = 2; s->done = 1; }
+        } else {
+            if (small_step) { s->status = 1; s->done = 1; }
+            else {
+                s->lambda *= s->nu; s->nu *= 2.0;
+                if (s->lambda > 1e30) { s->status = 4; s->done = 1; }
+            }
+        }
+    }
+    if (accepted) {
+        for (int i = 0; i < P; ++i) { s->x[i] = s->xt[i]; s->g[i] = gt[i]; }
+        for (int i = 0; i < P * P; ++i) s->H[i] = Ht[i];
+        s->cost = cost_t; s->n_valid = cnt;
+    }
+    if (s->done) return;
+    // next trial point from (H, g, lambda) at the accepted x
+    double D[P], A[P * P], gs[P], st[P];
+    for (;;) {
+        if (s->iterations >= s->max_iter) { s->status = 3; s->done = 1; return; }
+        s->iterations++;
+        for (int i = 0; i < P; ++i) { double d = sqrt(s->H[i * P + i]); D[i] = (d > 1e-300) ? d : 1.0; }
+        for (int i = 0; i < P; ++i) {
+            for (int j = 0; j < P; ++j) A[i * P + j] = s->H[i * P + j] / (D[i] * D[j]);
+            A[i * P + i] += s->lambda;
+            gs[i] = -s->g[i] / D[i];
+        }
+        if (chol_solve_dev(P, A, gs, st)) break;
+        s->lambda *= s->nu; s->nu *= 2.0;
+        if (s->lambda > 1e30) { s->status = 4; s->done = 1; return; }
+    }
+    double xnorm = 0.0, dnorm = 0.0, dx[P];
+    for (int i = 0; i < P; ++i) {
+        s->xt[i] = clampd(s->x[i] + st[i] / D[i], s->lower[i], s->upper[i]);
+        dx[i] = s->xt[i] - s->x[i];
+        xnorm += s->x[i] * s->x[i]; dnorm += dx[i] * dx[i];
+    }
+    double pred = 0.0;
+    for (int i = 0; i < P; ++i) {
+        double hd = 0.0;
+        for (int j = 0; j < P; ++j) hd += s->H[i * P + j] * dx[j];
+        pred -= dx[i] * (s->g[i] + 0.5 * hd);
+    }
+    s->xnorm = sqrt(xnorm); s->dnorm = sqrt(dnorm); s->pred = pred;
+}
+
+extern "C" int32_t acm_lm_default_config(acm_lm_config* cfg) {
+    if (!cfg) return ACM_ERR_INVALID_ARG;
+    cfg->max_iterations = 100;        // bin/camera_converter.rs:411
+    cfg->cost_tolerance = 1e-6;       // :412
+    cfg->parameter_tolerance = 1e-8;  // :413
+    cfg->gradient_tolerance = 1e-6;   // :414
+    cfg->lambda0 = 1e-3;
+    cfg->invalid_penalty = 0.0;
+    cfg->check_every = 4;
+    return ACM_OK;
+}
+
+extern "C" int32_t acm_lm_solve(acm_ctx* ctx, const acm_camera* init, int32_t residual_kind, const acm_points* xyz, const acm_points* uv,
+                                const double* lower, const double* upper, const acm_lm_config* cfg_in, double* out_params,
+                                acm_lm_result* result) {
+    if (!ctx || !out_params || !result) return ACM_ERR_INVALID_ARG;
+    int32_t rc = check_lin_args(ctx, init, xyz, uv);
+    if (rc) return rc;
+    acm_lm_config cfg;
+    if (cfg_in) cfg = *cfg_in; else acm_lm_default_config(&cfg);
+    if (cfg.check_every < 1) cfg.check_every = 1;
+    const auto t_start = std::chrono::steady_clock::now();
+    const int P = init->n_params;
+    LmState* h = static_cast<LmState*>(ctx->h_lm);
+    LmState* d = static_cast<LmState*>(ctx->d_lm);
+    memset(h, 0, sizeof(LmState));
+    for (int i = 0; i < P; ++i) {
+        h->lower[i] = lower ? lower[i] : -INFINITY;
+        h->upper[i] = upper ? upper[i] : INFINITY;
+        double v = init->params[i];
+        v = v < h->lower[i] ? h->lower[i] : (v > h->upper[i] ? h->upper[i] : v);
+        h->x[i] = v; h->xt[i] = v;
+    }
+    h->lambda = cfg.lambda0; h->nu = 2.0;
+    h->cost_tol = cfg.cost_tolerance; h->param_tol = cfg.parameter_tolerance; h->grad_tol = cfg.gradient_tolerance;
+    h->max_iter = cfg.max_iterations; h->first = 1; h->P = P; h->status = 3;
+    ACM_CUDA(ctx, cudaMemcpyAsync(d, h, sizeof(LmState), cudaMemcpyHostToDevice, ctx->stream));
+    // the host copy doubles as the read-back buffer: wait until the upload has consumed it
+    ACM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+
+    int nacc = 0;
+    auto one_iteration = [&]() -> int32_t {
+        int32_t r = enqueue_linearize(ctx, init, residual_kind, d, xyz, uv, cfg.invalid_penalty, &nacc);
+        if (r) return r;
+        ACM_DISPATCH_LIN(init->model, residual_kind, (lm_step_kernel<Lin<M, KIND>::ND, Lin<M, KIND>::UNIT_C><<<1, 32, 0, ctx->stream>>>(d, ctx->d_reduce)));
+        ACM_CHECK_LAUNCH(ctx);
+        return ACM_OK;
+    };
+    const int max_passes = cfg.max_iterations + 2;
+    int enq = 0;
+    bool done = false;
+    while (!done && enq < max_passes) {
+        for (int k = 0; k < cfg.check_every && enq < max_passes; ++k, ++enq) {
+            rc = one_iteration();
+            if (rc) return rc;
+        }
+        ACM_CUDA(ctx, cudaMemcpyAsync(h, d, sizeof(LmState), cudaMemcpyDeviceToHost, ctx->stream));
+        ACM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        done = h->done != 0;
+    }
+    for (int i = 0; i < P; ++i) out_params[i] = h->x[i];
+    result->status = h->status; result->iterations = h->iterations; result->passes = h->passes;
+    result->initial_cost = h->initial_cost; result->final_cost = h->cost; result->n_valid = (uint64_t)h->n_valid;
+    result->elapsed_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count();
+    return ACM_OK;
+}
