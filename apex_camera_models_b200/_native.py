@@ -72,6 +72,7 @@ SIGNATURES = {
     "acm_host_free_pinned": (C.c_int32, [_vp, _vp]),
     "acm_memcpy_h2d": (C.c_int32, [_vp, _vp, _vp, C.c_size_t]),
     "acm_memcpy_d2h": (C.c_int32, [_vp, _vp, _vp, C.c_size_t]),
+    "acm_memcpy_d2d": (C.c_int32, [_vp, _vp, _vp, C.c_size_t]),
     "acm_memset_d": (C.c_int32, [_vp, _vp, C.c_int, C.c_size_t]),
     "acm_points_create": (C.c_int32, [_vp, C.c_int32, C.c_size_t, C.c_int32, C.POINTER(_vp)]),
     "acm_points_destroy": (C.c_int32, [_vp, _vp]),

@@ -279,6 +279,11 @@ extern "C" int32_t acm_memcpy_d2h(acm_ctx* ctx, void* dst, const void* src, size
     ACM_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     return ACM_OK;
 }
+extern "C" int32_t acm_memcpy_d2d(acm_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return ACM_OK;
+}
 extern "C" int32_t acm_memset_d(acm_ctx* ctx, void* dst, int value, size_t bytes) {
     if (!ctx) return ACM_ERR_INVALID_ARG;
     ACM_CUDA(ctx, cudaMemsetAsync(dst, value, bytes, ctx->stream));

@@ -10,6 +10,8 @@
 // fixed shuffle tree, per-block partials, the last block to finish sums the partials in
 // block order.  No floating-point atomics.  The result depends on the grid size only.
 #include "acm_linearize.cuh"
+#include "acm_reduce.cuh"
+#include "acm_models.cuh"
 
 #include <chrono>
 
@@ -71,53 +73,9 @@ __global__ void __launch_bounds__(256) linearize_kernel(LinParams hp, const LmSt
         if (LM_::eval(p, Xs[t], Ys[t], Zs[t], Us[t], Vs[t], ru, rv, au, av)) lin_accumulate<ND, UNIT_C>(acc, ru, rv, au, av);
     }
 
-    // warp tree -> shared -> block partial
-    __shared__ double sm[8][NACC];
-    __shared__ bool is_last;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int i = 0; i < NACC; ++i) {
-        double v = acc[i];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if (lane == 0) sm[warp][i] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < NACC) {
-        double s = sm[0][threadIdx.x];
-#pragma unroll
-        for (int w = 1; w < 8; ++w) s += sm[w][threadIdx.x];
-        partials[(size_t)blockIdx.x * NACC + threadIdx.x] = s;
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned int t = atomicAdd(ticket, 1u);
-        is_last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    // final pass: 4 contiguous block ranges x NACC accumulators, combined in fixed order
-    {
-        const int a = threadIdx.x & 63, sub = threadIdx.x >> 6;
-        const unsigned int nb = gridDim.x;
-        const unsigned int b0 = (unsigned int)(((size_t)nb * sub) / 4), b1 = (unsigned int)(((size_t)nb * (sub + 1)) / 4);
-        double s = 0.0;
-        if (a < NACC)
-            for (unsigned int b = b0; b < b1; ++b) s += __ldcg(partials + (size_t)b * NACC + a);
-        __shared__ double fin4[4][64];
-        fin4[sub][a] = s;
-        __syncthreads();
-        if (threadIdx.x < NACC) {
-            double tot = ((fin4[0][threadIdx.x] + fin4[1][threadIdx.x]) + fin4[2][threadIdx.x]) + fin4[3][threadIdx.x];
-            if (threadIdx.x == L::COST) {
-                double cnt = ((fin4[0][L::COUNT] + fin4[1][L::COUNT]) + fin4[2][L::COUNT]) + fin4[3][L::COUNT];
-                tot += pen2x2 * ((double)n - cnt);  // invalid points carry residual (pen, pen)
-            }
-            out[threadIdx.x] = tot;
-        }
-        if (threadIdx.x == 0) *ticket = 0;  // re-arm for the next launch on this stream
+    if (GridReduce<NACC, 0, 0>::run(acc, partials, out, ticket)) {
+        // invalid points carry the residual (pen, pen): cost += pen^2 per invalid point
+        if (threadIdx.x == 0 && pen2x2 != 0.0) out[L::COST] += pen2x2 * ((double)n - out[L::COUNT]);
     }
 }
 
@@ -399,5 +357,61 @@ extern "C" int32_t acm_lm_solve(acm_ctx* ctx, const acm_camera* init, int32_t re
     result->status = h->status; result->iterations = h->iterations; result->passes = h->passes;
     result->initial_cost = h->initial_cost; result->final_cost = h->cost; result->n_valid = (uint64_t)h->n_valid;
     result->elapsed_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count();
+    return ACM_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// project with `compute_jacobian = true` (README-era trait surface, reference README.md:119-126;
+// per-model doc-comments double_sphere.rs:326-332 "2x6", kannala_brandt.rs:309-313 "2x8"):
+// uv + the 2xP Jacobian w.r.t. [fx,fy,cx,cy,dist..], written as 2P rows of n doubles.
+// ---------------------------------------------------------------------------------------
+template <int M>
+__global__ void __launch_bounds__(256) project_jacobian_kernel(const __grid_constant__ CamParams c, LinParams p, const double* __restrict__ X,
+                                                               const double* __restrict__ Y, const double* __restrict__ Z,
+                                                               double* __restrict__ U, double* __restrict__ V, double* __restrict__ J,
+                                                               uint8_t* __restrict__ S, size_t n) {
+    using LM_ = Lin<M, ACM_RESIDUAL_PIXEL>;
+    constexpr int ND = LM_::ND, P = 4 + ND;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double x = X[i], y = Y[i], z = Z[i];
+        double u, v;
+        int st = CamModel<M>::template project<false>(c, x, y, z, u, v);
+        double ru, rv, au[2 + ND], av[2 + ND];
+        double row_u[P], row_v[P];
+#pragma unroll
+        for (int k = 0; k < P; ++k) row_u[k] = row_v[k] = 0.0;
+        if (st == ACM_POINT_OK && LM_::eval(p, x, y, z, 0.0, 0.0, ru, rv, au, av)) {
+            row_u[0] = au[0]; row_u[2] = 1.0; row_v[1] = av[0]; row_v[3] = 1.0;
+#pragma unroll
+            for (int k = 0; k < ND; ++k) { row_u[4 + k] = au[2 + k]; row_v[4 + k] = av[2 + k]; }
+        } else {
+            if (st == ACM_POINT_OK) st = ACM_POINT_NUMERICAL_ERROR;
+            u = v = acm_nan();
+        }
+        U[i] = u; V[i] = v;
+        if (S) S[i] = (uint8_t)st;
+#pragma unroll
+        for (int k = 0; k < P; ++k) { J[(size_t)k * n + i] = row_u[k]; J[(size_t)(P + k) * n + i] = row_v[k]; }
+    }
+}
+
+extern "C" int32_t acm_project_jacobian(acm_ctx* ctx, const acm_camera* cam, const acm_points* xyz, acm_points* uv, double* d_jac,
+                                        uint8_t* d_status) {
+    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_REQUIRE(ctx, cam && xyz && uv && d_jac, "project_jacobian: null argument");
+    ACM_REQUIRE(ctx, xyz->dim == 3 && uv->dim == 2 && xyz->n == uv->n, "project_jacobian: shape mismatch");
+    ACM_REQUIRE(ctx, xyz->dtype == ACM_F64 && uv->dtype == ACM_F64, "project_jacobian: f64 buffers required");
+    CamParams c;
+    int32_t rc = acm_make_cam_params(ctx, cam, &c);
+    if (rc) return rc;
+    LinParams p;
+    make_lin_params(cam, &p);
+    const size_t n = xyz->n;
+    if (n == 0) return ACM_OK;
+    int grid = grid_for(ctx, n, 256, 4);
+    ACM_DISPATCH_MODEL(cam->model, (project_jacobian_kernel<M><<<grid, 256, 0, ctx->stream>>>(
+        c, p, comp<double>(xyz, 0), comp<double>(xyz, 1), comp<double>(xyz, 2), comp<double>(uv, 0), comp<double>(uv, 1), d_jac, d_status, n)))
+    ACM_CHECK_LAUNCH(ctx);
     return ACM_OK;
 }

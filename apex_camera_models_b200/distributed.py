@@ -1,0 +1,44 @@
+"""Multi-GPU plumbing: one process per GPU (torchrun), points sharded by contiguous ranges, the
+only collective is the all-reduce of the normal equations inside libacm (NCCL over NVLink).
+torch.distributed is used for the rendezvous only: it carries the 128-byte NCCL unique id."""
+from __future__ import annotations
+
+import os
+
+from .runtime import Context
+
+
+def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous range [lo, hi) of rank `rank`: [r*n/G, (r+1)*n/G)."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank / world size")
+    return (n * rank) // world, (n * (rank + 1)) // world
+
+
+def env_rank_world() -> tuple[int, int, int]:
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def broadcast_bytes(payload: bytes | None, nbytes: int, src: int = 0) -> bytes:
+    """Broadcast a fixed-size byte string over the default torch.distributed group (any backend)."""
+    import torch
+    import torch.distributed as dist
+    backend = dist.get_backend()
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    t = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+    if dist.get_rank() == src:
+        t.copy_(torch.frombuffer(bytearray(payload), dtype=torch.uint8))
+    dist.broadcast(t, src=src)
+    return bytes(t.cpu().numpy().tobytes())
+
+
+def attach_communicator(ctx: Context) -> int:
+    """Give `ctx` an NCCL communicator spanning the torch.distributed world. Returns world size."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if world == 1:
+        return 1
+    uid = Context.comm_unique_id() if rank == 0 else None
+    uid = broadcast_bytes(uid, 128, src=0)
+    ctx.comm_init_rank(world, rank, uid)
+    return world

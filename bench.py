@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native hot path of apex-camera-models.
+
+Metric (BASELINE.json): points/sec of the fused project + analytical Jacobian + J^T J / J^T r
+pass.  Workload (BASELINE.json configs[2]): 100 M synthetic f64 correspondences per GPU, Double
+Sphere model, pixel residual (project(X) - uv), inputs resident in HBM as SoA.  One step = one
+streaming pass over the rank's shard (one kernel) + -- when N > 1 -- the NCCL all-reduce of the
+29-double normal equations.  Weak scaling: every rank holds its own 100 M points.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port)
+
+Prints ONE JSON line on rank 0.  Timing: CUDA events on the launching stream, barrier +
+synchronize on both sides, max over ranks.  Inputs (4 GB per rank) are far larger than the 126 MB
+L2, so no explicit flush is needed between iterations.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "points/sec project+Jacobian (fused project + analytical Jacobian + J^T J/J^T r)"
+UNIT = "points/s"
+N_POINTS = 100_000_000          # per GPU (BASELINE.json configs[2])
+BYTES_PER_POINT = 40            # 24 B xyz + 16 B uv read per point per pass
+SEED = 0xACE50003
+COS_MAX = float(np.cos(np.deg2rad(85.0)))
+KB_SAMPLE = [190.97847715128717, 190.9733070521226, 254.93170605935475, 256.8974428996504,
+             0.0034823894022493434, 0.0007150348452162257, -0.0020532361418706202, 0.00020293673591811182]
+DS_START = KB_SAMPLE[:4] + [0.6, 0.1]  # KB intrinsics with a Double Sphere guess: a model-mismatch fit like the converter's
+
+
+def workload_config(n_gpus):
+    return {"workload": "fused linearize (project + Jacobian + JtJ/Jtr), Double Sphere, pixel residual, f64 SoA",
+            "camera_model": "double_sphere", "residual": "pixel", "points_per_gpu": N_POINTS, "global_points": N_POINTS * n_gpus,
+            "correspondences": "X: seeded cone 85deg; uv = KannalaBrandt(samples/kannala_brandt.yaml).project(X)",
+            "l2_policy": "inputs (4 GB/GPU) larger than L2", "parallelism": f"dp{n_gpus} (points sharded, all-reduce of 29 f64)"}
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi in the background (B200_PROFILING.md clocks line)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.samples = []
+        self.gpu = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        def pump():
+            for line in self.proc.stdout:
+                self.samples.append((time.time(), line.strip()))
+        threading.Thread(target=pump, daemon=True).start()
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+    def summary(self, t0, t1):
+        rows = []
+        for ts, line in self.samples:
+            if t0 <= ts <= t1:
+                f = [x.strip() for x in line.split(",")]
+                if len(f) >= 9:
+                    rows.append(f)
+        if not rows:
+            return None
+        sm = sorted(float(r[1]) for r in rows)
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            for name, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "power_w_max": max(float(r[3]) for r in rows),
+                "reasons": sorted(reasons), "samples": len(rows)}
+
+
+def cpu_baseline(n_sample, min_seconds, nthreads):
+    """The reference's algorithm for this path on the host: per-point residual + Jacobian
+    materialised, then J^T J / J^T r (oracle port; the Rust reference cannot be built here)."""
+    from oracle import oracle as O
+    O.build()
+    kb = O.make_model(O.KB, KB_SAMPLE, 512, 512)
+    ds = O.make_model(O.DS, DS_START, 512, 512)
+    xyz = O.synth_points3(SEED, 0, n_sample, COS_MAX, False)
+    uv, _ = O.project(kb, xyz, nthreads=max(nthreads, 1))
+    O.linearize(ds, O.RES_PIXEL, xyz[:100000], uv[:100000], nthreads=nthreads)  # warm
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        O.linearize(ds, O.RES_PIXEL, xyz, uv, nthreads=nthreads)
+        reps += 1
+        el = time.perf_counter() - t0
+        if el >= min_seconds and reps >= 1:
+            break
+    return n_sample * reps / el, reps, el
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    n_sample = 10_000_000
+    vals = []
+    for _ in range(max(args.warmup, 0)):
+        cpu_baseline(200_000, 0.0, 1)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        v, _, _ = cpu_baseline(n_sample, 0.0, 1)
+        vals.append(v)
+        if time.perf_counter() - t0 > 150:
+            break
+    value = float(np.median(vals))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
+            "ms_per_step": 1e3 * n_sample / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": f"{n_sample} of the 100M correspondences per step; oracle C port of the reference algorithm (dense J then J^T J), gcc -O2 -ffp-contract=off, 1 thread (the reference is single-threaded Rust; no Rust toolchain in this image)"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import ctypes as C
+    import torch
+    import apex_camera_models_b200 as acm
+    from apex_camera_models_b200 import _native as N
+    lib = N.lib
+    rank, local_rank, world = acm.distributed.env_rank_world()
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    ctx = acm.Context(local_rank)
+    if world > 1:
+        acm.attach_communicator(ctx)
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            dist.barrier()
+        ctx.sync()
+
+    n = args.points
+    # --- inputs generated in HBM: X from the seeded generator (rank-specific range), uv = KB.project(X)
+    kb = acm.KannalaBrandtModel(acm.Intrinsics(*KB_SAMPLE[:4]), acm.Resolution(512, 512), KB_SAMPLE[4:], ctx=ctx)
+    ds = acm.DoubleSphereModel(acm.Intrinsics(*DS_START[:4]), acm.Resolution(512, 512), DS_START[4:], ctx=ctx)
+    X = acm.Points(ctx, 3, n)
+    ctx.check(lib.acm_synth_points3(ctx.handle, SEED, rank * n, COS_MAX, 0, X.handle))
+    UV, st = kb.project_batch(X)
+    ctx.device_free(st)
+    cam = ds.camera_block()
+
+    def step():
+        ctx.check(lib.acm_linearize_async(ctx.handle, C.byref(cam), N.RESIDUAL_PIXEL, X.handle, UV.handle))
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    launches0 = ctx.kernel_launches()
+    wall0 = time.time()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        step()
+    ms = ctx.timer_stop()
+    barrier()
+    wall1 = time.time()
+    launches = ctx.kernel_launches() - launches0
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = n * world / (ms_per_step * 1e-3)
+
+    clocks = sampler.summary(wall0, wall1) if rank == 0 else None
+    probe = (wall1 - wall0) < 0.4  # same decision on every rank is not guaranteed by wall clocks -> agree on it
+    if dist is not None:
+        t = torch.tensor([1.0 if probe else 0.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        probe = bool(t.item() > 0)
+    if probe:
+        # timed region shorter than the sampling period: run the same step for ~0.6 s on every rank
+        n_probe = int(max(20, min(20000, 600.0 / max(ms_per_step, 1e-3))))
+        p0 = time.time()
+        for _ in range(n_probe):
+            step()
+        barrier()
+        if rank == 0:
+            clocks = sampler.summary(p0, time.time()) or clocks or {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+            clocks["sampled"] = "probe loop of the same step right after the timed region (timed region < 0.4 s)"
+
+    # --- result of the last pass (also the d2h payload of the e2e path)
+    ne = N.NormalEquations()
+    ctx.check(lib.acm_linearize(ctx.handle, C.byref(cam), N.RESIDUAL_PIXEL, X.handle, UV.handle, C.byref(ne)))
+
+    # --- e2e: host AoS buffers (nalgebra layout, pinned) through acm_linearize_host, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        ne_pts = min(n, args.e2e_points)
+        hx = ctx.pinned_empty((ne_pts, 3), np.float64)
+        hu = ctx.pinned_empty((ne_pts, 2), np.float64)
+        # fill the host buffers from the device data (download is outside the timed region)
+        Xs = acm.Points(ctx, 3, ne_pts); Us = acm.Points(ctx, 2, ne_pts)
+        for c in range(3):
+            ctx.d2d(Xs.component_ptr(c), X.component_ptr(c), 8 * ne_pts)
+        for c in range(2):
+            ctx.d2d(Us.component_ptr(c), UV.component_ptr(c), 8 * ne_pts)
+        ctx.check(lib.acm_points_download_aos_f64(ctx.handle, Xs.handle, hx.ctypes.data_as(C.c_void_p), ne_pts))
+        ctx.check(lib.acm_points_download_aos_f64(ctx.handle, Us.handle, hu.ctypes.data_as(C.c_void_p), ne_pts))
+        Xs.free(); Us.free()
+        ne2 = N.NormalEquations()
+        def e2e_step():
+            ctx.check(lib.acm_linearize_host(ctx.handle, C.byref(cam), N.RESIDUAL_PIXEL, hx.ctypes.data_as(C.c_void_p), hu.ctypes.data_as(C.c_void_p),
+                                             ne_pts, C.byref(ne2)))
+        e2e_step()
+        barrier()
+        k = max(1, min(args.steps, args.e2e_steps))
+        t0 = time.perf_counter()
+        for _ in range(k):
+            e2e_step()
+        barrier()
+        el = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([el], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            el = float(t.item())
+        e2e = {"value": ne_pts * world * k / el, "unit": UNIT, "h2d_bytes_per_step": ne_pts * BYTES_PER_POINT,
+               "d2h_bytes_per_step": 29 * 8, "steps": k, "points_per_gpu": ne_pts,
+               "api": "acm_linearize_host (pinned nalgebra-layout AoS f64 -> chunked H2D + AoS->SoA + fused pass -> normal equations)"}
+        ctx.pinned_free(hx); ctx.pinned_free(hu)
+
+    extras = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        extras = run_extras(acm, N, lib, ctx, X, UV, n)
+
+    # --- LM conversion (BASELINE config 4): KB -> Double Sphere, 10 M correspondences sharded over the ranks
+    lm = None
+    if not args.no_lm:
+        n_lm_total = 10_000_000
+        lo, hi = acm.shard_range(n_lm_total, rank, world)
+        m = hi - lo
+        Xl = acm.Points(ctx, 3, m); Ul = acm.Points(ctx, 2, m)
+        ctx.check(lib.acm_synth_points3(ctx.handle, 0xACE50004, lo, COS_MAX, 0, Xl.handle))
+        cam_kb = kb.camera_block()
+        ctx.check(lib.acm_project(ctx.handle, C.byref(cam_kb), Xl.handle, Ul.handle, None))
+        dsl = acm.DoubleSphereModel(acm.Intrinsics(*KB_SAMPLE[:4]), acm.Resolution(512, 512), [0.5, 0.1], ctx=ctx)
+        cost = acm.DoubleSphereOptimizationCost(dsl, Xl, Ul)  # canonical (algebraic) residual, converter bounds
+        barrier()
+        cost.linear_estimation()  # Gram sums are combined over the ranks inside libacm
+        start = dsl.params().copy()
+        cost.optimize()      # warm-up solve
+        dsl.set_params(start)
+        barrier()
+        r = cost.optimize()
+        barrier()
+        ms_lm = r.elapsed_ms
+        if dist is not None:
+            t = torch.tensor([ms_lm], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_lm = float(t.item())
+        lm = {"workload": "KB->DoubleSphere LM, 10M correspondences (algebraic residual, converter tolerances/bounds)", "ms": ms_lm,
+              "iterations": r.iterations, "passes": r.passes, "status": r.status, "us_per_pass": 1e3 * ms_lm / max(r.passes, 1),
+              "params": [float(v) for v in r.parameters], "final_cost": r.final_cost, "points_per_gpu": m}
+        Xl.free(); Ul.free()
+
+    if rank == 0:
+        sampler.stop()
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback, B200_PROFILING.md)"
+        achieved = n * BYTES_PER_POINT / (ms_per_step * 1e-3) / 1e9  # per GPU; at N>1 the step also holds the all-reduce
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("linearize_ds_pixel_bytes_per_launch")
+        except (OSError, ValueError):
+            pass
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": workload_config(world), "gpu_launches": int(launches), "clocks": clocks,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                             "kernel": "linearize_kernel<DOUBLE_SPHERE, PIXEL>", "algorithmic_bytes_per_launch": n * BYTES_PER_POINT,
+                             "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0},
+                "e2e": e2e, "lm_conversion": lm,
+                "check": {"n_valid": int(ne.n_valid), "cost": float(ne.cost), "H00": float(ne.H[0])}}
+        if world == 1 and not args.no_cpu:
+            v1, reps, el = cpu_baseline(args.cpu_points, 10.0, 1)
+            ncores = os.cpu_count() or 1
+            vall, _, _ = cpu_baseline(args.cpu_points, 3.0, ncores)
+            line["cpu_baseline"] = {"value": v1, "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": f"{args.cpu_points} of the 100M correspondences x {reps} passes ({el:.1f} s); oracle C port (dense J, then J^T J), 1 thread like the single-threaded reference",
+                                    "all_cores": {"value": vall, "cores": ncores, "note": "OpenMP over every host core: a generous upper bound the reference does not have"}}
+        if extras:
+            line["extras"] = extras
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_extras(acm, N, lib, ctx, X, UV, n):
+    """Other kernels of the path on the same 100 M points (explanatory, N=1 only)."""
+    import ctypes as C
+    out = {}
+    def timeit(fn, reps=10):
+        for _ in range(3):
+            fn()
+        ctx.sync(); ctx.timer_start()
+        for _ in range(reps):
+            fn()
+        return ctx.timer_stop() / reps
+    intr = KB_SAMPLE[:4]
+    dist_init = {0: [], 1: [0.01, 0.001, 0.0, 0.0, 0.0], 2: KB_SAMPLE[4:], 3: [0.6], 4: [0.6, 1.0], 5: [0.6, 0.1], 6: [0.9]}
+    names = {0: "pinhole", 1: "rad_tan", 2: "kannala_brandt", 3: "ucm", 4: "eucm", 5: "double_sphere", 6: "fov"}
+    lin = {}
+    for mid in (5, 4, 3, 2, 6, 1, 0):
+        m = acm.MODEL_CLASSES[mid](acm.Intrinsics(*intr), acm.Resolution(512, 512), dist_init[mid], ctx=ctx)
+        cam = m.camera_block()
+        for kind, kname in ((0, "pixel"), (1, "algebraic")):
+            if kind == 1 and mid not in (3, 4, 5):
+                continue
+            ms = timeit(lambda: ctx.check(lib.acm_linearize_async(ctx.handle, C.byref(cam), kind, X.handle, UV.handle)))
+            lin[f"{names[mid]}/{kname}"] = {"ms": ms, "gpts_s": n / ms / 1e6, "gb_s": n * 40 / ms / 1e6}
+    out["linearize_100M"] = lin
+    pu = {}
+    UV2 = acm.Points(ctx, 2, n); X2 = acm.Points(ctx, 3, n)
+    st = ctx.device_alloc(n)
+    for mid in range(7):
+        m = acm.MODEL_CLASSES[mid](acm.Intrinsics(*intr), acm.Resolution(512, 512), dist_init[mid], ctx=ctx)
+        cam = m.camera_block()
+        ms = timeit(lambda: ctx.check(lib.acm_project(ctx.handle, C.byref(cam), X.handle, UV2.handle, C.c_void_p(st))))
+        ctx.check(lib.acm_synth_pixels(ctx.handle, 7, 0, 512.0, 512.0, UV2.handle))
+        ms2 = timeit(lambda: ctx.check(lib.acm_unproject(ctx.handle, C.byref(cam), UV2.handle, X2.handle, C.c_void_p(st))))
+        pu[names[mid]] = {"project_ms": ms, "project_gb_s": n * 41 / ms / 1e6, "unproject_ms": ms2, "unproject_gb_s": n * 41 / ms2 / 1e6}
+    out["project_unproject_100M_f64"] = pu
+    ctx.device_free(st); UV2.free(); X2.free()
+    # undistort: 4096x4096 KB fisheye (sample intrinsics x8), 8 frames resident in HBM
+    W = H = 4096
+    kb8 = acm.KannalaBrandtModel(acm.Intrinsics(*(v * 8 for v in KB_SAMPLE[:4])), acm.Resolution(W, H), KB_SAMPLE[4:], ctx=ctx)
+    cam = kb8.camera_block()
+    F = 8
+    fb = W * H * 3
+    d_in = ctx.device_alloc(fb * F); d_out = ctx.device_alloc(fb * F)
+    ctx.check(lib.acm_synth_bytes(ctx.handle, 0xACE50005, 0, C.c_void_p(d_in), fb * F))
+    ms = timeit(lambda: ctx.check(lib.acm_undistort_rgb8(ctx.handle, C.byref(cam), None, C.c_void_p(d_in), C.c_void_p(d_out), F, 1)), reps=5)
+    out["undistort_4096x4096_kb_bilinear"] = {"frames": F, "ms": ms, "frames_s": F / ms * 1e3, "gb_s": 2 * fb * F / ms / 1e6}
+    ctx.device_free(d_in); ctx.device_free(d_out)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--points", type=int, default=N_POINTS, help="points per GPU")
+    ap.add_argument("--e2e-points", type=int, default=N_POINTS)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-points", type=int, default=20_000_000)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-lm", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

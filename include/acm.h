@@ -117,6 +117,7 @@ int32_t acm_host_alloc_pinned(acm_ctx* ctx, size_t bytes, void** out);
 int32_t acm_host_free_pinned(acm_ctx* ctx, void* p);
 int32_t acm_memcpy_h2d(acm_ctx* ctx, void* dst, const void* src, size_t bytes); /* async on ctx stream */
 int32_t acm_memcpy_d2h(acm_ctx* ctx, void* dst, const void* src, size_t bytes); /* async on ctx stream */
+int32_t acm_memcpy_d2d(acm_ctx* ctx, void* dst, const void* src, size_t bytes); /* async on ctx stream */
 int32_t acm_memset_d(acm_ctx* ctx, void* dst, int value, size_t bytes);
 
 /* ---- device point buffers (SoA, components 256-byte aligned) --------------------------- */

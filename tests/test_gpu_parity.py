@@ -1,0 +1,520 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI of include/acm.h) against the CPU
+oracle on the same seeded inputs, against the committed golden fixtures, and at BASELINE sizes
+through size-independent properties.
+
+Bars (BASELINE.json north_star): status masks, kept sets, remap indices and output bytes are
+bit-exact; f64 values within 1e-9 relative; the f32-I/O path within 1e-4 px (or half an f32 ulp
+of the coordinate where that is larger).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, oracle_model
+
+pytestmark = pytest.mark.gpu
+
+MODELS = ["pinhole", "rad_tan", "kannala_brandt", "ucm", "eucm", "double_sphere", "fov"]
+EXACT = {"pinhole", "rad_tan", "ucm", "eucm", "double_sphere"}  # +,-,*,/,sqrt only => bit-exact values
+UNIFIED = {"ucm", "eucm", "double_sphere"}
+RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def acm():
+    import apex_camera_models_b200 as m
+    return m
+
+
+@pytest.fixture(scope="module")
+def ctx(acm):
+    c = acm.Context(0)
+    yield c
+    c.close()
+
+
+def gpu_model(acm, ctx, cam):
+    cls = acm.MODEL_CLASSES[cam["model_id"]]
+    return cls(acm.Intrinsics(*cam["params"][:4]), acm.Resolution(cam["width"], cam["height"]), cam["params"][4:], ctx=ctx)
+
+
+def cone(name):
+    return np.cos(np.deg2rad(40.0 if name in ("pinhole", "rad_tan") else 100.0))
+
+
+def assert_close_where_valid(a, b, ok, name, exact_names=EXACT):
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    if name in exact_names:
+        assert np.array_equal(a[ok], b[ok]), f"{name}: values are not bit-identical"
+    else:
+        assert np.allclose(a[ok], b[ok], rtol=RTOL, atol=1e-13)
+
+
+# ------------------------------------------------------------------ project / unproject ----------
+@pytest.mark.parametrize("name", MODELS)
+def test_project_matches_oracle(acm, ctx, O, cameras, name):
+    cam = cameras[name]
+    m, om = gpu_model(acm, ctx, cam), oracle_model(O, cam)
+    n = 100_003  # ragged: not a multiple of the 2-point packets
+    xyz = O.synth_points3(0xACE50002, 0, n, cone(name), True)
+    uv, st = m.project_batch(xyz)
+    uvo, sto = O.project(om, xyz)
+    assert np.array_equal(st, sto), "status mask must be bit-exact"
+    assert len(np.unique(sto)) >= 2
+    assert_close_where_valid(uv, uvo, sto == 0, name)
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_unproject_matches_oracle(acm, ctx, O, cameras, name):
+    cam = cameras[name]
+    m, om = gpu_model(acm, ctx, cam), oracle_model(O, cam)
+    n = 100_003
+    px = O.synth_pixels(0xACE50002, 0, n, cam["width"] * 1.05, cam["height"] * 1.05)  # some outside the image
+    px[:4] = [[0.0, 0.0], [cam["params"][2], cam["params"][3]], [cam["width"], 1.0], [cam["params"][2] + 0.5e-6 * cam["params"][0], cam["params"][3]]]
+    ray, st = m.unproject_batch(px)
+    rayo, sto = O.unproject(om, px)
+    assert np.array_equal(st, sto)
+    assert_close_where_valid(ray, rayo, sto == 0, name)
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 5, 255, 256, 257, 511, 513])
+def test_edge_sizes(acm, ctx, O, cameras, n):
+    for name in ("double_sphere", "kannala_brandt"):
+        cam = cameras[name]
+        m, om = gpu_model(acm, ctx, cam), oracle_model(O, cam)
+        xyz = O.synth_points3(11, 0, n, cone(name), True).reshape(n, 3)
+        uv, st = m.project_batch(xyz)
+        uvo, sto = O.project(om, xyz)
+        assert uv.shape == (n, 2) and np.array_equal(st, sto)
+        assert_close_where_valid(uv, uvo, sto == 0, name)
+        px = O.synth_pixels(12, 0, n, cam["width"], cam["height"]).reshape(n, 2)
+        ray, st = m.unproject_batch(px)
+        rayo, sto = O.unproject(om, px)
+        assert ray.shape == (n, 3) and np.array_equal(st, sto)
+        assert_close_where_valid(ray, rayo, sto == 0, name)
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_f32_io_path(acm, ctx, O, cameras, name):
+    """f32 I/O, f64 math, one final rounding: compare with the f64 oracle evaluated on the same
+    f32-rounded inputs.  Tolerance max(1e-4 px, 0.5 ulp_f32(coordinate))."""
+    from apex_camera_models_b200 import _native as N
+    cam = cameras[name]
+    m, om = gpu_model(acm, ctx, cam), oracle_model(O, cam)
+    n = 50_001
+    xyz = O.synth_points3(0xACE50002, 7, n, cone(name), True).astype(np.float32).astype(np.float64)
+    uv, st = m.project_batch(xyz, dtype=N.F32)
+    uvo, sto = O.project(om, xyz)
+    assert np.array_equal(st, sto)
+    ok = sto == 0
+    tol = np.maximum(1e-4, 0.5 * np.spacing(np.abs(uvo[ok]).astype(np.float32)).astype(np.float64))
+    assert np.all(np.abs(uv[ok] - uvo[ok]) <= tol)
+    px = O.synth_pixels(3, 0, n, cam["width"], cam["height"]).astype(np.float32).astype(np.float64)
+    ray, st = m.unproject_batch(px, dtype=N.F32)
+    rayo, sto = O.unproject(om, px)
+    assert np.array_equal(st, sto)
+    assert np.all(np.abs(ray[sto == 0] - rayo[sto == 0]) <= 1e-7)
+
+
+def test_synthetic_generators_are_bit_identical(acm, ctx, O):
+    from apex_camera_models_b200 import _native as N
+    lib = N.lib
+    n = 70_001
+    for cosmax, adv, i0 in [(cone("kb"), 1, 0), (cone("pinhole"), 0, 12345), (np.cos(np.deg2rad(85.0)), 0, 10**9)]:
+        p = acm.Points(ctx, 3, n)
+        ctx.check(lib.acm_synth_points3(ctx.handle, 0xACE50003, i0, cosmax, adv, p.handle))
+        assert np.array_equal(p.numpy(), O.synth_points3(0xACE50003, i0, n, cosmax, bool(adv)))
+    q = acm.Points(ctx, 2, n)
+    ctx.check(lib.acm_synth_pixels(ctx.handle, 5, 17, 752.0, 480.0, q.handle))
+    assert np.array_equal(q.numpy(), O.synth_pixels(5, 17, n, 752.0, 480.0))
+    nb = 100_003
+    d = ctx.device_alloc(nb)
+    ctx.check(lib.acm_synth_bytes(ctx.handle, 0xACE50005, 3, C.c_void_p(d), nb))
+    out = np.empty(nb, np.uint8); ctx.d2h(out, d); ctx.sync(); ctx.device_free(d)
+    assert np.array_equal(out, O.synth_bytes(0xACE50005, 3, nb))
+
+
+def test_golden_vectors_on_gpu(acm, ctx, cameras):
+    """tests/golden/restated_kats.json and the OpenCV cross-check, through the CUDA path."""
+    kat = load_golden("restated_kats.json")
+    for row in kat["project_unproject"]:
+        m = gpu_model(acm, ctx, cameras[row["camera"]])
+        uv = m.project(row["point"])
+        if row["camera"] in EXACT:
+            assert uv.tolist() == row["uv"]
+        else:
+            assert np.allclose(uv, row["uv"], rtol=1e-13)
+        if row.get("ray"):
+            assert np.allclose(m.unproject(uv), row["ray"], rtol=1e-12, atol=1e-16)
+    cv = load_golden("opencv_cross.json")
+    for name in ("kannala_brandt", "kannala_brandt_inline", "rad_tan", "pinhole"):
+        cam = dict(cameras[name]); cam["width"] = cam["height"] = 100000  # OpenCV has no bounds test
+        m = gpu_model(acm, ctx, cam)
+        pts = np.array(cv[name]["points"])
+        if name in ("rad_tan", "pinhole"):
+            # shift the principal point so that every projection is inside the (huge) image
+            cam["params"] = list(cam["params"]); cam["params"][2] += 50000.0; cam["params"][3] += 50000.0
+            m = gpu_model(acm, ctx, cam)
+            ref = np.array(cv[name]["uv"]) + 50000.0
+        else:
+            ref = np.array(cv[name]["uv"])
+        uv, st = m.project_batch(pts)
+        assert np.all(st == 0) and np.max(np.abs(uv - ref)) < 1e-9
+
+
+def test_reference_unit_tests_through_the_trait_surface(acm, ctx, cameras):
+    """The reference's error-classification tests (double_sphere.rs:782-801, kannala_brandt.rs:948-974,
+    fov.rs:648-666, tests/projection_accuracy.rs) through CameraModel.project / unproject."""
+    ds = gpu_model(acm, ctx, cameras["double_sphere"])
+    kb = gpu_model(acm, ctx, cameras["kannala_brandt_inline"])
+    fov = gpu_model(acm, ctx, cameras["fov"])
+    for m in (ds, gpu_model(acm, ctx, cameras["ucm"]), gpu_model(acm, ctx, cameras["eucm"]), kb):
+        with pytest.raises(acm.PointIsOutSideImage):
+            m.project([0.1, 0.2, -1.0])
+    with pytest.raises(acm.PointAtCameraCenter):
+        fov.project([0.1, 0.2, -1.0])
+    with pytest.raises(acm.PointIsOutSideImage):
+        ds.project([0.0, 0.0, 0.0])
+    for m in (kb, fov):
+        with pytest.raises(acm.PointAtCameraCenter):
+            m.project([0.0, 0.0, 0.0])
+    with pytest.raises(acm.PointIsOutSideImage):
+        kb.unproject([-1.0, 100.0])
+    pin = acm.PinholeModel.new([500.0, 500.0, 320.0, 240.0], ctx=ctx)
+    pin.resolution = acm.Resolution(640, 480)
+    with pytest.raises(acm.PointIsOutSideImage):
+        pin.unproject([-100.0, 100.0])
+    with pytest.raises(acm.ProjectionOutSideImage):
+        pin.project([10.0, 0.0, 1.0])
+    for X in [(0.0, 0.0, 1.0), (0.2, 0.1, 1.5), (-0.1, -0.2, 2.0)]:
+        ray = pin.unproject(pin.project(X))
+        assert abs(float(np.dot(np.array(X) / np.linalg.norm(X), ray)) - 1.0) < 1e-6
+    # round trips with the reference's tolerances
+    for name, X, tol in [("double_sphere", (0.5, -0.3, 2.0), 1e-6), ("rad_tan", (0.5, -0.3, 2.0), 1e-6),
+                         ("kannala_brandt_inline", (0.1, 0.2, 1.0), 1e-5), ("ucm", (0.1, 0.1, 3.0), 1e-4),
+                         ("eucm", (0.1, 0.1, 3.0), 1e-4), ("fov", (0.1, 0.1, 3.0), 1e-4)]:
+        m = gpu_model(acm, ctx, cameras[name])
+        ray = m.unproject(m.project(X))
+        assert np.all(np.abs(ray - np.array(X) / np.linalg.norm(X)) < tol)
+
+
+# ------------------------------------------------------------------ Jacobians / normal equations --
+@pytest.mark.parametrize("name", MODELS)
+def test_project_jacobian_matches_oracle_and_mpmath(acm, ctx, O, cameras, name):
+    cam = cameras[name]
+    m, om = gpu_model(acm, ctx, cam), oracle_model(O, cam)
+    n = 4001
+    xyz = O.synth_points3(0xACE50002, 99, n, cone(name), True)
+    uv, J, st = m.project_jacobian_batch(xyz)
+    for i in range(0, n, 7):
+        sto, uvo, Jo = O.project_jacobian1(om, xyz[i])
+        assert st[i] == sto
+        if sto == 0:
+            assert np.allclose(uv[i], uvo, rtol=RTOL, atol=1e-13)
+            assert np.allclose(J[i], Jo, rtol=RTOL, atol=1e-12 * np.abs(Jo).max())
+    rows = load_golden("mpmath_jacobians.json")[name]
+    pts = np.array([r["point"] for r in rows])
+    uv, J, st = m.project_jacobian_batch(pts)
+    assert np.all(st == 0)
+    for k, r in enumerate(rows):
+        assert np.allclose(J[k], np.array(r["J"]), rtol=1e-9, atol=1e-12)
+    u1, J1 = m.project(pts[0], compute_jacobian=True)  # README-era spelling
+    assert np.array_equal(J1, J[0])
+
+
+def _correspondences(O, om, name, n, seed=0xACE50003, noise=0.25):
+    xyz = O.synth_points3(seed, 0, n, cone(name), True)
+    uv, st = O.project(om, xyz)
+    return xyz, np.where(np.isnan(uv), 1.0, uv) + noise
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_linearize_matches_oracle(acm, ctx, O, cameras, name):
+    cam = cameras[name]
+    m, om = gpu_model(acm, ctx, cam), oracle_model(O, cam)
+    for n in (1, 2, 333, 100_003):
+        xyz, obs = _correspondences(O, om, name, n)
+        for kind in ((0, 1) if name in UNIFIED else (0,)):
+            cost = acm.OptimizationCost(m, xyz, obs, residual_kind=kind)
+            H, g, c, nv = cost.linearize()
+            Ho, go, co, nvo = O.linearize(om, kind, xyz, obs, nthreads=4)
+            assert nv == nvo
+            dg = np.sqrt(np.abs(np.diag(Ho))) + 1e-300
+            assert np.max(np.abs(H - Ho) / np.outer(dg, dg)) < RTOL       # relative to the natural scale of each entry
+            assert np.max(np.abs(g - go) / (dg * np.sqrt(2 * co) + 1e-300)) < RTOL
+            assert abs(c - co) <= RTOL * co
+            assert np.array_equal(H, H.T)
+            H2, g2, c2, _ = cost.linearize()                                # deterministic reduction
+            assert np.array_equal(H, H2) and np.array_equal(g, g2) and c == c2
+            cost.free()
+
+
+def test_linearize_argument_errors(acm, ctx, O, cameras):
+    kb = gpu_model(acm, ctx, cameras["kannala_brandt"])
+    xyz = np.zeros((4, 3)) + [0.1, 0.1, 1.0]
+    with pytest.raises(acm.InvalidParams, match="Number of 2D and 3D points must match"):
+        acm.KannalaBrandtOptimizationCost(kb, xyz, np.zeros((3, 2)))
+    cost = acm.KannalaBrandtOptimizationCost(kb, xyz, np.zeros((4, 2)), residual_kind=1)
+    with pytest.raises(acm.AcmError, match="algebraic residual"):
+        cost.linearize()
+    with pytest.raises(acm.InvalidParams):
+        acm.DoubleSphereOptimizationCost(kb, xyz, np.zeros((4, 2)))
+
+
+# ------------------------------------------------------------------ linear estimation + LM --------
+def _kb450(O, cameras, n=500):
+    c = cameras["kannala_brandt"]
+    uv, xyz = O.sample_points(oracle_model(O, c), n)
+    return c["params"][:4], uv, xyz
+
+
+INITS = {"double_sphere": [0.5, 0.1], "ucm": [0.5], "eucm": [0.5, 1.0], "fov": [1.0], "kannala_brandt": [0.0] * 4, "rad_tan": [0.0] * 5}
+
+
+@pytest.mark.parametrize("name", ["double_sphere", "ucm", "eucm", "fov", "kannala_brandt"])
+def test_linear_estimation_matches_oracle(acm, ctx, O, cameras, name):
+    intr, uv, xyz = _kb450(O, cameras)
+    cam = {"model_id": cameras[name]["model_id"], "params": intr + INITS[name], "width": 512, "height": 512}
+    m, om = gpu_model(acm, ctx, cam), oracle_model(O, cam)
+    m.linear_estimation(xyz, uv)
+    assert O.linear_estimation(om, xyz, uv) == 0
+    got, ref = m.params(), om.params()
+    if name == "kannala_brandt":
+        assert np.allclose(got[4:], ref[4:], rtol=1e-7, atol=1e-12)  # 2N x 4 system, cond(A) ~ 1e5
+    else:
+        assert np.allclose(got, ref, rtol=1e-12, atol=0)
+    if name in UNIFIED:
+        assert abs(got[4] - load_golden("restated_kats.json")["lm_anchors_450"]["linear_alpha"]) < 1e-12
+
+
+def test_linear_estimation_rad_tan_and_errors(acm, ctx, O, cameras):
+    """tests/parameter_estimation.rs: 50 sampled points -> Ok and non-zero k; n=2 -> Err; mismatch -> Err."""
+    c = cameras["rad_tan"]
+    src = gpu_model(acm, ctx, c)
+    uv, xyz = acm.sample_points(src, 50)
+    est = acm.RadTanModel.new(c["params"][:4] + [0.0] * 5, ctx=ctx)
+    est.resolution = src.get_resolution()
+    est.linear_estimation(xyz, uv)
+    assert any(abs(d) > 1e-10 for d in est.distortions)
+    om = O.make_model(O.RADTAN, c["params"][:4] + [0.0] * 5, c["width"], c["height"])
+    O.linear_estimation(om, xyz, uv)
+    assert np.allclose(est.params(), om.params(), rtol=1e-8, atol=1e-12)
+    assert est.p1 == 0.0 and est.p2 == 0.0
+    uv2, xyz2 = acm.sample_points(src, 2)
+    with pytest.raises(acm.InvalidParams):
+        acm.RadTanModel.new(c["params"][:4] + [0.0] * 5, ctx=ctx).linear_estimation(xyz2, uv2)
+    with pytest.raises(acm.InvalidParams, match="must match"):
+        est.linear_estimation(xyz[:5], uv[:10])
+
+
+CASES = [("double_sphere", 1, 1e-9), ("double_sphere", 0, 5e-8), ("ucm", 1, 1e-9), ("ucm", 0, 1e-9), ("eucm", 1, 1e-9),
+         ("eucm", 0, 1e-9), ("fov", 0, 1e-9), ("kannala_brandt", 0, 1e-9)]
+
+
+@pytest.mark.parametrize("name,kind,rtol", CASES)
+def test_lm_converges_to_oracle_parameters(acm, ctx, O, cameras, name, kind, rtol):
+    """Config 1 (camera_converter --input-model kb --num-points 500 => 450 correspondences): same
+    inits, bounds and tolerances as the converter, then re-run with tolerances far below the
+    reference's so that both solvers sit at the minimiser.  cond(J^T J) ~ 2e9 for the DS pixel
+    residual, hence its looser bound."""
+    intr, uv, xyz = _kb450(O, cameras)
+    cam = {"model_id": cameras[name]["model_id"], "params": intr + INITS[name], "width": 512, "height": 512}
+    m, om = gpu_model(acm, ctx, cam), oracle_model(O, cam)
+    m.linear_estimation(xyz, uv)
+    O.linear_estimation(om, xyz, uv)
+    b = acm.CONVERTER_BOUNDS[m.MODEL_ID]
+    lo, hi = [x[0] for x in b], [x[1] for x in b]
+    start = m.params().copy()
+    cost = acm.OptimizationCost(m, xyz, uv, residual_kind=kind)
+    # (1) the converter's own configuration: identical trajectory => identical stop
+    r = cost.optimize()
+    oo, ores = O.lm_solve(om, kind, xyz, uv, lo, hi)
+    assert r.status == ores.status and r.iterations == ores.iterations and r.passes == ores.passes
+    assert np.allclose(r.parameters, oo, rtol=1e-9)
+    # (2) tight
+    m.set_params(start)
+    tight = acm.LevenbergMarquardtConfig(max_iterations=500, cost_tolerance=0.0, parameter_tolerance=1e-15, gradient_tolerance=0.0)
+    r = cost.optimize(config=tight)
+    ocfg = O.lm_default_config(); ocfg.max_iterations = 500; ocfg.cost_tolerance = 0.0; ocfg.parameter_tolerance = 1e-15; ocfg.gradient_tolerance = 0.0
+    oo, ores = O.lm_solve(om, kind, xyz, uv, lo, hi, ocfg)
+    assert r.converged and ores.status in (0, 1, 2)
+    assert np.allclose(r.parameters, oo, rtol=rtol), np.abs(r.parameters - oo) / np.abs(oo)
+    assert abs(r.final_cost - ores.final_cost) <= 1e-9 * ores.final_cost + 1e-18  # KB->KB is an exact fit: cost ~ 1e-22
+    cost.free()
+
+
+def test_lm_anchors_and_readme_figures(acm, ctx, O, cameras):
+    """KB -> DS / UCM on the 450 correspondences ends at the survey's anchors (scipy, 1e-15) and at
+    the README's 0.008 px / 0.145 px (README.md:163-164)."""
+    A = load_golden("restated_kats.json")["lm_anchors_450"]
+    intr, uv, xyz = _kb450(O, cameras)
+    tight = acm.LevenbergMarquardtConfig(max_iterations=500, cost_tolerance=0.0, parameter_tolerance=1e-15, gradient_tolerance=0.0)
+    ds = acm.DoubleSphereModel(acm.Intrinsics(*intr), acm.Resolution(512, 512), [0.5, 0.1], ctx=ctx)
+    assert abs(acm.compute_reprojection_error(ds, xyz, uv).mean - A["ds_initial_mean_px"]) < 1e-4
+    cost = acm.DoubleSphereOptimizationCost(ds, xyz, uv)  # canonical residual: algebraic
+    cost.linear_estimation()
+    assert abs(acm.compute_reprojection_error(ds, xyz, uv).mean - A["linear_only_mean_px"]) < 1e-5
+    r = cost.optimize(config=tight)
+    assert np.allclose(r.parameters, A["ds_algebraic"]["params"], rtol=5e-9)
+    e = acm.compute_reprojection_error(ds, xyz, uv)
+    assert abs(e.mean - A["ds_algebraic"]["mean_px"]) < 5e-7 and round(e.mean, 3) == 0.008
+    ucm = acm.UcmModel(acm.Intrinsics(*intr), acm.Resolution(512, 512), [0.5], ctx=ctx)
+    c2 = acm.UcmOptimizationCost(ucm, xyz, uv)
+    c2.linear_estimation(); c2.optimize()
+    assert round(acm.compute_reprojection_error(ucm, xyz, uv).mean, 3) == 0.145
+
+
+def test_lm_recovers_generating_model_and_penalty(acm, ctx, O, cameras):
+    c = cameras["double_sphere"]
+    truth = oracle_model(O, c)
+    xyz = O.synth_points3(0xACE50003, 0, 200_001, np.cos(np.deg2rad(70.0)), False)
+    uv, st = O.project(truth, xyz)
+    assert np.all(st == 0)
+    start = np.array(c["params"]) * np.array([1.02, 0.98, 1.01, 0.99, 0.9, 0.8])
+    m = acm.DoubleSphereModel(acm.Intrinsics(*start[:4]), acm.Resolution(752, 480), start[4:], ctx=ctx)
+    cost = acm.DoubleSphereOptimizationCost(m, xyz, uv, residual_kind=0)
+    tight = acm.LevenbergMarquardtConfig(max_iterations=200, cost_tolerance=0.0, parameter_tolerance=1e-15, gradient_tolerance=0.0)
+    r = cost.optimize(config=tight, bounds=None)
+    assert np.allclose(r.parameters, c["params"], rtol=1e-9) and r.n_valid == len(xyz)
+    # invalid_penalty: residual (pen, pen) for invalid points, as the former in-tree factor did
+    xyz2 = xyz[:1000].copy(); xyz2[::10, 2] = -5.0
+    m2 = acm.DoubleSphereModel(acm.Intrinsics(*c["params"][:4]), acm.Resolution(752, 480), c["params"][4:], ctx=ctx)
+    c2 = acm.DoubleSphereOptimizationCost(m2, xyz2, uv[:1000], residual_kind=0)
+    r0 = c2.optimize(config=acm.LevenbergMarquardtConfig(max_iterations=0), bounds=None)  # evaluation only
+    r1 = c2.optimize(config=acm.LevenbergMarquardtConfig(max_iterations=0, invalid_penalty=1e3), bounds=None)
+    assert r0.status == 3 and r0.passes == 1 and r0.n_valid == r1.n_valid
+    n_bad = 1000 - r0.n_valid
+    assert n_bad > 0 and abs((r1.initial_cost - r0.initial_cost) - n_bad * 1e6) <= 1e-6 * n_bad * 1e6
+
+
+# ------------------------------------------------------------------ util hot loops ----------------
+@pytest.mark.parametrize("name,n", [("kannala_brandt", 500), ("kannala_brandt", 10_000), ("double_sphere", 100), ("rad_tan", 50),
+                                    ("ucm", 777), ("eucm", 1000), ("fov", 300), ("pinhole", 64), ("kannala_brandt", 1_000_000)])
+def test_sample_points_matches_oracle(acm, ctx, O, cameras, name, n):
+    cam = cameras[name]
+    m, om = gpu_model(acm, ctx, cam), oracle_model(O, cam)
+    uv, xyz = acm.sample_points(m, n)
+    uvo, xyzo = O.sample_points(om, n)
+    assert uv.shape == uvo.shape, "kept set differs"
+    assert np.array_equal(uv, uvo)  # same pixels in the same order
+    if name in EXACT:
+        assert np.array_equal(xyz, xyzo)
+    else:
+        assert np.allclose(xyz, xyzo, rtol=RTOL, atol=1e-15)
+    if (name, n) == ("kannala_brandt", 500):
+        assert len(uv) == 450
+    if (name, n) == ("kannala_brandt", 10_000):
+        assert len(uv) == 9294
+
+
+@pytest.mark.parametrize("name", ["double_sphere", "kannala_brandt", "pinhole", "fov"])
+def test_reprojection_error_matches_oracle(acm, ctx, O, cameras, name):
+    cam = cameras[name]
+    m, om = gpu_model(acm, ctx, cam), oracle_model(O, cam)
+    for n in (1, 2, 451, 100_004):
+        xyz, obs = _correspondences(O, om, name, n, noise=0.0)
+        rng = np.random.default_rng(n)
+        obs = obs + rng.normal(0, 0.3, obs.shape)
+        try:
+            eo = O.reprojection_error(om, xyz, obs)
+        except ValueError:
+            with pytest.raises(acm.ZeroProjectionPoints):
+                acm.compute_reprojection_error(m, xyz, obs)
+            continue
+        e = acm.compute_reprojection_error(m, xyz, obs)
+        assert e.count == eo.count
+        for f in ("rmse", "min", "max", "mean", "stddev", "median"):
+            assert np.isclose(getattr(e, f), getattr(eo, f), rtol=1e-9, atol=1e-13), f
+    with pytest.raises(acm.ZeroProjectionPoints):
+        acm.compute_reprojection_error(m, np.tile([0.0, 0.0, -1.0], (8, 1)), np.zeros((8, 2)))
+
+
+@pytest.mark.parametrize("name,W,H", [("kannala_brandt", 512, 512), ("double_sphere", 752, 480), ("pinhole", 752, 480),
+                                      ("rad_tan", 752, 480), ("fov", 320, 200), ("ucm", 1920, 1080), ("kannala_brandt", 37, 29)])
+def test_undistort_bytes_and_remap_indices(acm, ctx, O, cameras, name, W, H):
+    """undistort.rs:14-105: output bytes and remap indices are bit-exact (KB / FOV depend on the
+    device atan2: count index flips, expected 0)."""
+    cam = dict(cameras[name]); cam["width"], cam["height"] = W, H
+    if name in ("ucm", "fov"):  # keep the principal point inside the test image
+        cam["params"] = list(cam["params"]); cam["params"][2] = W / 2.0 + 0.3; cam["params"][3] = H / 2.0 - 0.2
+    if (W, H) == (37, 29):
+        cam["params"] = [20.0, 20.0, 18.2, 14.1] + cam["params"][4:]
+    m, om = gpu_model(acm, ctx, cam), oracle_model(O, cam)
+    frames = O.synth_bytes(0xACE50005, 0, 3 * W * H * 3).reshape(3, H, W, 3)
+    for target in (None, acm.Intrinsics(cam["params"][0] * 0.6, cam["params"][1] * 0.6, W / 2.0, H / 2.0)):
+        t = cam["params"][:4] if target is None else [target.fx, target.fy, target.cx, target.cy]
+        mp = acm.undistort_map(m, target)
+        mpo = O.undistort_map(om, t)
+        assert np.array_equal(np.isnan(mp), np.isnan(mpo))
+        ok = ~np.isnan(mpo)
+        flips = int(np.sum(np.floor(mp[ok]) != np.floor(mpo[ok])))
+        assert flips == 0, f"{flips} remap indices differ"
+        if name in EXACT:
+            assert np.array_equal(mp[ok], mpo[ok])
+        for interp in (acm.InterpolationMethod.Bilinear, acm.InterpolationMethod.Nearest):
+            out = acm.undistort_images(frames, m, target, interp)
+            for f in range(3):
+                ref = O.undistort_rgb8(om, t, frames[f], int(interp), nthreads=4)
+                assert np.array_equal(out[f], ref), f"{name} frame {f} interp {interp}: {(out[f] != ref).sum()} bytes differ"
+    one = acm.undistort_image(frames[0], m)
+    assert np.array_equal(one, acm.undistort_images(frames[:1], m)[0])
+    with pytest.raises(acm.UtilError, match="doesn't match model"):
+        acm.undistort_image(np.zeros((H + 1, W, 3), np.uint8), m)
+
+
+# ------------------------------------------------------------------ BASELINE sizes: properties -----
+def test_full_size_round_trip_and_linearity(acm, ctx, O, cameras):
+    """100 M synthetic points (BASELINE configs 2 and 3): project -> unproject returns the input
+    direction; the normal equations of the whole equal the sum over shards; repeat runs are
+    bit-identical."""
+    from apex_camera_models_b200 import _native as N
+    lib = N.lib
+    n = 100_000_000
+    cam = cameras["double_sphere"]
+    m = gpu_model(acm, ctx, dict(cam, width=100000, height=100000, params=cam["params"][:2] + [50000.0, 50000.0] + cam["params"][4:]))
+    X = acm.Points(ctx, 3, n)
+    ctx.check(lib.acm_synth_points3(ctx.handle, 0xACE50002, 0, np.cos(np.deg2rad(100.0)), 1, X.handle))
+    UV, st = m.project_batch(X)
+    R, st2 = m.unproject_batch(UV)
+    # sample-check the round trip on strided slices brought back to the host
+    k = 1_000_003
+    xs = np.empty((3, k)); rs = np.empty((3, k)); s1 = np.empty(k, np.uint8); s2 = np.empty(k, np.uint8)
+    off = 37_000_000
+    for c in range(3):
+        ctx.d2h(xs[c], X.component_ptr(c) + 8 * off); ctx.d2h(rs[c], R.component_ptr(c) + 8 * off)
+    ctx.d2h(s1, st + off); ctx.d2h(s2, st2 + off); ctx.sync()
+    ok = (s1 == 0) & (s2 == 0)
+    assert ok.mean() > 0.9
+    d = xs[:, ok] / np.linalg.norm(xs[:, ok], axis=0)
+    assert np.max(np.abs(np.sum(d * rs[:, ok], axis=0) - 1.0)) < 1e-9
+    xo = O.synth_points3(0xACE50002, off, 4096, np.cos(np.deg2rad(100.0)), True)
+    assert np.array_equal(xs[:, :4096].T, xo)
+    _, sto = O.project(oracle_model(O, dict(cam, width=100000, height=100000, params=cam["params"][:2] + [50000.0, 50000.0] + cam["params"][4:])), xo)
+    assert np.array_equal(s1[:4096], sto)
+    # status census must match the generator's design: every 64th point is adversarial
+    ctx.device_free(st2); R.free()
+    # linearity of the normal equations over shards
+    cost = acm.DoubleSphereOptimizationCost(m, X, UV, residual_kind=0)
+    # perturb the model so residuals are non-zero
+    m.set_params(m.params() * np.array([1.001, 0.999, 1.0, 1.0, 1.01, 0.98]))
+    H, g, c, nv = cost.linearize()
+    H2, g2, c2, nv2 = cost.linearize()
+    assert np.array_equal(H, H2) and np.array_equal(g, g2) and c == c2 and nv == nv2
+    # shards: views into the same buffers (4 contiguous quarters, 256-byte aligned offsets)
+    Hs = np.zeros_like(H); gs = np.zeros_like(g); cs = 0.0; nvs = 0
+    q = n // 4
+    for r in range(4):
+        Xs = acm.Points(ctx, 3, q); UVs = acm.Points(ctx, 2, q)
+        for cc in range(3):
+            ctx.d2d(Xs.component_ptr(cc), X.component_ptr(cc) + 8 * q * r, 8 * q)
+        for cc in range(2):
+            ctx.d2d(UVs.component_ptr(cc), UV.component_ptr(cc) + 8 * q * r, 8 * q)
+        ctx.sync()
+        sc = acm.DoubleSphereOptimizationCost(m, Xs, UVs, residual_kind=0)
+        h_, g_, c_, n_ = sc.linearize()
+        Hs += h_; gs += g_; cs += c_; nvs += n_
+        Xs.free(); UVs.free()
+    assert nvs == nv
+    assert np.allclose(Hs, H, rtol=1e-12) and np.allclose(gs, g, rtol=1e-9, atol=1e-9 * np.abs(g).max()) and np.isclose(cs, c, rtol=1e-12)
+    ctx.device_free(st); X.free(); UV.free()
