@@ -20,6 +20,42 @@
 #define LIN_SQRT_EPS 1.4901161193847656e-08
 #define LIN_PRECISION 1e-3
 
+// ---------------------------------------------------------------------------------------
+// Branch-free f64 reciprocal / rsqrt / sqrt for the solver kernels.  The CUDA library versions
+// carry a slow-path CALL for special operands inside the streaming loop, which stops the
+// compiler from interleaving the two points a thread owns.  Here: MUFU seed (rcp.approx /
+// rsqrt.approx, ~2^-23) + two Newton steps in FMA arithmetic => <= 2 ulp for normal operands;
+// 0, inf and NaN propagate to NaN/inf and are rejected by the validity compares downstream.
+// (Only used where the tolerance is 1e-9 relative -- never in the bit-exact project kernels.)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double fast_rcp(double a) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    double e = fma(-a, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-a, r, 1.0);
+    return fma(r, e, r);
+}
+__device__ __forceinline__ double fast_rsqrt(double a) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    const double h = 0.5 * a;
+    y = y * fma(-h, y * y, 1.5);   // 2^-23 -> ~2^-45
+    return y * fma(-h, y * y, 1.5);  // -> full double precision
+}
+// sqrt(a) with 1/sqrt(a) as a by-product.  One Newton step on the seed (inv accurate to ~2^-44,
+// enough for a Jacobian entry), then a Heron correction with the exact fma residual, which
+// squares the error: s is accurate to <= 1 ulp.
+__device__ __forceinline__ double fast_sqrt(double a, double& inv) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    y = y * fma(-0.5 * a, y * y, 1.5);
+    double s = a * y;
+    double r = fma(-s, s, a);
+    inv = y;
+    return fma(r, 0.5 * y, s);
+}
+
 template <int ND> struct AccLayout {
     static constexpr int HFF = 0, HFC = 2, HCC = 4, HFD = 6, HCD = 6 + 2 * ND, HDD = 6 + 4 * ND;
     static constexpr int GF = HDD + ND * (ND + 1) / 2, GC = GF + 2, GD = GC + 2, COST = GD + ND, COUNT = COST + 1;
@@ -63,12 +99,11 @@ template <> struct Lin<ACM_MODEL_PINHOLE, ACM_RESIDUAL_PIXEL> {
     static constexpr int ND = 0; static constexpr bool UNIT_C = true;
     static __device__ __forceinline__ bool eval(const LinParams& p, double x, double y, double z, double u, double v,
                                                 double& ru, double& rv, double* au, double* av) {
-        if (!(z >= LIN_SQRT_EPS)) return false;
-        double iz = 1.0 / z;
+        double iz = fast_rcp(z);
         double mx = x * iz, my = y * iz;
         ru = fma(p.fx, mx, p.cx) - u; rv = fma(p.fy, my, p.cy) - v;
         au[0] = mx; av[0] = my; au[1] = av[1] = 1.0;
-        return true;
+        return z >= LIN_SQRT_EPS;
     }
 };
 
@@ -76,9 +111,8 @@ template <> struct Lin<ACM_MODEL_RADTAN, ACM_RESIDUAL_PIXEL> {
     static constexpr int ND = 5; static constexpr bool UNIT_C = true;
     static __device__ __forceinline__ bool eval(const LinParams& p, double x, double y, double z, double u, double v,
                                                 double& ru, double& rv, double* au, double* av) {
-        if (!(z >= LIN_SQRT_EPS)) return false;
         const double k1 = p.d[0], k2 = p.d[1], p1 = p.d[2], p2 = p.d[3], k3 = p.d[4];
-        double iz = 1.0 / z;
+        double iz = fast_rcp(z);
         double xp = x * iz, yp = y * iz;
         double rho = xp * xp + yp * yp, rho2 = rho * rho, rho3 = rho2 * rho;
         double rad = 1.0 + k1 * rho + k2 * rho2 + k3 * rho3;
@@ -94,7 +128,7 @@ template <> struct Lin<ACM_MODEL_RADTAN, ACM_RESIDUAL_PIXEL> {
         au[4] = p.fx * xy2; av[4] = p.fy * ty;    // p1
         au[5] = p.fx * tx;  av[5] = p.fy * xy2;   // p2
         au[6] = fxx * rho3; av[6] = fyy * rho3;   // k3
-        return true;
+        return z >= LIN_SQRT_EPS;
     }
 };
 
@@ -102,11 +136,13 @@ template <> struct Lin<ACM_MODEL_KANNALA_BRANDT, ACM_RESIDUAL_PIXEL> {
     static constexpr int ND = 4; static constexpr bool UNIT_C = true;
     static __device__ __forceinline__ bool eval(const LinParams& p, double x, double y, double z, double u, double v,
                                                 double& ru, double& rv, double* au, double* av) {
-        if (!(z >= LIN_EPS)) return false;  // z < 0 and 0 <= z < EPS both fail (kannala_brandt.rs:345-351)
-        double r = sqrt(x * x + y * y);
-        double th = atan2(r, z);
-        double xr = 0.0, yr = 0.0;
-        if (r >= LIN_EPS) { double ir = 1.0 / r; xr = x * ir; yr = y * ir; }
+        const bool ok = z >= LIN_EPS;  // z < 0 and 0 <= z < EPS both fail (kannala_brandt.rs:345-351)
+        double ir;
+        double r = fast_sqrt(x * x + y * y, ir);
+        const bool on_axis = !(r >= LIN_EPS);  // also catches r = NaN from x = y = 0
+        r = on_axis ? 0.0 : r;
+        double th = atan2(r, ok ? z : 1.0);
+        double xr = on_axis ? 0.0 : x * ir, yr = on_axis ? 0.0 : y * ir;
         double t2 = th * th, t3 = t2 * th, t5 = t3 * t2, t7 = t5 * t2, t9 = t7 * t2;
         double thd = th + p.d[0] * t3 + p.d[1] * t5 + p.d[2] * t7 + p.d[3] * t9;
         double mx = thd * xr, my = thd * yr;
@@ -117,7 +153,7 @@ template <> struct Lin<ACM_MODEL_KANNALA_BRANDT, ACM_RESIDUAL_PIXEL> {
         au[3] = fxr * t5; av[3] = fyr * t5;
         au[4] = fxr * t7; av[4] = fyr * t7;
         au[5] = fxr * t9; av[5] = fyr * t9;
-        return true;
+        return ok;
     }
 };
 
@@ -127,7 +163,8 @@ template <> struct Unified<ACM_MODEL_UCM> {
     static constexpr int ND = 1;
     static __device__ __forceinline__ bool den(const LinParams& p, double x, double y, double z, double& den, double* dd) {
         const double alpha = p.d[0];
-        double d = sqrt(x * x + y * y + z * z);
+        double id;
+        double d = fast_sqrt(x * x + y * y + z * z, id);
         den = alpha * d + (1.0 - alpha) * z;
         dd[0] = d - z;
         return (den >= LIN_PRECISION) && (z > -p.k0 * d);
@@ -139,14 +176,14 @@ template <> struct Unified<ACM_MODEL_EUCM> {
         const double alpha = p.d[0], beta = p.d[1];
         double rr = x * x + y * y;
         double q = beta * rr + z * z;
-        double id = rsqrt(q);
-        double d = q * id;
+        double id;
+        double d = fast_sqrt(q, id);
         den = alpha * d + (1.0 - alpha) * z;
         dd[0] = d - z;
         dd[1] = 0.5 * alpha * rr * id;
         bool cond = true;
         if (alpha > 0.5) cond = !(z < den * p.k0);
-        return (den >= LIN_PRECISION) && cond && (q > 0.0);
+        return (den >= LIN_PRECISION) && cond;
     }
 };
 template <> struct Unified<ACM_MODEL_DOUBLE_SPHERE> {
@@ -154,16 +191,17 @@ template <> struct Unified<ACM_MODEL_DOUBLE_SPHERE> {
     static __device__ __forceinline__ bool den(const LinParams& p, double x, double y, double z, double& den, double* dd) {
         const double alpha = p.d[0], xi = p.d[1];
         double rr = x * x + y * y;
-        double d1 = sqrt(rr + z * z);
+        double id1;
+        double d1 = fast_sqrt(rr + z * z, id1);
         double g = fma(xi, d1, z);
         double q = fma(g, g, rr);
-        double id2 = rsqrt(q);
-        double d2 = q * id2;
+        double id2;
+        double d2 = fast_sqrt(q, id2);
         double oma = 1.0 - alpha;
         den = alpha * d2 + oma * g;
         dd[0] = d2 - g;
         dd[1] = d1 * fma(alpha * g, id2, oma);
-        return (den >= LIN_PRECISION) && (z > -p.k0 * d1) && (q > 0.0);
+        return (den >= LIN_PRECISION) && (z > -p.k0 * d1);
     }
 };
 
@@ -172,15 +210,15 @@ template <int M> struct LinUnifiedPixel {
     static __device__ __forceinline__ bool eval(const LinParams& p, double x, double y, double z, double u, double v,
                                                 double& ru, double& rv, double* au, double* av) {
         double den, dd[2];
-        if (!Unified<M>::den(p, x, y, z, den, dd)) return false;
-        double inv = 1.0 / den;
+        const bool ok = Unified<M>::den(p, x, y, z, den, dd);
+        double inv = fast_rcp(den);
         double mx = x * inv, my = y * inv;
         ru = fma(p.fx, mx, p.cx) - u; rv = fma(p.fy, my, p.cy) - v;
         double cu = -(p.fx * mx) * inv, cv = -(p.fy * my) * inv;  // d(u)/d(den), d(v)/d(den)
         au[0] = mx; av[0] = my; au[1] = av[1] = 1.0;
 #pragma unroll
         for (int k = 0; k < ND; ++k) { au[2 + k] = cu * dd[k]; av[2 + k] = cv * dd[k]; }
-        return true;
+        return ok;
     }
 };
 template <int M> struct LinUnifiedAlgebraic {
@@ -188,13 +226,13 @@ template <int M> struct LinUnifiedAlgebraic {
     static __device__ __forceinline__ bool eval(const LinParams& p, double x, double y, double z, double u, double v,
                                                 double& ru, double& rv, double* au, double* av) {
         double den, dd[2];
-        if (!Unified<M>::den(p, x, y, z, den, dd)) return false;
+        const bool ok = Unified<M>::den(p, x, y, z, den, dd);
         double du = u - p.cx, dv = v - p.cy;
         ru = p.fx * x - du * den; rv = p.fy * y - dv * den;
         au[0] = x; av[0] = y; au[1] = den; av[1] = den;
 #pragma unroll
         for (int k = 0; k < ND; ++k) { au[2 + k] = -du * dd[k]; av[2 + k] = -dv * dd[k]; }
-        return true;
+        return ok;
     }
 };
 template <> struct Lin<ACM_MODEL_UCM, ACM_RESIDUAL_PIXEL> : LinUnifiedPixel<ACM_MODEL_UCM> {};
@@ -208,7 +246,8 @@ template <> struct Lin<ACM_MODEL_FOV, ACM_RESIDUAL_PIXEL> {
     static constexpr int ND = 1; static constexpr bool UNIT_C = true;
     static __device__ __forceinline__ bool eval(const LinParams& p, double x, double y, double z, double u, double v,
                                                 double& ru, double& rv, double* au, double* av) {
-        if (!(z >= LIN_SQRT_EPS)) return false;
+        const bool ok = z >= LIN_SQRT_EPS;
+        z = ok ? z : 1.0;
         const double w = p.d[0], t = p.k0;
         double r2 = x * x + y * y;
         double rd, drd;
@@ -228,13 +267,58 @@ template <> struct Lin<ACM_MODEL_FOV, ACM_RESIDUAL_PIXEL> {
         ru = fma(p.fx, mx, p.cx) - u; rv = fma(p.fy, my, p.cy) - v;
         au[0] = mx; av[0] = my; au[1] = av[1] = 1.0;
         au[2] = p.fx * x * drd; av[2] = p.fy * y * drd;
-        return true;
+        return ok;
     }
 };
 
 // ---------------------------------------------------------------------------------------
 // rank-2 update of the packed normal equations with the two sparse rows
 // ---------------------------------------------------------------------------------------
+// Invalid points are folded in branch-free: every factor is replaced by an exact 0 (a select,
+// never a multiplication by zero, so NaN/inf of a rejected point cannot leak).
+template <int ND, bool UNIT_C>
+__device__ __forceinline__ void lin_accumulate_masked(double* acc, bool ok, double ru, double rv, double* au, double* av) {
+    ru = ok ? ru : 0.0; rv = ok ? rv : 0.0;
+#pragma unroll
+    for (int k = 0; k < 2 + ND; ++k) { au[k] = ok ? au[k] : 0.0; av[k] = ok ? av[k] : 0.0; }
+    using L = AccLayout<ND>;
+    acc[L::HFF + 0] = fma(au[0], au[0], acc[L::HFF + 0]);
+    acc[L::HFF + 1] = fma(av[0], av[0], acc[L::HFF + 1]);
+    acc[L::GF + 0] = fma(au[0], ru, acc[L::GF + 0]);
+    acc[L::GF + 1] = fma(av[0], rv, acc[L::GF + 1]);
+    if (UNIT_C) {
+        acc[L::HFC + 0] += au[0];
+        acc[L::HFC + 1] += av[0];
+        acc[L::GC + 0] += ru;
+        acc[L::GC + 1] += rv;
+    } else {
+        acc[L::HFC + 0] = fma(au[0], au[1], acc[L::HFC + 0]);
+        acc[L::HFC + 1] = fma(av[0], av[1], acc[L::HFC + 1]);
+        acc[L::HCC + 0] = fma(au[1], au[1], acc[L::HCC + 0]);
+        acc[L::HCC + 1] = fma(av[1], av[1], acc[L::HCC + 1]);
+        acc[L::GC + 0] = fma(au[1], ru, acc[L::GC + 0]);
+        acc[L::GC + 1] = fma(av[1], rv, acc[L::GC + 1]);
+    }
+#pragma unroll
+    for (int k = 0; k < ND; ++k) {
+        acc[L::HFD + k] = fma(au[0], au[2 + k], acc[L::HFD + k]);
+        acc[L::HFD + ND + k] = fma(av[0], av[2 + k], acc[L::HFD + ND + k]);
+        if (UNIT_C) {
+            acc[L::HCD + k] += au[2 + k];
+            acc[L::HCD + ND + k] += av[2 + k];
+        } else {
+            acc[L::HCD + k] = fma(au[1], au[2 + k], acc[L::HCD + k]);
+            acc[L::HCD + ND + k] = fma(av[1], av[2 + k], acc[L::HCD + ND + k]);
+        }
+        acc[L::GD + k] = fma(au[2 + k], ru, fma(av[2 + k], rv, acc[L::GD + k]));
+#pragma unroll
+        for (int j = 0; j <= k; ++j)
+            acc[L::HDD + L::tri(j, k)] = fma(au[2 + j], au[2 + k], fma(av[2 + j], av[2 + k], acc[L::HDD + L::tri(j, k)]));
+    }
+    acc[L::COST] = fma(ru, ru, fma(rv, rv, acc[L::COST]));
+    acc[L::COUNT] += ok ? 1.0 : 0.0;
+}
+
 template <int ND, bool UNIT_C>
 __device__ __forceinline__ void lin_accumulate(double* acc, double ru, double rv, const double* au, const double* av) {
     using L = AccLayout<ND>;

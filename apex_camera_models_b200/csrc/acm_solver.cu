@@ -56,13 +56,26 @@ __global__ void __launch_bounds__(256) linearize_kernel(LinParams hp, const LmSt
 #pragma unroll
     for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
 
+    // Software-pipelined stream: the five 16-byte loads of the next pair of points are in flight
+    // while the current pair is evaluated, so that the few resident warps (accumulators cost
+    // registers) still keep enough bytes in flight to cover the HBM latency.
     const size_t npairs = n >> 1;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += stride) {
-        const double2 x = __ldcs(X + i), y = __ldcs(Y + i), z = __ldcs(Z + i), u = __ldcs(U + i), v = __ldcs(V + i);
-        double ru, rv, au[2 + ND], av[2 + ND];
-        if (LM_::eval(p, x.x, y.x, z.x, u.x, v.x, ru, rv, au, av)) lin_accumulate<ND, UNIT_C>(acc, ru, rv, au, av);
-        if (LM_::eval(p, x.y, y.y, z.y, u.y, v.y, ru, rv, au, av)) lin_accumulate<ND, UNIT_C>(acc, ru, rv, au, av);
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double2 x, y, z, u, v;
+    if (i < npairs) { x = __ldcs(X + i); y = __ldcs(Y + i); z = __ldcs(Z + i); u = __ldcs(U + i); v = __ldcs(V + i); }
+#pragma unroll 1
+    while (i < npairs) {
+        const size_t nx = i + stride;
+        const size_t j = nx < npairs ? nx : i;  // clamp: the tail re-reads its own (cached) packet
+        const double2 x2 = __ldcs(X + j), y2 = __ldcs(Y + j), z2 = __ldcs(Z + j), u2 = __ldcs(U + j), v2 = __ldcs(V + j);
+        double ru0, rv0, au0[2 + ND], av0[2 + ND], ru1, rv1, au1[2 + ND], av1[2 + ND];
+        const bool ok0 = LM_::eval(p, x.x, y.x, z.x, u.x, v.x, ru0, rv0, au0, av0);
+        const bool ok1 = LM_::eval(p, x.y, y.y, z.y, u.y, v.y, ru1, rv1, au1, av1);
+        lin_accumulate_masked<ND, UNIT_C>(acc, ok0, ru0, rv0, au0, av0);
+        lin_accumulate_masked<ND, UNIT_C>(acc, ok1, ru1, rv1, au1, av1);
+        x = x2; y = y2; z = z2; u = u2; v = v2;
+        i = nx;
     }
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
         const size_t t = n - 1;
@@ -70,7 +83,8 @@ __global__ void __launch_bounds__(256) linearize_kernel(LinParams hp, const LmSt
         const double* Zs = reinterpret_cast<const double*>(Z); const double* Us = reinterpret_cast<const double*>(U);
         const double* Vs = reinterpret_cast<const double*>(V);
         double ru, rv, au[2 + ND], av[2 + ND];
-        if (LM_::eval(p, Xs[t], Ys[t], Zs[t], Us[t], Vs[t], ru, rv, au, av)) lin_accumulate<ND, UNIT_C>(acc, ru, rv, au, av);
+        const bool ok = LM_::eval(p, Xs[t], Ys[t], Zs[t], Us[t], Vs[t], ru, rv, au, av);
+        lin_accumulate_masked<ND, UNIT_C>(acc, ok, ru, rv, au, av);
     }
 
     if (GridReduce<NACC, 0, 0>::run(acc, partials, out, ticket)) {
