@@ -46,14 +46,44 @@ __device__ __forceinline__ double fast_rsqrt(double a) {
 // sqrt(a) with 1/sqrt(a) as a by-product.  One Newton step on the seed (inv accurate to ~2^-44,
 // enough for a Jacobian entry), then a Heron correction with the exact fma residual, which
 // squares the error: s is accurate to <= 1 ulp.
+template <bool REFINE_INV = false>
 __device__ __forceinline__ double fast_sqrt(double a, double& inv) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-    y = y * fma(-0.5 * a, y * y, 1.5);
+    const double h = 0.5 * a;
+    y = y * fma(-h, y * y, 1.5);
     double s = a * y;
     double r = fma(-s, s, a);
-    inv = y;
+    inv = REFINE_INV ? y * fma(-h, y * y, 1.5) : y;  // refined: full precision (feeds a residual)
     return fma(r, 0.5 * y, s);
+}
+
+// atan2(a, b) for a >= 0, b > 0 (first quadrant: all the fisheye models need).  Two argument
+// reductions that share ONE reciprocal -- swap so that t = num/den <= 1, then
+// atan(t) = pi/4 + atan((num-den)/(num+den)) above tan(pi/8) -- leave |t| <= sqrt(2)-1, where a
+// degree-10 polynomial in t^2 (Chebyshev-node fit computed with mpmath, approximation error
+// 6.9e-17 relative) is evaluated by Horner.  ~25 FP64 instructions, no branch, no slow path.
+__device__ __forceinline__ double fast_atan2_q1(double a, double b) {
+    const bool swap = a > b;
+    const double num = swap ? b : a, den = swap ? a : b;
+    const bool hi = num > 0.41421356237309503 * den;
+    const double n2 = hi ? num - den : num;
+    const double d2 = hi ? num + den : den;
+    const double t = n2 * fast_rcp(d2);
+    const double s = t * t;
+    double q = 2.11353731576932463e-02;
+    q = fma(q, s, -4.34805221571646222e-02);
+    q = fma(q, s, 5.68834922680901064e-02);
+    q = fma(q, s, -6.64023393042940807e-02);
+    q = fma(q, s, 7.68995349630685748e-02);
+    q = fma(q, s, -9.09077307480841423e-02);
+    q = fma(q, s, 1.11111061804559458e-01);
+    q = fma(q, s, -1.42857141809764665e-01);
+    q = fma(q, s, 1.99999999988551114e-01);
+    q = fma(q, s, -3.33333333333284410e-01);
+    double at = fma(t * s, q, t);
+    at = hi ? 0.78539816339744828 + at : at;
+    return swap ? 1.5707963267948966 - at : at;
 }
 
 template <int ND> struct AccLayout {
@@ -138,10 +168,10 @@ template <> struct Lin<ACM_MODEL_KANNALA_BRANDT, ACM_RESIDUAL_PIXEL> {
                                                 double& ru, double& rv, double* au, double* av) {
         const bool ok = z >= LIN_EPS;  // z < 0 and 0 <= z < EPS both fail (kannala_brandt.rs:345-351)
         double ir;
-        double r = fast_sqrt(x * x + y * y, ir);
+        double r = fast_sqrt<true>(x * x + y * y, ir);
         const bool on_axis = !(r >= LIN_EPS);  // also catches r = NaN from x = y = 0
         r = on_axis ? 0.0 : r;
-        double th = atan2(r, ok ? z : 1.0);
+        double th = fast_atan2_q1(r, ok ? z : 1.0);
         double xr = on_axis ? 0.0 : x * ir, yr = on_axis ? 0.0 : y * ir;
         double t2 = th * th, t3 = t2 * th, t5 = t3 * t2, t7 = t5 * t2, t9 = t7 * t2;
         double thd = th + p.d[0] * t3 + p.d[1] * t5 + p.d[2] * t7 + p.d[3] * t9;
@@ -257,7 +287,7 @@ template <> struct Lin<ACM_MODEL_FOV, ACM_RESIDUAL_PIXEL> {
             drd = (1.0 + t * t) * iw - 2.0 * t * iw * iw;
         } else {
             double r = sqrt(r2);
-            double a = atan2(2.0 * t * r, z);
+            double a = fast_atan2_q1(2.0 * t * r, z);
             double da = z * r * (1.0 + t * t) / (4.0 * t * t * r2 + z * z);
             double irw = iw / r;
             rd = a * irw;
@@ -380,3 +410,88 @@ __host__ __device__ inline void lin_unpack(const double* r, double* H, double* g
     *cost = 0.5 * r[L::COST];
     *count = cnt;
 }
+
+// ---------------------------------------------------------------------------------------
+// LinOps<M, KIND>: what the streaming kernel, the LM step and the host unpack use.
+// Generic: per-model eval() + the sparse rank-2 update above.
+// ---------------------------------------------------------------------------------------
+template <int M, int KIND> struct LinOps {
+    using E = Lin<M, KIND>;
+    static constexpr int ND = E::ND, P = 4 + ND;
+    using L = AccLayout<ND>;
+    static constexpr int NACC = L::N, COST = L::COST, COUNT = L::COUNT;
+    static __device__ __forceinline__ void point(double* acc, const LinParams& p, double x, double y, double z, double u, double v) {
+        double ru, rv, au[2 + ND], av[2 + ND];
+        const bool ok = E::eval(p, x, y, z, u, v, ru, rv, au, av);
+        lin_accumulate_masked<ND, E::UNIT_C>(acc, ok, ru, rv, au, av);
+    }
+    __host__ __device__ static void unpack(const double* r, double* H, double* g, double* cost, double* count) {
+        lin_unpack<ND, E::UNIT_C>(r, H, g, cost, count);
+    }
+};
+
+// Kannala-Brandt: J_u[k_i] = fx*xr*theta^(2i+1), J_v[k_i] = fy*yr*theta^(2i+1), so every product
+// with a distortion column factors through the odd powers t_k = theta^(2k+3):
+//   H[f,d_k] = sum (m*f*r) t_k      H[c,d_k] = sum (f*r) t_k      g[d_k] = sum (fxr*ru + fyr*rv) t_k
+//   H[d_j,d_k] = sum (fxr^2 + fyr^2) theta^(2(j+k)+6)  -> depends on j+k only: 7 power sums S_m
+// 48 accumulate instructions per point instead of 63, 37 accumulators instead of 45.
+template <> struct LinOps<ACM_MODEL_KANNALA_BRANDT, ACM_RESIDUAL_PIXEL> {
+    static constexpr int ND = 4, P = 8;
+    static constexpr int HFF = 0, HFC = 2, GF = 4, GC = 6, HFD = 8, HCD = 16, S = 24, GD = 31, COST = 35, COUNT = 36, NACC = 37;
+    static __device__ __forceinline__ void point(double* acc, const LinParams& p, double x, double y, double z, double u, double v) {
+        const bool ok = z >= LIN_EPS;  // kannala_brandt.rs:345-351
+        double ir;
+        double r = fast_sqrt<true>(x * x + y * y, ir);
+        const bool on_axis = !(r >= LIN_EPS);
+        r = on_axis ? 0.0 : r;
+        const double th = fast_atan2_q1(r, ok ? z : 1.0);
+        const double xr = on_axis ? 0.0 : x * ir, yr = on_axis ? 0.0 : y * ir;
+        const double t2 = th * th, t3 = t2 * th, t5 = t3 * t2, t7 = t5 * t2, t9 = t7 * t2;
+        const double thd = fma(p.d[3], t9, fma(p.d[2], t7, fma(p.d[1], t5, fma(p.d[0], t3, th))));
+        double mx = thd * xr, my = thd * yr;
+        double ru = fma(p.fx, mx, p.cx) - u, rv = fma(p.fy, my, p.cy) - v;
+        double fxr = p.fx * xr, fyr = p.fy * yr;
+        mx = ok ? mx : 0.0; my = ok ? my : 0.0; ru = ok ? ru : 0.0; rv = ok ? rv : 0.0; fxr = ok ? fxr : 0.0; fyr = ok ? fyr : 0.0;
+        acc[HFF] = fma(mx, mx, acc[HFF]); acc[HFF + 1] = fma(my, my, acc[HFF + 1]);
+        acc[HFC] += mx; acc[HFC + 1] += my;
+        acc[GF] = fma(mx, ru, acc[GF]); acc[GF + 1] = fma(my, rv, acc[GF + 1]);
+        acc[GC] += ru; acc[GC + 1] += rv;
+        const double t[4] = {t3, t5, t7, t9};
+        const double a = mx * fxr, b = my * fyr, c = fma(fxr, ru, fyr * rv), w = fma(fxr, fxr, fyr * fyr);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            acc[HFD + k] = fma(a, t[k], acc[HFD + k]);
+            acc[HFD + 4 + k] = fma(b, t[k], acc[HFD + 4 + k]);
+            acc[HCD + k] = fma(fxr, t[k], acc[HCD + k]);
+            acc[HCD + 4 + k] = fma(fyr, t[k], acc[HCD + 4 + k]);
+            acc[GD + k] = fma(c, t[k], acc[GD + k]);
+        }
+        const double wt3 = w * t3, wt5 = w * t5, wt7 = w * t7, wt9 = w * t9;
+        acc[S + 0] = fma(wt3, t3, acc[S + 0]);  // theta^6
+        acc[S + 1] = fma(wt3, t5, acc[S + 1]);  // theta^8
+        acc[S + 2] = fma(wt3, t7, acc[S + 2]);  // theta^10
+        acc[S + 3] = fma(wt3, t9, acc[S + 3]);  // theta^12
+        acc[S + 4] = fma(wt5, t9, acc[S + 4]);  // theta^14
+        acc[S + 5] = fma(wt7, t9, acc[S + 5]);  // theta^16
+        acc[S + 6] = fma(wt9, t9, acc[S + 6]);  // theta^18
+        acc[COST] = fma(ru, ru, fma(rv, rv, acc[COST]));
+        acc[COUNT] += ok ? 1.0 : 0.0;
+    }
+    __host__ __device__ static void unpack(const double* r, double* H, double* g, double* cost, double* count) {
+        for (int i = 0; i < P * P; ++i) H[i] = 0.0;
+        const double cnt = r[COUNT];
+        H[0 * P + 0] = r[HFF]; H[1 * P + 1] = r[HFF + 1];
+        H[0 * P + 2] = r[HFC]; H[1 * P + 3] = r[HFC + 1];
+        H[2 * P + 2] = cnt; H[3 * P + 3] = cnt;
+        for (int k = 0; k < 4; ++k) {
+            H[0 * P + 4 + k] = r[HFD + k]; H[1 * P + 4 + k] = r[HFD + 4 + k];
+            H[2 * P + 4 + k] = r[HCD + k]; H[3 * P + 4 + k] = r[HCD + 4 + k];
+            for (int j = 0; j <= k; ++j) H[(4 + j) * P + 4 + k] = r[S + j + k];
+            g[4 + k] = r[GD + k];
+        }
+        g[0] = r[GF]; g[1] = r[GF + 1]; g[2] = r[GC]; g[3] = r[GC + 1];
+        for (int a = 0; a < P; ++a) for (int b = 0; b < a; ++b) H[a * P + b] = H[b * P + a];
+        *cost = 0.5 * r[COST];
+        *count = cnt;
+    }
+};

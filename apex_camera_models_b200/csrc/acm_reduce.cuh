@@ -32,8 +32,10 @@ __device__ __forceinline__ void dd_add_prod(double& hi, double& lo, double a, do
     dd_add(hi, lo, p, pe);
 }
 
-template <int NS, int NM, int NP>
+template <int NS, int NM, int NP, int BS = 256>
 struct GridReduce {
+    static_assert(BS == 128 || BS == 256, "block size must be 128 or 256");
+    static constexpr int NW = BS / 32, NSUB = BS / 64;
     static constexpr int N = NS + NM + 2 * NP;
     static constexpr int NSLOT = NS + NM + NP;  // one thread owns one slot (a pair counts once)
 
@@ -47,10 +49,10 @@ struct GridReduce {
 
     // acc: this thread's N values.  partials: gridDim.x * N doubles.  Returns true in every thread
     // of the last block, after `out[0..N)` holds the final values (visible to that block).
-    // Block size must be 256.
+    // Block size must be BS.
     static __device__ bool run(double* acc, double* __restrict__ partials, double* __restrict__ out, unsigned int* __restrict__ ticket) {
-        __shared__ double sm[8][N > 0 ? N : 1];
-        __shared__ double fin4[4][N > 0 ? N : 1];
+        __shared__ double sm[NW][N > 0 ? N : 1];
+        __shared__ double fin4[NSUB][N > 0 ? N : 1];
         __shared__ bool is_last;
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -82,7 +84,7 @@ struct GridReduce {
             const int off = slot_offset(threadIdx.x), w = slot_width(threadIdx.x);
             double a[2] = {sm[0][off], w == 2 ? sm[0][off + 1] : 0.0};
 #pragma unroll
-            for (int k = 1; k < 8; ++k) {
+            for (int k = 1; k < NW; ++k) {
                 double b[2] = {sm[k][off], w == 2 ? sm[k][off + 1] : 0.0};
                 combine_slot(a, b, threadIdx.x);
             }
@@ -98,11 +100,11 @@ struct GridReduce {
         __syncthreads();
         if (!is_last) return false;
         __threadfence();
-        // final pass: 4 contiguous block ranges per slot, then combined in fixed order
+        // final pass: NSUB contiguous block ranges per slot, then combined in fixed order
         static_assert(NSLOT <= 64, "final pass assumes <= 64 slots");
         const int slot = threadIdx.x & 63, sub = threadIdx.x >> 6;
         const unsigned int nb = gridDim.x;
-        const unsigned int b0 = (unsigned int)(((size_t)nb * sub) / 4), b1 = (unsigned int)(((size_t)nb * (sub + 1)) / 4);
+        const unsigned int b0 = (unsigned int)(((size_t)nb * sub) / NSUB), b1 = (unsigned int)(((size_t)nb * (sub + 1)) / NSUB);
         if (slot < NSLOT) {
             const int off = slot_offset(slot), w = slot_width(slot);
             double a[2];
@@ -119,7 +121,7 @@ struct GridReduce {
             const int off = slot_offset(threadIdx.x), w = slot_width(threadIdx.x);
             double a[2] = {fin4[0][off], w == 2 ? fin4[0][off + 1] : 0.0};
 #pragma unroll
-            for (int k = 1; k < 4; ++k) {
+            for (int k = 1; k < NSUB; ++k) {
                 double b[2] = {fin4[k][off], w == 2 ? fin4[k][off + 1] : 0.0};
                 combine_slot(a, b, threadIdx.x);
             }

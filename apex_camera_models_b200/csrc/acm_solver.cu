@@ -13,6 +13,8 @@
 #include "acm_reduce.cuh"
 #include "acm_models.cuh"
 
+#include <stdlib.h>
+
 #include <chrono>
 
 struct LmState {
@@ -30,17 +32,15 @@ static_assert(sizeof(LmState) <= 4096, "LmState must fit the context's 4 KiB slo
 // ---------------------------------------------------------------------------------------
 // linearize kernel
 // ---------------------------------------------------------------------------------------
-template <int M, int KIND>
-__global__ void __launch_bounds__(256) linearize_kernel(LinParams hp, const LmState* __restrict__ lm, const double2* __restrict__ X,
+template <int M, int KIND, int BS>
+__global__ void __launch_bounds__(BS) linearize_kernel(LinParams hp, const LmState* __restrict__ lm, const double2* __restrict__ X,
                                                         const double2* __restrict__ Y, const double2* __restrict__ Z,
                                                         const double2* __restrict__ U, const double2* __restrict__ V, size_t n,
                                                         double pen2x2, double* __restrict__ partials, double* __restrict__ out,
                                                         unsigned int* __restrict__ ticket) {
-    using LM_ = Lin<M, KIND>;
+    using LM_ = LinOps<M, KIND>;
     constexpr int ND = LM_::ND;
-    constexpr bool UNIT_C = LM_::UNIT_C;
-    using L = AccLayout<ND>;
-    constexpr int NACC = L::N;
+    constexpr int NACC = LM_::NACC;
     static_assert(NACC <= 64, "final-pass layout assumes <= 64 accumulators");
 
     LinParams p = hp;
@@ -69,11 +69,8 @@ __global__ void __launch_bounds__(256) linearize_kernel(LinParams hp, const LmSt
         const size_t nx = i + stride;
         const size_t j = nx < npairs ? nx : i;  // clamp: the tail re-reads its own (cached) packet
         const double2 x2 = __ldcs(X + j), y2 = __ldcs(Y + j), z2 = __ldcs(Z + j), u2 = __ldcs(U + j), v2 = __ldcs(V + j);
-        double ru0, rv0, au0[2 + ND], av0[2 + ND], ru1, rv1, au1[2 + ND], av1[2 + ND];
-        const bool ok0 = LM_::eval(p, x.x, y.x, z.x, u.x, v.x, ru0, rv0, au0, av0);
-        const bool ok1 = LM_::eval(p, x.y, y.y, z.y, u.y, v.y, ru1, rv1, au1, av1);
-        lin_accumulate_masked<ND, UNIT_C>(acc, ok0, ru0, rv0, au0, av0);
-        lin_accumulate_masked<ND, UNIT_C>(acc, ok1, ru1, rv1, au1, av1);
+        LM_::point(acc, p, x.x, y.x, z.x, u.x, v.x);
+        LM_::point(acc, p, x.y, y.y, z.y, u.y, v.y);
         x = x2; y = y2; z = z2; u = u2; v = v2;
         i = nx;
     }
@@ -82,37 +79,49 @@ __global__ void __launch_bounds__(256) linearize_kernel(LinParams hp, const LmSt
         const double* Xs = reinterpret_cast<const double*>(X); const double* Ys = reinterpret_cast<const double*>(Y);
         const double* Zs = reinterpret_cast<const double*>(Z); const double* Us = reinterpret_cast<const double*>(U);
         const double* Vs = reinterpret_cast<const double*>(V);
-        double ru, rv, au[2 + ND], av[2 + ND];
-        const bool ok = LM_::eval(p, Xs[t], Ys[t], Zs[t], Us[t], Vs[t], ru, rv, au, av);
-        lin_accumulate_masked<ND, UNIT_C>(acc, ok, ru, rv, au, av);
+        LM_::point(acc, p, Xs[t], Ys[t], Zs[t], Us[t], Vs[t]);
     }
 
-    if (GridReduce<NACC, 0, 0>::run(acc, partials, out, ticket)) {
+    if (GridReduce<NACC, 0, 0, BS>::run(acc, partials, out, ticket)) {
         // invalid points carry the residual (pen, pen): cost += pen^2 per invalid point
-        if (threadIdx.x == 0 && pen2x2 != 0.0) out[L::COST] += pen2x2 * ((double)n - out[L::COUNT]);
+        if (threadIdx.x == 0 && pen2x2 != 0.0) out[LM_::COST] += pen2x2 * ((double)n - out[LM_::COUNT]);
     }
 }
 
-template <int M, int KIND>
-static int32_t launch_linearize(acm_ctx* ctx, const LinParams& hp, const LmState* d_lm, const acm_points* xyz, const acm_points* uv,
-                                double invalid_penalty) {
-    using L = AccLayout<Lin<M, KIND>::ND>;
+template <int M, int KIND, int BS>
+static int32_t launch_linearize_bs(acm_ctx* ctx, const LinParams& hp, const LmState* d_lm, const acm_points* xyz, const acm_points* uv,
+                                   double invalid_penalty) {
     static int blocks_per_sm = 0;
     if (!blocks_per_sm) {
         int b = 0;
-        ACM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, linearize_kernel<M, KIND>, 256, 0));
+        ACM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, linearize_kernel<M, KIND, BS>, BS, 0));
         blocks_per_sm = b > 0 ? b : 1;
     }
     const size_t n = xyz->n;
-    int grid = grid_for(ctx, (n >> 1) + 1, 256, blocks_per_sm);
+    int grid = grid_for(ctx, (n >> 1) + 1, BS, blocks_per_sm);
     int32_t rc = acm_ensure_partials(ctx, (size_t)ctx->sm_count * 32 * 64);
     if (rc) return rc;
-    linearize_kernel<M, KIND><<<grid, 256, 0, ctx->stream>>>(
+    linearize_kernel<M, KIND, BS><<<grid, BS, 0, ctx->stream>>>(
         hp, d_lm, comp<double2>(xyz, 0), comp<double2>(xyz, 1), comp<double2>(xyz, 2), comp<double2>(uv, 0), comp<double2>(uv, 1), n,
         2.0 * invalid_penalty * invalid_penalty, ctx->d_partials, ctx->d_reduce, ctx->d_ticket);
     ACM_CHECK_LAUNCH(ctx);
-    (void)sizeof(L);
     return ACM_OK;
+}
+
+// Block size per model: the accumulators of the wide models (KB: 37 doubles) push the
+// kernel past 128 registers/thread; 128-thread blocks then pack one more block per SM.
+// ACM_LIN_BLOCK=128|256 overrides (tuning aid).
+template <int M, int KIND>
+static int32_t launch_linearize(acm_ctx* ctx, const LinParams& hp, const LmState* d_lm, const acm_points* xyz, const acm_points* uv,
+                                double invalid_penalty) {
+    static int bs = 0;
+    if (!bs) {
+        bs = (M == ACM_MODEL_KANNALA_BRANDT) ? 128 : 256;
+        const char* e = getenv("ACM_LIN_BLOCK");
+        if (e && (atoi(e) == 128 || atoi(e) == 256)) bs = atoi(e);
+    }
+    if (bs == 128) return launch_linearize_bs<M, KIND, 128>(ctx, hp, d_lm, xyz, uv, invalid_penalty);
+    return launch_linearize_bs<M, KIND, 256>(ctx, hp, d_lm, xyz, uv, invalid_penalty);
 }
 
 #define ACM_DISPATCH_LIN(model, kind, ...)                                                                       \
@@ -163,7 +172,7 @@ static int32_t enqueue_linearize(acm_ctx* ctx, const acm_camera* cam, int32_t ki
     ACM_DISPATCH_LIN(cam->model, kind, {
         int32_t rc = launch_linearize<M, KIND>(ctx, hp, d_lm, xyz, uv, invalid_penalty);
         if (rc) return rc;
-        *nacc = AccLayout<Lin<M, KIND>::ND>::N;
+        *nacc = LinOps<M, KIND>::NACC;
     });
     return acm_allreduce_sum_f64(ctx, ctx->d_reduce, (size_t)*nacc);
 }
@@ -172,7 +181,7 @@ static int32_t unpack_host(acm_ctx* ctx, const acm_camera* cam, int32_t kind, co
     memset(out, 0, sizeof(*out));
     out->n_params = cam->n_params;
     double cnt = 0.0;
-    ACM_DISPATCH_LIN(cam->model, kind, (lin_unpack<Lin<M, KIND>::ND, Lin<M, KIND>::UNIT_C>(r, out->H, out->g, &out->cost, &cnt)));
+    ACM_DISPATCH_LIN(cam->model, kind, (LinOps<M, KIND>::unpack(r, out->H, out->g, &out->cost, &cnt)));
     out->n_valid = (uint64_t)cnt;
     return ACM_OK;
 }
@@ -235,13 +244,13 @@ __device__ inline bool chol_solve_dev(int P, const double* A, const double* b, d
 
 __device__ inline double clampd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
-template <int ND, bool UNIT_C>
+template <int M, int KIND>
 __global__ void lm_step_kernel(LmState* __restrict__ s, const double* __restrict__ red) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     if (s->done) return;
-    constexpr int P = 4 + ND;
+    constexpr int P = LinOps<M, KIND>::P;
     double Ht[P * P], gt[P], cost_t, cnt;
-    lin_unpack<ND, UNIT_C>(red, Ht, gt, &cost_t, &cnt);
+    LinOps<M, KIND>::unpack(red, Ht, gt, &cost_t, &cnt);
     s->passes++;
     bool accepted = false;
     if (s->first) {
@@ -351,7 +360,7 @@ extern "C" int32_t acm_lm_solve(acm_ctx* ctx, const acm_camera* init, int32_t re
     auto one_iteration = [&]() -> int32_t {
         int32_t r = enqueue_linearize(ctx, init, residual_kind, d, xyz, uv, cfg.invalid_penalty, &nacc);
         if (r) return r;
-        ACM_DISPATCH_LIN(init->model, residual_kind, (lm_step_kernel<Lin<M, KIND>::ND, Lin<M, KIND>::UNIT_C><<<1, 32, 0, ctx->stream>>>(d, ctx->d_reduce)));
+        ACM_DISPATCH_LIN(init->model, residual_kind, (lm_step_kernel<M, KIND><<<1, 32, 0, ctx->stream>>>(d, ctx->d_reduce)));
         ACM_CHECK_LAUNCH(ctx);
         return ACM_OK;
     };
