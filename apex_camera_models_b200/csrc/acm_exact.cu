@@ -6,6 +6,8 @@
 //
 // Data movement (HBM-bound kernels): SoA components, one 16-byte vector load per component
 // per thread (2 f64 or 4 f32 points), grid-stride loop over a grid of sm_count * k blocks.
+#include <stdlib.h>
+
 #include "acm_models.cuh"
 
 // ---------------------------------------------------------------------------------------
@@ -272,6 +274,132 @@ __global__ void __launch_bounds__(256) undistort_kernel(const __grid_constant__ 
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Fast bilinear path (W % 4 == 0, 4-byte aligned frames).  Byte-exact by construction:
+//  * The reference blends in f64 (undistort.rs:92-99) and rounds half away from zero.  Here the
+//    four tap weights are quantised once per output pixel to 24-bit fixed point
+//    (W_i = rn(w_i * 2^24), sum <= 2^24 + 2, so sum p_i W_i fits 32 bits).
+//    |S / 2^24 - sum p_i w_i| <= 4 * 255 * 2^-25 = 3.04e-5 and the f64 evaluation order of the
+//    reference moves the value by < 1e-12, so whenever the fractional part of S + 0.5 is farther
+//    than E = 640 / 2^24 = 3.8e-5 from an integer both round to the same byte.  Otherwise
+//    (probability 7.6e-5 per channel) the pixel is redone with the reference's exact f64
+//    expression, as are pixels with a weight of exactly 1 or whose window would leave the frame.
+//  * Instruction diet (the first version of this kernel was issue-bound at 151 instr/pixel):
+//    each 6-byte tap run is three aligned 32-bit loads + two PRMT with a per-pixel selector;
+//    five more PRMT gather the four taps of each channel into one register; the blend is three
+//    dp4a per channel against the weights split into byte planes (W = hi<<16 | mid<<8 | lo).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void blend_exact_px(const uint8_t* p, int row_stride, double wx, double wy, uint8_t* o) {
+    const uint8_t* q = p + row_stride;
+    const double wxi = 1.0 - wx, wyi = 1.0 - wy;
+    o[0] = blend(__ldg(p), __ldg(p + 3), __ldg(q), __ldg(q + 3), wx, wy, wxi, wyi);
+    o[1] = blend(__ldg(p + 1), __ldg(p + 4), __ldg(q + 1), __ldg(q + 4), wx, wy, wxi, wyi);
+    o[2] = blend(__ldg(p + 2), __ldg(p + 5), __ldg(q + 2), __ldg(q + 5), wx, wy, wxi, wyi);
+}
+
+// Thread <-> pixel mapping: a warp owns a 32-wide, 4-tall output patch, lane = x.  Neighbouring
+// lanes then read neighbouring source pixels (3 bytes apart), so one warp-wide 32-bit load touches
+// ~4 sectors instead of the ~17 of a "4 consecutive pixels per thread" mapping (ncu: the first
+// mapping was bound by L1 sector look-ups, 444 M per 8 frames).  The 96 output bytes of a patch row
+// are exchanged with two shuffles so that 24 lanes store one aligned word each.
+template <int M>
+__global__ void __launch_bounds__(256, 3) undistort_bilinear_fast_kernel(const __grid_constant__ CamParams c, double tfx, double tfy,
+                                                                      double tcx, double tcy, const uint8_t* __restrict__ in,
+                                                                      uint8_t* __restrict__ out, int W, int H, size_t n_frames) {
+    constexpr uint32_t TIE_E = 640u;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x0 = blockIdx.x * 64 + (warp & 1) * 32;        // patch origin
+    const int y0 = blockIdx.y * 16 + (warp >> 1) * 4;
+    const int uo = x0 + lane;
+    const size_t frame_bytes = (size_t)W * H * 3;
+    const int row_stride = 3 * W;
+    int off[4], offa[4], mode[4];          // mode: 0 black, 1 fast, 2 exact only, 3 redo this frame exactly
+    uint32_t sel[4], wlo[4], wmid[4], whi[4];
+    double wx[4], wy[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int vo = y0 + k;
+        double sx = 0.0, sy = 0.0;
+        int st = ACM_POINT_IS_OUTSIDE_IMAGE;
+        if (uo < W && vo < H) {
+            const double xn = ((double)uo - tcx) / tfx;
+            const double yn = ((double)vo - tcy) / tfy;
+            st = CamModel<M>::template project<true>(c, xn, yn, 1.0, sx, sy);
+        }
+        const Tap t = make_tap(sx, sy, st, W, H, ACM_INTERP_BILINEAR);
+        off[k] = t.off00; wx[k] = t.wx; wy[k] = t.wy;
+        mode[k] = t.ok ? 1 : 0;
+        const double wxi = 1.0 - t.wx, wyi = 1.0 - t.wy;
+        const uint32_t w00 = __double2uint_rn(wxi * wyi * 16777216.0), w10 = __double2uint_rn(t.wx * wyi * 16777216.0);
+        const uint32_t w01 = __double2uint_rn(wxi * t.wy * 16777216.0), w11 = __double2uint_rn(t.wx * t.wy * 16777216.0);
+        if (t.ok && ((size_t)t.off00 + (size_t)row_stride + 16 > frame_bytes || ((w00 | w10 | w01 | w11) >> 24))) mode[k] = 2;
+        // byte planes, tap order [00, 10, 01, 11]
+        wlo[k] = (w00 & 0xFF) | ((w10 & 0xFF) << 8) | ((w01 & 0xFF) << 16) | ((w11 & 0xFF) << 24);
+        wmid[k] = ((w00 >> 8) & 0xFF) | (((w10 >> 8) & 0xFF) << 8) | (((w01 >> 8) & 0xFF) << 16) | (((w11 >> 8) & 0xFF) << 24);
+        whi[k] = ((w00 >> 16) & 0xFF) | (((w10 >> 16) & 0xFF) << 8) | (((w01 >> 16) & 0xFF) << 16) | (((w11 >> 16) & 0xFF) << 24);
+        sel[k] = 0x3210u + 0x1111u * (uint32_t)(t.off00 & 3);
+        // invalid pixels load from offset 0 (always inside the frame): the 24 tap loads of a thread
+        // are issued back to back, ahead of any math or branch
+        offa[k] = mode[k] == 1 ? (t.off00 & ~3) : 0;
+    }
+    const bool has_slow = (mode[0] == 2) | (mode[1] == 2) | (mode[2] == 2) | (mode[3] == 2);
+    // output exchange: lane j < 24 stores word j of the 96-byte patch row = bytes of pixels p, p+1
+    const int src_lane = (4 * lane) / 3;
+    const uint32_t out_sel = (lane % 3 == 0) ? 0x4210u : (lane % 3 == 1) ? 0x5421u : 0x6542u;
+    const int valid_px = min(32, W - x0);                     // multiple of 4 because W % 4 == 0
+    const bool store_lane = (lane < 24) && (4 * lane + 3 < 3 * valid_px);
+    for (size_t f = 0; f < n_frames; ++f) {
+        const uint8_t* src = in + f * frame_bytes;
+        uint32_t ta[4][3], tb[4][3];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t* r0 = reinterpret_cast<const uint32_t*>(src + offa[k]);
+            const uint32_t* r1 = reinterpret_cast<const uint32_t*>(src + offa[k] + row_stride);
+            ta[k][0] = __ldg(r0); ta[k][1] = __ldg(r0 + 1); ta[k][2] = __ldg(r0 + 2);
+            tb[k][0] = __ldg(r1); tb[k][1] = __ldg(r1 + 1); tb[k][2] = __ldg(r1 + 2);
+        }
+        uint32_t px[4];  // [R G B .] per pixel
+        bool any_tie = false;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t A = __byte_perm(ta[k][0], ta[k][1], sel[k]), B = __byte_perm(ta[k][1], ta[k][2], sel[k]);    // [r0 g0 b0 r1] [g1 b1 . .]
+            const uint32_t A2 = __byte_perm(tb[k][0], tb[k][1], sel[k]), B2 = __byte_perm(tb[k][1], tb[k][2], sel[k]);
+            const uint32_t PR = __byte_perm(A, A2, 0x7430);                                       // [r00 r10 r01 r11]
+            const uint32_t T0 = __byte_perm(A, B, 0x5241), T1 = __byte_perm(A2, B2, 0x5241);      // [g0 g1 b0 b1]
+            const uint32_t PG = __byte_perm(T0, T1, 0x5410), PB = __byte_perm(T0, T1, 0x7632);
+            const uint32_t sr = (__dp4a(PR, whi[k], 0u) << 16) + (__dp4a(PR, wmid[k], 0u) << 8) + __dp4a(PR, wlo[k], 1u << 23);
+            const uint32_t sg = (__dp4a(PG, whi[k], 0u) << 16) + (__dp4a(PG, wmid[k], 0u) << 8) + __dp4a(PG, wlo[k], 1u << 23);
+            const uint32_t sb = (__dp4a(PB, whi[k], 0u) << 16) + (__dp4a(PB, wmid[k], 0u) << 8) + __dp4a(PB, wlo[k], 1u << 23);
+            const uint32_t rgb = __byte_perm(__byte_perm(sr, sg, 0x4473), sb, 0x4710);            // [sr.3 sg.3 sb.3 .]
+            const bool tie = (((sr + TIE_E) & 0xFFFFFFu) < 2u * TIE_E) | (((sg + TIE_E) & 0xFFFFFFu) < 2u * TIE_E) |
+                             (((sb + TIE_E) & 0xFFFFFFu) < 2u * TIE_E);
+            px[k] = mode[k] == 1 ? rgb : 0u;
+            if (tie && mode[k] == 1) { any_tie = true; mode[k] = 3; }
+        }
+        if (any_tie || has_slow) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (mode[k] >= 2) {
+                    uint8_t o[3];
+                    blend_exact_px(src + off[k], row_stride, wx[k], wy[k], o);
+                    px[k] = o[0] | (o[1] << 8) | ((uint32_t)o[2] << 16);
+                    if (mode[k] == 3) mode[k] = 1;
+                }
+            }
+        }
+        uint8_t* dst = out + f * frame_bytes;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t pa = __shfl_sync(0xffffffffu, px[k], src_lane);
+            const uint32_t pb = __shfl_sync(0xffffffffu, px[k], (src_lane + 1) & 31);
+            if (store_lane && y0 + k < H) {
+                uint32_t* d32 = reinterpret_cast<uint32_t*>(dst + ((size_t)(y0 + k) * W + x0) * 3) + lane;
+                __stcs(d32, __byte_perm(pa, pb, out_sel));
+            }
+        }
+    }
+}
+
 template <int M>
 __global__ void __launch_bounds__(256) undistort_map_kernel(const __grid_constant__ CamParams c, double tfx, double tfy, double tcx,
                                                             double tcy, double* __restrict__ src_xy, int W, int H) {
@@ -307,7 +435,13 @@ extern "C" int32_t acm_undistort_rgb8(acm_ctx* ctx, const acm_camera* cam, const
     if (rc) return rc;
     const int W = (int)cam->width, H = (int)cam->height;
     dim3 grid((W + 1023) / 1024, H);
-    ACM_DISPATCH_MODEL(cam->model, (undistort_kernel<M><<<grid, 256, 0, ctx->stream>>>(c, t[0], t[1], t[2], t[3], d_in, d_out, W, H, n_frames, interpolation)))
+    const bool aligned = ((reinterpret_cast<uintptr_t>(d_in) & 3) == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 3) == 0) && (W % 4 == 0);
+    if (interpolation == ACM_INTERP_BILINEAR && aligned && !getenv("ACM_UNDISTORT_GENERIC")) {
+        dim3 fgrid((W + 63) / 64, (H + 15) / 16);
+        ACM_DISPATCH_MODEL(cam->model, (undistort_bilinear_fast_kernel<M><<<fgrid, 256, 0, ctx->stream>>>(c, t[0], t[1], t[2], t[3], d_in, d_out, W, H, n_frames)))
+    } else {
+        ACM_DISPATCH_MODEL(cam->model, (undistort_kernel<M><<<grid, 256, 0, ctx->stream>>>(c, t[0], t[1], t[2], t[3], d_in, d_out, W, H, n_frames, interpolation)))
+    }
     ACM_CHECK_LAUNCH(ctx);
     return ACM_OK;
 }

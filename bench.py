@@ -360,11 +360,12 @@ def run_extras(acm, N, lib, ctx, X, UV, n):
         pu[names[mid]] = {"project_ms": ms, "project_gb_s": n * 41 / ms / 1e6, "unproject_ms": ms2, "unproject_gb_s": n * 41 / ms2 / 1e6}
     out["project_unproject_100M_f64"] = pu
     ctx.device_free(st); UV2.free(); X2.free()
-    # undistort: 4096x4096 KB fisheye (sample intrinsics x8), 8 frames resident in HBM
+    # undistort (BASELINE config 5): 4096x4096 KB fisheye (sample intrinsics x8), 32 frames resident in HBM
+    # = the per-GPU share of the 256-frame batch on 8 GPUs
     W = H = 4096
     kb8 = acm.KannalaBrandtModel(acm.Intrinsics(*(v * 8 for v in KB_SAMPLE[:4])), acm.Resolution(W, H), KB_SAMPLE[4:], ctx=ctx)
     cam = kb8.camera_block()
-    F = 8
+    F = 32
     fb = W * H * 3
     d_in = ctx.device_alloc(fb * F); d_out = ctx.device_alloc(fb * F)
     ctx.check(lib.acm_synth_bytes(ctx.handle, 0xACE50005, 0, C.c_void_p(d_in), fb * F))
