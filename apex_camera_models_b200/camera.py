@@ -245,6 +245,27 @@ class CameraModel:
         ctx.device_free(st_d); src.free(); dst.free()
         return out, st
 
+    def round_trip_batch(self, points_3d, dtype: int = N.F64):
+        """Fused project -> unproject (BASELINE config 2): (uv, ray, status_project, status_unproject).
+        Host (N,3) array in -> numpy out; device `Points` in -> (Points, Points, status ptr, status ptr)."""
+        ctx = self.ctx
+        cam = self.camera_block()
+        on_device = isinstance(points_3d, Points)
+        src = points_3d if on_device else Points.from_numpy(ctx, np.ascontiguousarray(points_3d, dtype=np.float64).reshape(-1, 3), dtype)
+        n = len(src)
+        uv, ray = Points(ctx, 2, n, src.dtype), Points(ctx, 3, n, src.dtype)
+        sp, su = ctx.device_alloc(max(n, 1)), ctx.device_alloc(max(n, 1))
+        ctx.check(_lib.acm_project_unproject(ctx.handle, C.byref(cam), src.handle, uv.handle, ray.handle, C.c_void_p(sp), C.c_void_p(su)))
+        if on_device:
+            return uv, ray, sp, su
+        a, b = uv.numpy(), ray.numpy()
+        s1, s2 = np.empty(n, dtype=np.uint8), np.empty(n, dtype=np.uint8)
+        if n:
+            ctx.d2h(s1, sp); ctx.d2h(s2, su)
+        ctx.sync()
+        ctx.device_free(sp); ctx.device_free(su); src.free(); uv.free(); ray.free()
+        return a, b, s1, s2
+
     def project_jacobian_batch(self, points_3d):
         """uv (N,2), J (N,2,P) w.r.t. [fx,fy,cx,cy,dist..], status (N,); geometric validity only."""
         ctx = self.ctx

@@ -143,6 +143,84 @@ static int32_t launch_unproject(acm_ctx* ctx, const CamParams& c, const acm_poin
     return ACM_OK;
 }
 
+// ---------------------------------------------------------------------------------------
+// fused round trip: xyz -> uv -> ray (BASELINE config 2)
+// ---------------------------------------------------------------------------------------
+template <int M, typename T>
+__global__ void __launch_bounds__(256) round_trip_kernel(const __grid_constant__ CamParams c, const T* __restrict__ X, const T* __restrict__ Y,
+                                                         const T* __restrict__ Z, T* __restrict__ U, T* __restrict__ V, T* __restrict__ RX,
+                                                         T* __restrict__ RY, T* __restrict__ RZ, uint8_t* __restrict__ SP,
+                                                         uint8_t* __restrict__ SU, size_t n) {
+    using VT = typename Vec<T>::type;
+    constexpr int NV = Vec<T>::N;
+    const size_t npk = n / NV;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    auto one = [&](double x, double y, double z, double& u, double& v, double& rx, double& ry, double& rz, int& sp, int& su) {
+        u = v = rx = ry = rz = acm_nan();
+        double uu, vv;
+        sp = CamModel<M>::template project<true>(c, x, y, z, uu, vv);
+        su = sp;
+        if (sp == ACM_POINT_OK) {
+            u = uu; v = vv;
+            if (sizeof(T) == 4) { uu = (double)(float)uu; vv = (double)(float)vv; }  // what the two-kernel path would read back
+            double ax, ay, az;
+            su = CamModel<M>::unproject(c, uu, vv, ax, ay, az);
+            if (su == ACM_POINT_OK) { rx = ax; ry = ay; rz = az; }
+        }
+    };
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npk; p += stride) {
+        double x[NV], y[NV], z[NV], u[NV], v[NV], rx[NV], ry[NV], rz[NV];
+        int sp[NV], su[NV];
+        Vec<T>::unpack(ld_stream(reinterpret_cast<const VT*>(X) + p), x);
+        Vec<T>::unpack(ld_stream(reinterpret_cast<const VT*>(Y) + p), y);
+        Vec<T>::unpack(ld_stream(reinterpret_cast<const VT*>(Z) + p), z);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) one(x[k], y[k], z[k], u[k], v[k], rx[k], ry[k], rz[k], sp[k], su[k]);
+        st_stream(reinterpret_cast<VT*>(U) + p, Vec<T>::pack(u));
+        st_stream(reinterpret_cast<VT*>(V) + p, Vec<T>::pack(v));
+        st_stream(reinterpret_cast<VT*>(RX) + p, Vec<T>::pack(rx));
+        st_stream(reinterpret_cast<VT*>(RY) + p, Vec<T>::pack(ry));
+        st_stream(reinterpret_cast<VT*>(RZ) + p, Vec<T>::pack(rz));
+        if (SP) StatusVec<NV>::store(SP + p * NV, sp);
+        if (SU) StatusVec<NV>::store(SU + p * NV, su);
+    }
+    const size_t t = npk * NV + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) {
+        double u, v, rx, ry, rz; int sp, su;
+        one((double)X[t], (double)Y[t], (double)Z[t], u, v, rx, ry, rz, sp, su);
+        U[t] = (T)u; V[t] = (T)v; RX[t] = (T)rx; RY[t] = (T)ry; RZ[t] = (T)rz;
+        if (SP) SP[t] = (uint8_t)sp;
+        if (SU) SU[t] = (uint8_t)su;
+    }
+}
+
+template <int M, typename T>
+static int32_t launch_round_trip(acm_ctx* ctx, const CamParams& c, const acm_points* xyz, acm_points* uv, acm_points* ray, uint8_t* sp, uint8_t* su) {
+    const size_t n = xyz->n;
+    if (n == 0) return ACM_OK;
+    constexpr int NV = Vec<T>::N;
+    int grid = grid_for(ctx, n / NV + NV, 256, 8);
+    round_trip_kernel<M, T><<<grid, 256, 0, ctx->stream>>>(c, comp<T>(xyz, 0), comp<T>(xyz, 1), comp<T>(xyz, 2), comp<T>(uv, 0), comp<T>(uv, 1),
+                                                            comp<T>(ray, 0), comp<T>(ray, 1), comp<T>(ray, 2), sp, su, n);
+    ACM_CHECK_LAUNCH(ctx);
+    return ACM_OK;
+}
+
+extern "C" int32_t acm_project_unproject(acm_ctx* ctx, const acm_camera* cam, const acm_points* xyz, acm_points* uv, acm_points* ray,
+                                         uint8_t* d_status_project, uint8_t* d_status_unproject) {
+    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_REQUIRE(ctx, cam && xyz && uv && ray, "acm_project_unproject: null argument");
+    ACM_REQUIRE(ctx, xyz->dim == 3 && uv->dim == 2 && ray->dim == 3, "acm_project_unproject: xyz / ray must have dim 3 and uv dim 2");
+    ACM_REQUIRE(ctx, xyz->n == uv->n && xyz->n == ray->n, "acm_project_unproject: point counts differ");
+    ACM_REQUIRE(ctx, xyz->dtype == uv->dtype && xyz->dtype == ray->dtype, "acm_project_unproject: dtypes differ");
+    CamParams c;
+    int32_t rc = acm_make_cam_params(ctx, cam, &c);
+    if (rc) return rc;
+    if (xyz->dtype == ACM_F64) { ACM_DISPATCH_MODEL(cam->model, return (launch_round_trip<M, double>(ctx, c, xyz, uv, ray, d_status_project, d_status_unproject))) }
+    else { ACM_DISPATCH_MODEL(cam->model, return (launch_round_trip<M, float>(ctx, c, xyz, uv, ray, d_status_project, d_status_unproject))) }
+    return ACM_OK;
+}
+
 extern "C" int32_t acm_project(acm_ctx* ctx, const acm_camera* cam, const acm_points* xyz, acm_points* uv, uint8_t* d_status) {
     if (!ctx) return ACM_ERR_INVALID_ARG;
     ACM_REQUIRE(ctx, cam && xyz && uv, "acm_project: null argument");

@@ -30,10 +30,168 @@ struct LmState {
 static_assert(sizeof(LmState) <= 4096, "LmState must fit the context's 4 KiB slot");
 
 // ---------------------------------------------------------------------------------------
+// LM step: serial algebra on P <= 9 unknowns, run by one thread out of shared memory.
+// Written for a small register footprint (arrays in the shared LmWork, rolled loops, not
+// inlined) because it is also called from the tail of the streaming kernel.
+// Divisions are hoisted into reciprocals (1/D_i, 1/L_ii): a serial f64 division costs ~250
+// cycles and the first version spent most of its 12 us on ~50 of them.
+// ---------------------------------------------------------------------------------------
+struct LmWork {
+    double Ht[ACM_MAX_PARAMS * ACM_MAX_PARAMS], A[ACM_MAX_PARAMS * ACM_MAX_PARAMS], L[ACM_MAX_PARAMS * ACM_MAX_PARAMS];
+    double gt[ACM_MAX_PARAMS], invD[ACM_MAX_PARAMS], gs[ACM_MAX_PARAMS], st[ACM_MAX_PARAMS], dx[ACM_MAX_PARAMS], yv[ACM_MAX_PARAMS],
+        invdiag[ACM_MAX_PARAMS];
+    double red[64];
+};
+
+__device__ __noinline__ bool chol_solve_work(int P, LmWork* w) {
+    double* L = w->L;
+#pragma unroll 1
+    for (int i = 0; i < P; ++i) {
+#pragma unroll 1
+        for (int j = 0; j <= i; ++j) {
+            double sum = w->A[i * P + j];
+#pragma unroll 1
+            for (int k = 0; k < j; ++k) sum -= L[i * P + k] * L[j * P + k];
+            if (i == j) {
+                if (!(sum > 0.0)) return false;
+                const double d = sqrt(sum);
+                L[i * P + i] = d;
+                w->invdiag[i] = 1.0 / d;
+            } else {
+                L[i * P + j] = sum * w->invdiag[j];
+            }
+        }
+    }
+#pragma unroll 1
+    for (int i = 0; i < P; ++i) {
+        double sum = w->gs[i];
+#pragma unroll 1
+        for (int k = 0; k < i; ++k) sum -= L[i * P + k] * w->yv[k];
+        w->yv[i] = sum * w->invdiag[i];
+    }
+#pragma unroll 1
+    for (int i = P - 1; i >= 0; --i) {
+        double sum = w->yv[i];
+#pragma unroll 1
+        for (int k = i + 1; k < P; ++k) sum -= L[k * P + i] * w->st[k];
+        w->st[i] = sum * w->invdiag[i];
+    }
+    return true;
+}
+
+__device__ inline double clampd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+__device__ __noinline__ void lm_step_core(int P, LmState* s, LmWork* w, double cost_t, double cnt) {
+    s->passes++;
+    bool accepted = false;
+    if (s->first) {
+        s->first = 0;
+        s->initial_cost = cost_t;
+        accepted = true;
+    } else {
+        const bool small_step = s->dnorm <= s->param_tol * (s->xnorm + s->param_tol);
+        if (s->pred > 0.0 && cost_t < s->cost) {
+            const double rho = (s->cost - cost_t) / s->pred;
+            const double dcost = s->cost - cost_t, cost_old = s->cost;
+            const double q = 2.0 * rho - 1.0, f = 1.0 - q * q * q;
+            s->lambda *= (f > 1.0 / 3.0) ? f : 1.0 / 3.0;
+            s->nu = 2.0;
+            if (s->lambda < 1e-15) s->lambda = 1e-15;
+            accepted = true;
+            double gmax = 0.0;
+#pragma unroll 1
+            for (int i = 0; i < P; ++i) gmax = fmax(gmax, fabs(w->gt[i]));
+            if (dcost <= s->cost_tol * cost_old) { s->status = 0; s->done = 1; }
+            else if (small_step) { s->status = 1; s->done = 1; }
+            else if (gmax <= s->grad_tol) { s->status = 2; s->done = 1; }
+        } else {
+            if (small_step) { s->status = 1; s->done = 1; }
+            else {
+                s->lambda *= s->nu; s->nu *= 2.0;
+                if (s->lambda > 1e30) { s->status = 4; s->done = 1; }
+            }
+        }
+    }
+    if (accepted) {
+#pragma unroll 1
+        for (int i = 0; i < P; ++i) { s->x[i] = s->xt[i]; s->g[i] = w->gt[i]; }
+#pragma unroll 1
+        for (int i = 0; i < P * P; ++i) s->H[i] = w->Ht[i];
+        s->cost = cost_t; s->n_valid = cnt;
+    }
+    if (s->done) return;
+    // next trial point from (H, g, lambda) at the accepted x
+    for (;;) {
+        if (s->iterations >= s->max_iter) { s->status = 3; s->done = 1; return; }
+        s->iterations++;
+#pragma unroll 1
+        for (int i = 0; i < P; ++i) { const double d = sqrt(s->H[i * P + i]); w->invD[i] = (d > 1e-300) ? 1.0 / d : 1.0; }
+#pragma unroll 1
+        for (int i = 0; i < P; ++i) {
+#pragma unroll 1
+            for (int j = 0; j < P; ++j) w->A[i * P + j] = s->H[i * P + j] * w->invD[i] * w->invD[j];
+            w->A[i * P + i] += s->lambda;
+            w->gs[i] = -s->g[i] * w->invD[i];
+        }
+        if (chol_solve_work(P, w)) break;
+        s->lambda *= s->nu; s->nu *= 2.0;
+        if (s->lambda > 1e30) { s->status = 4; s->done = 1; return; }
+    }
+    double xnorm = 0.0, dnorm = 0.0;
+#pragma unroll 1
+    for (int i = 0; i < P; ++i) {
+        s->xt[i] = clampd(s->x[i] + w->st[i] * w->invD[i], s->lower[i], s->upper[i]);
+        w->dx[i] = s->xt[i] - s->x[i];
+        xnorm += s->x[i] * s->x[i]; dnorm += w->dx[i] * w->dx[i];
+    }
+    double pred = 0.0;
+#pragma unroll 1
+    for (int i = 0; i < P; ++i) {
+        double hd = 0.0;
+#pragma unroll 1
+        for (int j = 0; j < P; ++j) hd += s->H[i * P + j] * w->dx[j];
+        pred -= w->dx[i] * (s->g[i] + 0.5 * hd);
+    }
+    s->xnorm = sqrt(xnorm); s->dnorm = sqrt(dnorm); s->pred = pred;
+}
+
+// Cooperative wrapper: `nthreads` threads copy the 1.1 KB state and the reduced accumulators into
+// shared memory, thread 0 runs the step, the threads copy the state back.  Returns immediately
+// (all threads) if the solve has already finished.
+template <int M, int KIND>
+__device__ __forceinline__ void lm_step_block(LmState* __restrict__ s, const double* __restrict__ red, LmState* sh, LmWork* w,
+                                              int tid, int nthreads) {
+    static_assert(sizeof(LmState) % sizeof(double) == 0, "LmState is copied as doubles");
+    constexpr int NW = sizeof(LmState) / sizeof(double);
+    double* shw = reinterpret_cast<double*>(sh);
+    const double* gw = reinterpret_cast<const double*>(s);
+    for (int i = tid; i < NW; i += nthreads) shw[i] = __ldcg(gw + i);
+    for (int i = tid; i < LinOps<M, KIND>::NACC; i += nthreads) w->red[i] = __ldcg(red + i);
+    __syncthreads();
+    if (sh->done) return;
+    if (tid == 0) {
+        double cost_t, cnt;
+        LinOps<M, KIND>::unpack(w->red, w->Ht, w->gt, &cost_t, &cnt);
+        lm_step_core(LinOps<M, KIND>::P, sh, w, cost_t, cnt);
+    }
+    __syncthreads();
+    double* gout = reinterpret_cast<double*>(s);
+    for (int i = tid; i < NW; i += nthreads) gout[i] = shw[i];
+}
+
+// Stand-alone step kernel: used when an all-reduce sits between the pass and the step (N > 1).
+template <int M, int KIND>
+__global__ void __launch_bounds__(64) lm_step_kernel(LmState* __restrict__ s, const double* __restrict__ red) {
+    __shared__ LmState sh;
+    __shared__ LmWork work;
+    lm_step_block<M, KIND>(s, red, &sh, &work, threadIdx.x, blockDim.x);
+}
+
+// ---------------------------------------------------------------------------------------
 // linearize kernel
 // ---------------------------------------------------------------------------------------
 template <int M, int KIND, int BS>
-__global__ void __launch_bounds__(BS) linearize_kernel(LinParams hp, const LmState* __restrict__ lm, const double2* __restrict__ X,
+__global__ void __launch_bounds__(BS) linearize_kernel(LinParams hp, LmState* __restrict__ lm, int fuse_step, const double2* __restrict__ X,
                                                         const double2* __restrict__ Y, const double2* __restrict__ Z,
                                                         const double2* __restrict__ U, const double2* __restrict__ V, size_t n,
                                                         double pen2x2, double* __restrict__ partials, double* __restrict__ out,
@@ -85,12 +243,21 @@ __global__ void __launch_bounds__(BS) linearize_kernel(LinParams hp, const LmSta
     if (GridReduce<NACC, 0, 0, BS>::run(acc, partials, out, ticket)) {
         // invalid points carry the residual (pen, pen): cost += pen^2 per invalid point
         if (threadIdx.x == 0 && pen2x2 != 0.0) out[LM_::COST] += pen2x2 * ((double)n - out[LM_::COUNT]);
+        if (lm && fuse_step) {
+            // single GPU: no all-reduce between the pass and the step, so the last block takes the
+            // LM step right here (saves a launch and the global round trip of the sums)
+            __shared__ LmState sh;
+            __shared__ LmWork work;
+            __threadfence();
+            __syncthreads();
+            lm_step_block<M, KIND>(lm, out, &sh, &work, threadIdx.x, BS);
+        }
     }
 }
 
 template <int M, int KIND, int BS>
-static int32_t launch_linearize_bs(acm_ctx* ctx, const LinParams& hp, const LmState* d_lm, const acm_points* xyz, const acm_points* uv,
-                                   double invalid_penalty) {
+static int32_t launch_linearize_bs(acm_ctx* ctx, const LinParams& hp, LmState* d_lm, int fuse_step, const acm_points* xyz,
+                                   const acm_points* uv, double invalid_penalty) {
     static int blocks_per_sm = 0;
     if (!blocks_per_sm) {
         int b = 0;
@@ -102,7 +269,7 @@ static int32_t launch_linearize_bs(acm_ctx* ctx, const LinParams& hp, const LmSt
     int32_t rc = acm_ensure_partials(ctx, (size_t)ctx->sm_count * 32 * 64);
     if (rc) return rc;
     linearize_kernel<M, KIND, BS><<<grid, BS, 0, ctx->stream>>>(
-        hp, d_lm, comp<double2>(xyz, 0), comp<double2>(xyz, 1), comp<double2>(xyz, 2), comp<double2>(uv, 0), comp<double2>(uv, 1), n,
+        hp, d_lm, fuse_step, comp<double2>(xyz, 0), comp<double2>(xyz, 1), comp<double2>(xyz, 2), comp<double2>(uv, 0), comp<double2>(uv, 1), n,
         2.0 * invalid_penalty * invalid_penalty, ctx->d_partials, ctx->d_reduce, ctx->d_ticket);
     ACM_CHECK_LAUNCH(ctx);
     return ACM_OK;
@@ -112,16 +279,16 @@ static int32_t launch_linearize_bs(acm_ctx* ctx, const LinParams& hp, const LmSt
 // kernel past 128 registers/thread; 128-thread blocks then pack one more block per SM.
 // ACM_LIN_BLOCK=128|256 overrides (tuning aid).
 template <int M, int KIND>
-static int32_t launch_linearize(acm_ctx* ctx, const LinParams& hp, const LmState* d_lm, const acm_points* xyz, const acm_points* uv,
-                                double invalid_penalty) {
+static int32_t launch_linearize(acm_ctx* ctx, const LinParams& hp, LmState* d_lm, int fuse_step, const acm_points* xyz,
+                                const acm_points* uv, double invalid_penalty) {
     static int bs = 0;
     if (!bs) {
         bs = (M == ACM_MODEL_KANNALA_BRANDT) ? 128 : 256;
         const char* e = getenv("ACM_LIN_BLOCK");
         if (e && (atoi(e) == 128 || atoi(e) == 256)) bs = atoi(e);
     }
-    if (bs == 128) return launch_linearize_bs<M, KIND, 128>(ctx, hp, d_lm, xyz, uv, invalid_penalty);
-    return launch_linearize_bs<M, KIND, 256>(ctx, hp, d_lm, xyz, uv, invalid_penalty);
+    if (bs == 128) return launch_linearize_bs<M, KIND, 128>(ctx, hp, d_lm, fuse_step, xyz, uv, invalid_penalty);
+    return launch_linearize_bs<M, KIND, 256>(ctx, hp, d_lm, fuse_step, xyz, uv, invalid_penalty);
 }
 
 #define ACM_DISPATCH_LIN(model, kind, ...)                                                                       \
@@ -165,12 +332,12 @@ static void make_lin_params(const acm_camera* cam, LinParams* p) {
     lin_derive(cam->model, *p);
 }
 
-static int32_t enqueue_linearize(acm_ctx* ctx, const acm_camera* cam, int32_t kind, const LmState* d_lm, const acm_points* xyz,
+static int32_t enqueue_linearize(acm_ctx* ctx, const acm_camera* cam, int32_t kind, LmState* d_lm, int fuse_step, const acm_points* xyz,
                                  const acm_points* uv, double invalid_penalty, int* nacc) {
     LinParams hp;
     make_lin_params(cam, &hp);
     ACM_DISPATCH_LIN(cam->model, kind, {
-        int32_t rc = launch_linearize<M, KIND>(ctx, hp, d_lm, xyz, uv, invalid_penalty);
+        int32_t rc = launch_linearize<M, KIND>(ctx, hp, d_lm, fuse_step, xyz, uv, invalid_penalty);
         if (rc) return rc;
         *nacc = LinOps<M, KIND>::NACC;
     });
@@ -191,7 +358,7 @@ extern "C" int32_t acm_linearize_async(acm_ctx* ctx, const acm_camera* cam, int3
     int32_t rc = check_lin_args(ctx, cam, xyz, uv);
     if (rc) return rc;
     int nacc = 0;
-    return enqueue_linearize(ctx, cam, residual_kind, nullptr, xyz, uv, 0.0, &nacc);
+    return enqueue_linearize(ctx, cam, residual_kind, nullptr, 0, xyz, uv, 0.0, &nacc);
 }
 
 extern "C" int32_t acm_linearize(acm_ctx* ctx, const acm_camera* cam, int32_t residual_kind, const acm_points* xyz, const acm_points* uv,
@@ -200,7 +367,7 @@ extern "C" int32_t acm_linearize(acm_ctx* ctx, const acm_camera* cam, int32_t re
     int32_t rc = check_lin_args(ctx, cam, xyz, uv);
     if (rc) return rc;
     int nacc = 0;
-    rc = enqueue_linearize(ctx, cam, residual_kind, nullptr, xyz, uv, 0.0, &nacc);
+    rc = enqueue_linearize(ctx, cam, residual_kind, nullptr, 0, xyz, uv, 0.0, &nacc);
     if (rc) return rc;
     ACM_CUDA(ctx, cudaMemcpyAsync(ctx->h_reduce, ctx->d_reduce, nacc * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     ACM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -221,99 +388,6 @@ extern "C" int32_t acm_linearize_host(acm_ctx* ctx, const acm_camera* cam, int32
     acm_points_destroy(ctx, xyz);
     acm_points_destroy(ctx, uv);
     return rc;
-}
-
-// ---------------------------------------------------------------------------------------
-// LM step (single thread; P <= 9)
-// ---------------------------------------------------------------------------------------
-__device__ inline bool chol_solve_dev(int P, const double* A, const double* b, double* x) {
-    double Lm[ACM_MAX_PARAMS * ACM_MAX_PARAMS];
-    for (int i = 0; i < P; ++i) {
-        for (int j = 0; j <= i; ++j) {
-            double s = A[i * P + j];
-            for (int k = 0; k < j; ++k) s -= Lm[i * P + k] * Lm[j * P + k];
-            if (i == j) { if (!(s > 0.0)) return false; Lm[i * P + i] = sqrt(s); }
-            else Lm[i * P + j] = s / Lm[j * P + j];
-        }
-    }
-    double yv[ACM_MAX_PARAMS];
-    for (int i = 0; i < P; ++i) { double s = b[i]; for (int k = 0; k < i; ++k) s -= Lm[i * P + k] * yv[k]; yv[i] = s / Lm[i * P + i]; }
-    for (int i = P - 1; i >= 0; --i) { double s = yv[i]; for (int k = i + 1; k < P; ++k) s -= Lm[k * P + i] * x[k]; x[i] = s / Lm[i * P + i]; }
-    return true;
-}
-
-__device__ inline double clampd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
-
-template <int M, int KIND>
-__global__ void lm_step_kernel(LmState* __restrict__ s, const double* __restrict__ red) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    if (s->done) return;
-    constexpr int P = LinOps<M, KIND>::P;
-    double Ht[P * P], gt[P], cost_t, cnt;
-    LinOps<M, KIND>::unpack(red, Ht, gt, &cost_t, &cnt);
-    s->passes++;
-    bool accepted = false;
-    if (s->first) {
-        s->first = 0;
-        s->initial_cost = cost_t;
-        accepted = true;
-    } else {
-        const bool small_step = s->dnorm <= s->param_tol * (s->xnorm + s->param_tol);
-        if (s->pred > 0.0 && cost_t < s->cost) {
-            const double rho = (s->cost - cost_t) / s->pred;
-            const double dcost = s->cost - cost_t, cost_old = s->cost;
-            const double q = 2.0 * rho - 1.0, f = 1.0 - q * q * q;
-            s->lambda *= (f > 1.0 / 3.0) ? f : 1.0 / 3.0;
-            s->nu = 2.0;
-            if (s->lambda < 1e-15) s->lambda = 1e-15;
-            accepted = true;
-            double gmax = 0.0;
-            for (int i = 0; i < P; ++i) gmax = fmax(gmax, fabs(gt[i]));
-            if (dcost <= s->cost_tol * cost_old) { s->status = 0; s->done = 1; }
-            else if (small_step) { s->status = 1; s->done = 1; }
-            else if (gmax <= s->grad_tol) { s->status = 2; s->done = 1; }
-        } else {
-            if (small_step) { s->status = 1; s->done = 1; }
-            else {
-                s->lambda *= s->nu; s->nu *= 2.0;
-                if (s->lambda > 1e30) { s->status = 4; s->done = 1; }
-            }
-        }
-    }
-    if (accepted) {
-        for (int i = 0; i < P; ++i) { s->x[i] = s->xt[i]; s->g[i] = gt[i]; }
-        for (int i = 0; i < P * P; ++i) s->H[i] = Ht[i];
-        s->cost = cost_t; s->n_valid = cnt;
-    }
-    if (s->done) return;
-    // next trial point from (H, g, lambda) at the accepted x
-    double D[P], A[P * P], gs[P], st[P];
-    for (;;) {
-        if (s->iterations >= s->max_iter) { s->status = 3; s->done = 1; return; }
-        s->iterations++;
-        for (int i = 0; i < P; ++i) { double d = sqrt(s->H[i * P + i]); D[i] = (d > 1e-300) ? d : 1.0; }
-        for (int i = 0; i < P; ++i) {
-            for (int j = 0; j < P; ++j) A[i * P + j] = s->H[i * P + j] / (D[i] * D[j]);
-            A[i * P + i] += s->lambda;
-            gs[i] = -s->g[i] / D[i];
-        }
-        if (chol_solve_dev(P, A, gs, st)) break;
-        s->lambda *= s->nu; s->nu *= 2.0;
-        if (s->lambda > 1e30) { s->status = 4; s->done = 1; return; }
-    }
-    double xnorm = 0.0, dnorm = 0.0, dx[P];
-    for (int i = 0; i < P; ++i) {
-        s->xt[i] = clampd(s->x[i] + st[i] / D[i], s->lower[i], s->upper[i]);
-        dx[i] = s->xt[i] - s->x[i];
-        xnorm += s->x[i] * s->x[i]; dnorm += dx[i] * dx[i];
-    }
-    double pred = 0.0;
-    for (int i = 0; i < P; ++i) {
-        double hd = 0.0;
-        for (int j = 0; j < P; ++j) hd += s->H[i * P + j] * dx[j];
-        pred -= dx[i] * (s->g[i] + 0.5 * hd);
-    }
-    s->xnorm = sqrt(xnorm); s->dnorm = sqrt(dnorm); s->pred = pred;
 }
 
 extern "C" int32_t acm_lm_default_config(acm_lm_config* cfg) {
@@ -358,10 +432,13 @@ extern "C" int32_t acm_lm_solve(acm_ctx* ctx, const acm_camera* init, int32_t re
 
     int nacc = 0;
     auto one_iteration = [&]() -> int32_t {
-        int32_t r = enqueue_linearize(ctx, init, residual_kind, d, xyz, uv, cfg.invalid_penalty, &nacc);
+        const int fuse = (ctx->n_ranks == 1 && !getenv("ACM_LM_NO_FUSE")) ? 1 : 0;
+        int32_t r = enqueue_linearize(ctx, init, residual_kind, d, fuse, xyz, uv, cfg.invalid_penalty, &nacc);
         if (r) return r;
-        ACM_DISPATCH_LIN(init->model, residual_kind, (lm_step_kernel<M, KIND><<<1, 32, 0, ctx->stream>>>(d, ctx->d_reduce)));
-        ACM_CHECK_LAUNCH(ctx);
+        if (!fuse) {
+            ACM_DISPATCH_LIN(init->model, residual_kind, (lm_step_kernel<M, KIND><<<1, 64, 0, ctx->stream>>>(d, ctx->d_reduce)));
+            ACM_CHECK_LAUNCH(ctx);
+        }
         return ACM_OK;
     };
     const int max_passes = cfg.max_iterations + 2;

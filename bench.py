@@ -350,16 +350,18 @@ def run_extras(acm, N, lib, ctx, X, UV, n):
     out["linearize_100M"] = lin
     pu = {}
     UV2 = acm.Points(ctx, 2, n); X2 = acm.Points(ctx, 3, n)
-    st = ctx.device_alloc(n)
+    st = ctx.device_alloc(n); st2 = ctx.device_alloc(n)
     for mid in range(7):
         m = acm.MODEL_CLASSES[mid](acm.Intrinsics(*intr), acm.Resolution(512, 512), dist_init[mid], ctx=ctx)
         cam = m.camera_block()
         ms = timeit(lambda: ctx.check(lib.acm_project(ctx.handle, C.byref(cam), X.handle, UV2.handle, C.c_void_p(st))))
         ctx.check(lib.acm_synth_pixels(ctx.handle, 7, 0, 512.0, 512.0, UV2.handle))
         ms2 = timeit(lambda: ctx.check(lib.acm_unproject(ctx.handle, C.byref(cam), UV2.handle, X2.handle, C.c_void_p(st))))
-        pu[names[mid]] = {"project_ms": ms, "project_gb_s": n * 41 / ms / 1e6, "unproject_ms": ms2, "unproject_gb_s": n * 41 / ms2 / 1e6}
+        ms3 = timeit(lambda: ctx.check(lib.acm_project_unproject(ctx.handle, C.byref(cam), X.handle, UV2.handle, X2.handle, C.c_void_p(st), C.c_void_p(st2))))
+        pu[names[mid]] = {"project_ms": ms, "project_gb_s": n * 41 / ms / 1e6, "unproject_ms": ms2, "unproject_gb_s": n * 41 / ms2 / 1e6,
+                          "round_trip_fused_ms": ms3, "round_trip_fused_gb_s": n * 66 / ms3 / 1e6}
     out["project_unproject_100M_f64"] = pu
-    ctx.device_free(st); UV2.free(); X2.free()
+    ctx.device_free(st); ctx.device_free(st2); UV2.free(); X2.free()
     # undistort (BASELINE config 5): 4096x4096 KB fisheye (sample intrinsics x8), 32 frames resident in HBM
     # = the per-GPU share of the 256-frame batch on 8 GPUs
     W = H = 4096

@@ -247,19 +247,20 @@ void orc_lm_default_config(orc_lm_config* c) {
     c->lambda0 = 1e-3; c->invalid_penalty = 0.0;
 }
 
+/* divisions hoisted into reciprocals of the diagonal (same arithmetic as the device step) */
 static int chol_solve(int P, const double* A, const double* b, double* x) {
-    double L[81];
+    double L[81], inv[9];
     for (int i = 0; i < P; ++i) {
         for (int j = 0; j <= i; ++j) {
             double s = A[i * P + j];
             for (int k = 0; k < j; ++k) s -= L[i * P + k] * L[j * P + k];
-            if (i == j) { if (!(s > 0.0)) return 0; L[i * P + i] = sqrt(s); }
-            else L[i * P + j] = s / L[j * P + j];
+            if (i == j) { if (!(s > 0.0)) return 0; L[i * P + i] = sqrt(s); inv[i] = 1.0 / L[i * P + i]; }
+            else L[i * P + j] = s * inv[j];
         }
     }
     double yv[9];
-    for (int i = 0; i < P; ++i) { double s = b[i]; for (int k = 0; k < i; ++k) s -= L[i * P + k] * yv[k]; yv[i] = s / L[i * P + i]; }
-    for (int i = P - 1; i >= 0; --i) { double s = yv[i]; for (int k = i + 1; k < P; ++k) s -= L[k * P + i] * x[k]; x[i] = s / L[i * P + i]; }
+    for (int i = 0; i < P; ++i) { double s = b[i]; for (int k = 0; k < i; ++k) s -= L[i * P + k] * yv[k]; yv[i] = s * inv[i]; }
+    for (int i = P - 1; i >= 0; --i) { double s = yv[i]; for (int k = i + 1; k < P; ++k) s -= L[k * P + i] * x[k]; x[i] = s * inv[i]; }
     return 1;
 }
 
@@ -280,16 +281,16 @@ int orc_lm_solve(const orc_model* m_init, int kind, const double* xyz, const dou
     double lambda = cfg->lambda0, nu = 2.0;
     while (res->iterations < cfg->max_iterations) {
         res->iterations++;
-        for (int i = 0; i < P; ++i) { double d = sqrt(H[i * P + i]); D[i] = (d > 1e-300) ? d : 1.0; }
+        for (int i = 0; i < P; ++i) { double d = sqrt(H[i * P + i]); D[i] = (d > 1e-300) ? 1.0 / d : 1.0; } /* D holds 1/sqrt(H_ii) */
         for (int i = 0; i < P; ++i) {
-            for (int j = 0; j < P; ++j) A[i * P + j] = H[i * P + j] / (D[i] * D[j]);
+            for (int j = 0; j < P; ++j) A[i * P + j] = H[i * P + j] * D[i] * D[j];
             A[i * P + i] += lambda;
-            gs[i] = -g[i] / D[i];
+            gs[i] = -g[i] * D[i];
         }
         if (!chol_solve(P, A, gs, s)) { lambda *= nu; nu *= 2.0; if (lambda > 1e30) { res->status = 4; break; } continue; }
         double xnorm = 0.0, dnorm = 0.0;
         for (int i = 0; i < P; ++i) {
-            xt[i] = clampd(x[i] + s[i] / D[i], lower ? lower[i] : -INFINITY, upper ? upper[i] : INFINITY);
+            xt[i] = clampd(x[i] + s[i] * D[i], lower ? lower[i] : -INFINITY, upper ? upper[i] : INFINITY);
             dx[i] = xt[i] - x[i];
             xnorm += x[i] * x[i]; dnorm += dx[i] * dx[i];
         }

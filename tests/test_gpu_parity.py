@@ -78,6 +78,32 @@ def test_unproject_matches_oracle(acm, ctx, O, cameras, name):
     assert_close_where_valid(ray, rayo, sto == 0, name)
 
 
+@pytest.mark.parametrize("name", MODELS)
+def test_fused_round_trip_matches_oracle(acm, ctx, O, cameras, name):
+    """BASELINE config 2: project -> unproject in one kernel == oracle project, then oracle unproject."""
+    cam = cameras[name]
+    m, om = gpu_model(acm, ctx, cam), oracle_model(O, cam)
+    n = 65_537
+    xyz = O.synth_points3(0xACE50002, 3, n, cone(name), True)
+    uv, ray, sp, su = m.round_trip_batch(xyz)
+    uvo, spo = O.project(om, xyz)
+    assert np.array_equal(sp, spo)
+    assert_close_where_valid(uv, uvo, spo == 0, name)
+    ok = spo == 0
+    rayo, suo = O.unproject(om, uv[ok])  # unproject what the device projected (KB / FOV differ in the last ulps)
+    assert np.array_equal(su[ok], suo) and np.array_equal(su[~ok], spo[~ok])
+    good = np.zeros(n, bool); good[np.flatnonzero(ok)[suo == 0]] = True
+    assert_close_where_valid(ray[ok], rayo, suo == 0, name)
+    assert np.all(np.isnan(ray[~good]))
+    # the direction comes back (the sample UCM / EUCM cameras have alpha > 1, for which the reference's
+    # unproject is not the exact inverse: ucm.rs:614-616 uses 1e-4 at one point, tests/ use dot > 0.99)
+    d = xyz[good] / np.linalg.norm(xyz[good], axis=1, keepdims=True)
+    if name in ("ucm", "eucm"):
+        assert np.min(np.sum(ray[good] * d, axis=1)) > 0.99
+    else:
+        assert np.max(np.abs(ray[good] - d)) < 1e-5
+
+
 @pytest.mark.parametrize("n", [0, 1, 2, 3, 5, 255, 256, 257, 511, 513])
 def test_edge_sizes(acm, ctx, O, cameras, n):
     for name in ("double_sphere", "kannala_brandt"):
