@@ -15,6 +15,7 @@
 //   GF[2] GC[2] GD[ND]   COST   COUNT
 #pragma once
 #include "acm_internal.cuh"
+#include "acm_math.cuh"
 
 #define LIN_EPS 2.220446049250313e-16
 #define LIN_SQRT_EPS 1.4901161193847656e-08
@@ -28,14 +29,7 @@
 // 0, inf and NaN propagate to NaN/inf and are rejected by the validity compares downstream.
 // (Only used where the tolerance is 1e-9 relative -- never in the bit-exact project kernels.)
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ double fast_rcp(double a) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
-    double e = fma(-a, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-a, r, 1.0);
-    return fma(r, e, r);
-}
+__device__ __forceinline__ double fast_rcp(double a) { return acm_rcp(a); }
 __device__ __forceinline__ double fast_rsqrt(double a) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
@@ -58,33 +52,7 @@ __device__ __forceinline__ double fast_sqrt(double a, double& inv) {
     return fma(r, 0.5 * y, s);
 }
 
-// atan2(a, b) for a >= 0, b > 0 (first quadrant: all the fisheye models need).  Two argument
-// reductions that share ONE reciprocal -- swap so that t = num/den <= 1, then
-// atan(t) = pi/4 + atan((num-den)/(num+den)) above tan(pi/8) -- leave |t| <= sqrt(2)-1, where a
-// degree-10 polynomial in t^2 (Chebyshev-node fit computed with mpmath, approximation error
-// 6.9e-17 relative) is evaluated by Horner.  ~25 FP64 instructions, no branch, no slow path.
-__device__ __forceinline__ double fast_atan2_q1(double a, double b) {
-    const bool swap = a > b;
-    const double num = swap ? b : a, den = swap ? a : b;
-    const bool hi = num > 0.41421356237309503 * den;
-    const double n2 = hi ? num - den : num;
-    const double d2 = hi ? num + den : den;
-    const double t = n2 * fast_rcp(d2);
-    const double s = t * t;
-    double q = 2.11353731576932463e-02;
-    q = fma(q, s, -4.34805221571646222e-02);
-    q = fma(q, s, 5.68834922680901064e-02);
-    q = fma(q, s, -6.64023393042940807e-02);
-    q = fma(q, s, 7.68995349630685748e-02);
-    q = fma(q, s, -9.09077307480841423e-02);
-    q = fma(q, s, 1.11111061804559458e-01);
-    q = fma(q, s, -1.42857141809764665e-01);
-    q = fma(q, s, 1.99999999988551114e-01);
-    q = fma(q, s, -3.33333333333284410e-01);
-    double at = fma(t * s, q, t);
-    at = hi ? 0.78539816339744828 + at : at;
-    return swap ? 1.5707963267948966 - at : at;
-}
+__device__ __forceinline__ double fast_atan2_q1(double a, double b) { return acm_atan2_q1<false>(a, b); }
 
 template <int ND> struct AccLayout {
     static constexpr int HFF = 0, HFC = 2, HCC = 4, HFD = 6, HCD = 6 + 2 * ND, HDD = 6 + 4 * ND;

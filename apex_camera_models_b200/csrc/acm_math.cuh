@@ -1,0 +1,49 @@
+// Branch-free f64 helpers shared by every translation unit.  Written with explicit __fma_rn /
+// __dmul_rn / __dadd_rn intrinsics so that they compile to the same instructions with and without
+// -fmad=false.
+#pragma once
+#include <cuda_runtime.h>
+
+// 1/a for normal finite a: MUFU seed (~2^-23) + two Newton steps => <= 1 ulp.
+__device__ __forceinline__ double acm_rcp(double a) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    double e = __fma_rn(-a, r, 1.0);
+    r = __fma_rn(r, e, r);
+    e = __fma_rn(-a, r, 1.0);
+    return __fma_rn(r, e, r);
+}
+
+// atan2(a, b) for a >= 0, b > 0 (first quadrant: all that the fisheye models need).  Two argument
+// reductions share ONE reciprocal -- swap so that t = num/den <= 1, then
+// atan(t) = pi/4 + atan((num-den)/(num+den)) above tan(pi/8) -- leaving |t| <= sqrt(2)-1, where a
+// degree-10 polynomial in t^2 (Chebyshev-node fit computed with mpmath at 60 digits, approximation
+// error 6.9e-17 relative) is evaluated by Horner.  Total error <= ~1.5 ulp, like the CUDA library's
+// atan2 (2 ulp), in ~25 FP64 instructions with no branch and no slow-path call.
+// Operands whose magnitude would push the MUFU seed into its flush-to-zero range take the library
+// function (a branch that is practically never taken; GUARD = false drops it for the solver kernels,
+// whose streaming loop must stay one basic block and whose inputs are sane by construction).
+template <bool GUARD = true>
+__device__ __forceinline__ double acm_atan2_q1(double a, double b) {
+    const bool swap = a > b;
+    const double num = swap ? b : a, den = swap ? a : b;
+    if (GUARD && !(den > 1e-280 && den < 1e280)) return atan2(a, b);
+    const bool hi = num > __dmul_rn(0.41421356237309503, den);
+    const double n2 = hi ? __dsub_rn(num, den) : num;
+    const double d2 = hi ? __dadd_rn(num, den) : den;
+    const double t = __dmul_rn(n2, acm_rcp(d2));
+    const double s = __dmul_rn(t, t);
+    double q = 2.11353731576932463e-02;
+    q = __fma_rn(q, s, -4.34805221571646222e-02);
+    q = __fma_rn(q, s, 5.68834922680901064e-02);
+    q = __fma_rn(q, s, -6.64023393042940807e-02);
+    q = __fma_rn(q, s, 7.68995349630685748e-02);
+    q = __fma_rn(q, s, -9.09077307480841423e-02);
+    q = __fma_rn(q, s, 1.11111061804559458e-01);
+    q = __fma_rn(q, s, -1.42857141809764665e-01);
+    q = __fma_rn(q, s, 1.99999999988551114e-01);
+    q = __fma_rn(q, s, -3.33333333333284410e-01);
+    double at = __fma_rn(__dmul_rn(t, s), q, t);
+    at = hi ? __dadd_rn(0.78539816339744828, at) : at;
+    return swap ? __dsub_rn(1.5707963267948966, at) : at;
+}

@@ -5,6 +5,7 @@
 // be bit-exact.  Per-model line references are to /root/reference/src/camera/<model>.rs.
 #pragma once
 #include "acm_internal.cuh"
+#include "acm_math.cuh"
 
 #define ACM_EPS 2.220446049250313e-16        // f64::EPSILON
 #define ACM_SQRT_EPS 1.4901161193847656e-08  // f64::EPSILON.sqrt() == 2^-26
@@ -106,7 +107,7 @@ template <> struct CamModel<ACM_MODEL_KANNALA_BRANDT> {
         if (z < 0.0) return ACM_POINT_IS_OUTSIDE_IMAGE;
         else if (z < ACM_EPS) return ACM_POINT_AT_CAMERA_CENTER;
         double r = sqrt(x * x + y * y);
-        double th = atan2(r, z);
+        double th = acm_atan2_q1(r, z);  // r >= 0, z >= EPS: first quadrant (<= 1.5 ulp, see acm_math.cuh)
         double t2 = th * th;
         double t3 = t2 * th;
         double t5 = t3 * t2;
@@ -261,7 +262,7 @@ template <> struct CamModel<ACM_MODEL_FOV> {
         double t = c.k0;
         double rd;
         if (r2 < ACM_SQRT_EPS) rd = 2.0 * t / w;
-        else rd = atan2(2.0 * t * r, z) / (r * w);
+        else rd = acm_atan2_q1(2.0 * t * r, z) / (r * w);  // 2*t*r >= 0, z >= sqrt(EPS)
         double mx = x * rd, my = y * rd;
         u = c.fx * mx + c.cx;
         v = c.fy * my + c.cy;

@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(256) linest_kb_kernel(double fx, double fy, do
         double xw = X[i], yw = Y[i], zw = Z[i], u = U[i], v = V[i];
         if (zw <= ACM_EPS) continue;
         double rw = sqrt(xw * xw + yw * yw);
-        double th = atan2(rw, zw);
+        double th = acm_atan2_q1(rw, zw);
         double t2 = th * th, t3 = t2 * th, t5 = t3 * t2, t7 = t5 * t2, t9 = t7 * t2;
         double x_r = (rw < ACM_EPS) ? 0.0 : xw / rw, y_r = (rw < ACM_EPS) ? 0.0 : yw / rw;
         if ((fabs(fx * x_r) < ACM_EPS && fabs(x_r) > ACM_EPS) || (fabs(fy * y_r) < ACM_EPS && fabs(y_r) > ACM_EPS)) acc[0] += 1.0;
@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(256) linest_fov_kernel(double fx, double fy, d
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         double x = X[i], y = Y[i], z = Z[i];
         double r2 = x * x + y * y, r = sqrt(r2);
-        double a = atan2(2.0 * t * r, z);
+        double a = (z > 0.0 && r >= 0.0) ? acm_atan2_q1(2.0 * t * r, z) : atan2(2.0 * t * r, z);  // the grid search has no z guard
         double rd = (r2 < ACM_SQRT_EPS) ? 2.0 * t / w : a / (r * w);
         double mx = x * rd, my = y * rd;
         double up = fx * mx + cx, vp = fy * my + cy;
