@@ -19,6 +19,6 @@ from .optimization import (DoubleSphereOptimizationCost, EucmOptimizationCost, F
                            UcmOptimizationCost, CONVERTER_BOUNDS, CANONICAL_RESIDUAL)
 from .util import (InterpolationMethod, ProjectionError, compute_reprojection_error, sample_points, undistort_image,
                    undistort_images, undistort_map)
-from .distributed import attach_communicator, shard_range
+from .distributed import attach_communicator, attach_peers, shard_range
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -106,6 +106,9 @@ SIGNATURES = {
     "acm_comm_init_rank": (C.c_int32, [_vp, C.c_int32, C.c_int32, _u8p]),
     "acm_comm_destroy": (C.c_int32, [_vp]),
     "acm_comm_size": (C.c_int32, [_vp]),
+    "acm_peer_export": (C.c_int32, [_vp, _u8p]),
+    "acm_peer_attach": (C.c_int32, [_vp, C.c_int32, C.c_int32, _u8p]),
+    "acm_peer_detach": (C.c_int32, [_vp]),
 }
 
 

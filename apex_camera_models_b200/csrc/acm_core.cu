@@ -51,6 +51,8 @@ extern "C" int32_t acm_ctx_create(int32_t device, void* cuda_stream, acm_ctx** o
     ctx->d_partials = nullptr; ctx->partials_cap = 0; ctx->d_reduce = nullptr; ctx->d_ticket = nullptr; ctx->h_reduce = nullptr;
     ctx->d_lm = nullptr; ctx->h_lm = nullptr; ctx->d_stage[0] = ctx->d_stage[1] = nullptr; ctx->stage_cap = 0;
     ctx->h_stage = nullptr; ctx->h_stage_cap = 0;
+    ctx->peer_local = nullptr; ctx->d_peer_ptrs = nullptr; ctx->peer_n = 0; ctx->peer_rank = 0; ctx->peer_seq = 0;
+    for (int i = 0; i < ACM_MAX_PEERS; ++i) ctx->peer_mapped[i] = nullptr;
 #define CREATE_CUDA(call)                                                                                     \
     do { cudaError_t _e = (call); if (_e != cudaSuccess) { int32_t rc = acm_fail(nullptr, ACM_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(_e)); delete ctx; return rc; } } while (0)
     CREATE_CUDA(cudaSetDevice(device));
@@ -82,6 +84,8 @@ extern "C" int32_t acm_ctx_destroy(acm_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     acm_comm_destroy(ctx);
+    acm_peer_detach(ctx);
+    cudaFree(ctx->peer_local);
     cudaFree(ctx->d_partials); cudaFree(ctx->d_reduce); cudaFree(ctx->d_ticket); cudaFreeHost(ctx->h_reduce);
     cudaFree(ctx->d_lm); cudaFreeHost(ctx->h_lm);
     cudaFree(ctx->d_stage[0]); cudaFree(ctx->d_stage[1]); cudaFreeHost(ctx->h_stage);
@@ -599,8 +603,65 @@ extern "C" int32_t acm_comm_size(const acm_ctx* ctx) { return ctx ? ctx->n_ranks
 
 // Sum a small f64 vector over all ranks on the compute stream (no-op without a communicator).
 int32_t acm_allreduce_sum_f64(acm_ctx* ctx, double* d_buf, size_t count) {
-    if (!ctx->comm || ctx->n_ranks == 1) return ACM_OK;
+    if (ctx->n_ranks == 1) return ACM_OK;
+    if (!ctx->comm) return acm_fail(ctx, ACM_ERR_NCCL, "this operation needs an NCCL communicator (acm_comm_init_rank) when ranks > 1");
     int r = g_nccl.AllReduce(d_buf, d_buf, count, /*ncclFloat64*/ 8, /*ncclSum*/ 0, ctx->comm, ctx->stream);
     if (r != 0) return acm_fail(ctx, ACM_ERR_NCCL, "ncclAllReduce: %s", nccl_err(r));
+    return ACM_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// NVLink peer exchange buffers (CUDA IPC; one process per GPU)
+// ---------------------------------------------------------------------------------------
+extern "C" int32_t acm_peer_export(acm_ctx* ctx, uint8_t handle[64]) {
+    if (!ctx || !handle) return ACM_ERR_INVALID_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle is 64 bytes");
+    ACM_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->peer_local) {
+        ACM_CUDA(ctx, cudaMalloc(&ctx->peer_local, ACM_PEER_BUFFER_DOUBLES * sizeof(double)));
+        ACM_CUDA(ctx, cudaMemset(ctx->peer_local, 0, ACM_PEER_BUFFER_DOUBLES * sizeof(double)));
+        ACM_CUDA(ctx, cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t h;
+    ACM_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->peer_local));
+    memcpy(handle, &h, 64);
+    return ACM_OK;
+}
+
+extern "C" int32_t acm_peer_attach(acm_ctx* ctx, int32_t n_ranks, int32_t rank, const uint8_t* handles) {
+    if (!ctx || !handles) return ACM_ERR_INVALID_ARG;
+    ACM_REQUIRE(ctx, n_ranks >= 1 && n_ranks <= ACM_MAX_PEERS && rank >= 0 && rank < n_ranks, "peer_attach: bad rank / size (at most 8 ranks)");
+    ACM_REQUIRE(ctx, ctx->peer_local != nullptr, "peer_attach: call acm_peer_export first");
+    ACM_REQUIRE(ctx, ctx->peer_n == 0, "peer_attach: peers already attached");
+    ACM_CUDA(ctx, cudaSetDevice(ctx->device));
+    double* ptrs[ACM_MAX_PEERS];
+    for (int r = 0; r < n_ranks; ++r) {
+        if (r == rank) { ptrs[r] = ctx->peer_local; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)r * 64, 64);
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            for (int q = 0; q < r; ++q) if (ctx->peer_mapped[q]) { cudaIpcCloseMemHandle(ctx->peer_mapped[q]); ctx->peer_mapped[q] = nullptr; }
+            return acm_fail(ctx, ACM_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
+        }
+        ctx->peer_mapped[r] = p;
+        ptrs[r] = static_cast<double*>(p);
+    }
+    ACM_CUDA(ctx, cudaMalloc(&ctx->d_peer_ptrs, ACM_MAX_PEERS * sizeof(double*)));
+    ACM_CUDA(ctx, cudaMemcpy(ctx->d_peer_ptrs, ptrs, n_ranks * sizeof(double*), cudaMemcpyHostToDevice));
+    ctx->peer_n = n_ranks; ctx->peer_rank = rank; ctx->peer_seq = 0;
+    if (ctx->n_ranks == 1) { ctx->n_ranks = n_ranks; ctx->rank = rank; }
+    return ACM_OK;
+}
+
+extern "C" int32_t acm_peer_detach(acm_ctx* ctx) {
+    if (!ctx) return ACM_ERR_INVALID_ARG;
+    if (ctx->peer_n == 0) return ACM_OK;
+    cudaStreamSynchronize(ctx->stream);
+    for (int r = 0; r < ACM_MAX_PEERS; ++r) if (ctx->peer_mapped[r]) { cudaIpcCloseMemHandle(ctx->peer_mapped[r]); ctx->peer_mapped[r] = nullptr; }
+    cudaFree(ctx->d_peer_ptrs); ctx->d_peer_ptrs = nullptr;
+    ctx->peer_n = 0;
+    if (!ctx->comm) { ctx->n_ranks = 1; ctx->rank = 0; }
     return ACM_OK;
 }

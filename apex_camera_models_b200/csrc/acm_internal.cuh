@@ -32,6 +32,8 @@ struct acm_points {
     void* base;
 };
 
+#define ACM_MAX_PEERS 8
+
 struct NcclApi;  // dlopen'ed NCCL entry points (acm_core.cu)
 
 struct acm_ctx {
@@ -61,6 +63,22 @@ struct acm_ctx {
     // NCCL
     void* comm;
     int n_ranks, rank;
+    // NVLink peer exchange (acm_peer_*)
+    double* peer_local;          // this rank's exchange buffer (exported through CUDA IPC)
+    void* peer_mapped[ACM_MAX_PEERS];  // peers' buffers opened in this process (nullptr for self)
+    double** d_peer_ptrs;        // device array [n_peers] of every rank's buffer, indexed by rank
+    int peer_n, peer_rank;
+    unsigned long long peer_seq; // exchange counter, advances identically on every rank
+};
+
+// exchange buffer: 2 alternating sets x ACM_MAX_PEERS rank slots x (64 values + flag + padding)
+#define ACM_PEER_SLOT_DOUBLES 72
+#define ACM_PEER_BUFFER_DOUBLES (2 * ACM_MAX_PEERS * ACM_PEER_SLOT_DOUBLES)
+
+struct PeerArgs {
+    double* const* bufs;         // nullptr: exchange disabled
+    int n_ranks, rank;
+    unsigned long long seq;
 };
 
 int32_t acm_fail(acm_ctx* ctx, int32_t code, const char* fmt, ...);

@@ -81,88 +81,53 @@ __device__ __noinline__ bool chol_solve_work(int P, LmWork* w) {
 
 __device__ inline double clampd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
-__device__ __noinline__ void lm_step_core(int P, LmState* s, LmWork* w, double cost_t, double cnt) {
+// Decision part of the step (thread 0): accept / reject the trial point, update the damping,
+// test convergence.  Returns true when the trial point was accepted.
+__device__ __noinline__ bool lm_decide(int P, LmState* s, const LmWork* w, double cost_t) {
     s->passes++;
-    bool accepted = false;
+    if (!(cost_t == cost_t)) { s->status = 4; s->done = 1; return false; }  // NaN sums (poisoned exchange or NaN observations): stop
     if (s->first) {
         s->first = 0;
         s->initial_cost = cost_t;
-        accepted = true;
-    } else {
-        const bool small_step = s->dnorm <= s->param_tol * (s->xnorm + s->param_tol);
-        if (s->pred > 0.0 && cost_t < s->cost) {
-            const double rho = (s->cost - cost_t) / s->pred;
-            const double dcost = s->cost - cost_t, cost_old = s->cost;
-            const double q = 2.0 * rho - 1.0, f = 1.0 - q * q * q;
-            s->lambda *= (f > 1.0 / 3.0) ? f : 1.0 / 3.0;
-            s->nu = 2.0;
-            if (s->lambda < 1e-15) s->lambda = 1e-15;
-            accepted = true;
-            double gmax = 0.0;
-#pragma unroll 1
-            for (int i = 0; i < P; ++i) gmax = fmax(gmax, fabs(w->gt[i]));
-            if (dcost <= s->cost_tol * cost_old) { s->status = 0; s->done = 1; }
-            else if (small_step) { s->status = 1; s->done = 1; }
-            else if (gmax <= s->grad_tol) { s->status = 2; s->done = 1; }
-        } else {
-            if (small_step) { s->status = 1; s->done = 1; }
-            else {
-                s->lambda *= s->nu; s->nu *= 2.0;
-                if (s->lambda > 1e30) { s->status = 4; s->done = 1; }
-            }
-        }
+        return true;
     }
-    if (accepted) {
+    const bool small_step = s->dnorm <= s->param_tol * (s->xnorm + s->param_tol);
+    if (s->pred > 0.0 && cost_t < s->cost) {
+        const double rho = (s->cost - cost_t) / s->pred;
+        const double dcost = s->cost - cost_t, cost_old = s->cost;
+        const double q = 2.0 * rho - 1.0, f = 1.0 - q * q * q;
+        s->lambda *= (f > 1.0 / 3.0) ? f : 1.0 / 3.0;
+        s->nu = 2.0;
+        if (s->lambda < 1e-15) s->lambda = 1e-15;
+        double gmax = 0.0;
 #pragma unroll 1
-        for (int i = 0; i < P; ++i) { s->x[i] = s->xt[i]; s->g[i] = w->gt[i]; }
-#pragma unroll 1
-        for (int i = 0; i < P * P; ++i) s->H[i] = w->Ht[i];
-        s->cost = cost_t; s->n_valid = cnt;
+        for (int i = 0; i < P; ++i) gmax = fmax(gmax, fabs(w->gt[i]));
+        if (dcost <= s->cost_tol * cost_old) { s->status = 0; s->done = 1; }
+        else if (small_step) { s->status = 1; s->done = 1; }
+        else if (gmax <= s->grad_tol) { s->status = 2; s->done = 1; }
+        return true;
     }
-    if (s->done) return;
-    // next trial point from (H, g, lambda) at the accepted x
-    for (;;) {
-        if (s->iterations >= s->max_iter) { s->status = 3; s->done = 1; return; }
-        s->iterations++;
-#pragma unroll 1
-        for (int i = 0; i < P; ++i) { const double d = sqrt(s->H[i * P + i]); w->invD[i] = (d > 1e-300) ? 1.0 / d : 1.0; }
-#pragma unroll 1
-        for (int i = 0; i < P; ++i) {
-#pragma unroll 1
-            for (int j = 0; j < P; ++j) w->A[i * P + j] = s->H[i * P + j] * w->invD[i] * w->invD[j];
-            w->A[i * P + i] += s->lambda;
-            w->gs[i] = -s->g[i] * w->invD[i];
-        }
-        if (chol_solve_work(P, w)) break;
+    if (small_step) { s->status = 1; s->done = 1; }
+    else {
         s->lambda *= s->nu; s->nu *= 2.0;
-        if (s->lambda > 1e30) { s->status = 4; s->done = 1; return; }
+        if (s->lambda > 1e30) { s->status = 4; s->done = 1; }
     }
-    double xnorm = 0.0, dnorm = 0.0;
-#pragma unroll 1
-    for (int i = 0; i < P; ++i) {
-        s->xt[i] = clampd(s->x[i] + w->st[i] * w->invD[i], s->lower[i], s->upper[i]);
-        w->dx[i] = s->xt[i] - s->x[i];
-        xnorm += s->x[i] * s->x[i]; dnorm += w->dx[i] * w->dx[i];
-    }
-    double pred = 0.0;
-#pragma unroll 1
-    for (int i = 0; i < P; ++i) {
-        double hd = 0.0;
-#pragma unroll 1
-        for (int j = 0; j < P; ++j) hd += s->H[i * P + j] * w->dx[j];
-        pred -= w->dx[i] * (s->g[i] + 0.5 * hd);
-    }
-    s->xnorm = sqrt(xnorm); s->dnorm = sqrt(dnorm); s->pred = pred;
+    return false;
 }
 
-// Cooperative wrapper: `nthreads` threads copy the 1.1 KB state and the reduced accumulators into
-// shared memory, thread 0 runs the step, the threads copy the state back.  Returns immediately
-// (all threads) if the solve has already finished.
+// Cooperative step: `nthreads` (>= 81) threads copy the 1.1 KB state and the reduced accumulators
+// into shared memory; thread 0 decides and factors, the element-wise parts (copies, scaled matrix,
+// trial point, quadratic-model rows) are spread over the threads; the state is copied back.
+// The arithmetic of every scalar is the same as in the serial reference (oracle/acm_oracle_solver.c),
+// including the order of the few sums, so both walk the same trajectory.
 template <int M, int KIND>
 __device__ __forceinline__ void lm_step_block(LmState* __restrict__ s, const double* __restrict__ red, LmState* sh, LmWork* w,
                                               int tid, int nthreads) {
     static_assert(sizeof(LmState) % sizeof(double) == 0, "LmState is copied as doubles");
     constexpr int NW = sizeof(LmState) / sizeof(double);
+    constexpr int P = LinOps<M, KIND>::P;
+    __shared__ int flag_accept, flag_ok;
+    __shared__ double s_cost_t, s_cnt;
     double* shw = reinterpret_cast<double*>(sh);
     const double* gw = reinterpret_cast<const double*>(s);
     for (int i = tid; i < NW; i += nthreads) shw[i] = __ldcg(gw + i);
@@ -172,7 +137,65 @@ __device__ __forceinline__ void lm_step_block(LmState* __restrict__ s, const dou
     if (tid == 0) {
         double cost_t, cnt;
         LinOps<M, KIND>::unpack(w->red, w->Ht, w->gt, &cost_t, &cnt);
-        lm_step_core(LinOps<M, KIND>::P, sh, w, cost_t, cnt);
+        s_cost_t = cost_t; s_cnt = cnt;
+        flag_accept = lm_decide(P, sh, w, cost_t) ? 1 : 0;
+    }
+    __syncthreads();
+    if (flag_accept) {
+        if (tid < P) { sh->x[tid] = sh->xt[tid]; sh->g[tid] = w->gt[tid]; }
+        if (tid < P * P) sh->H[tid] = w->Ht[tid];
+        if (tid == 0) { sh->cost = s_cost_t; sh->n_valid = s_cnt; }
+    }
+    __syncthreads();
+    if (!sh->done) {
+        // next trial point from (H, g, lambda) at the accepted x
+        for (;;) {
+            if (tid == 0) {
+                flag_ok = 1;
+                if (sh->iterations >= sh->max_iter) { sh->status = 3; sh->done = 1; flag_ok = -1; }
+                else sh->iterations++;
+            }
+            if (tid < P) { const double d = sqrt(sh->H[tid * P + tid]); w->invD[tid] = (d > 1e-300) ? 1.0 / d : 1.0; }
+            __syncthreads();
+            if (flag_ok < 0) break;
+            if (tid < P * P) {
+                const int i = tid / P, j = tid - i * P;
+                double a = sh->H[tid] * w->invD[i] * w->invD[j];
+                if (i == j) a += sh->lambda;
+                w->A[tid] = a;
+            }
+            if (tid < P) w->gs[tid] = -sh->g[tid] * w->invD[tid];
+            __syncthreads();
+            if (tid == 0) {
+                if (!chol_solve_work(P, w)) {
+                    sh->lambda *= sh->nu; sh->nu *= 2.0;
+                    flag_ok = 0;
+                    if (sh->lambda > 1e30) { sh->status = 4; sh->done = 1; flag_ok = -1; }
+                }
+            }
+            __syncthreads();
+            if (flag_ok != 0) break;
+        }
+        if (flag_ok > 0) {
+            if (tid < P) {
+                sh->xt[tid] = clampd(sh->x[tid] + w->st[tid] * w->invD[tid], sh->lower[tid], sh->upper[tid]);
+                w->dx[tid] = sh->xt[tid] - sh->x[tid];
+            }
+            __syncthreads();
+            if (tid < P) {
+                double hd = 0.0;
+#pragma unroll 1
+                for (int j = 0; j < P; ++j) hd += sh->H[tid * P + j] * w->dx[j];
+                w->yv[tid] = w->dx[tid] * (sh->g[tid] + 0.5 * hd);   // row of the quadratic model
+            }
+            __syncthreads();
+            if (tid == 0) {
+                double xnorm = 0.0, dnorm = 0.0, pred = 0.0;
+#pragma unroll 1
+                for (int i = 0; i < P; ++i) { xnorm += sh->x[i] * sh->x[i]; dnorm += w->dx[i] * w->dx[i]; pred -= w->yv[i]; }
+                sh->xnorm = sqrt(xnorm); sh->dnorm = sqrt(dnorm); sh->pred = pred;
+            }
+        }
     }
     __syncthreads();
     double* gout = reinterpret_cast<double*>(s);
@@ -181,17 +204,75 @@ __device__ __forceinline__ void lm_step_block(LmState* __restrict__ s, const dou
 
 // Stand-alone step kernel: used when an all-reduce sits between the pass and the step (N > 1).
 template <int M, int KIND>
-__global__ void __launch_bounds__(64) lm_step_kernel(LmState* __restrict__ s, const double* __restrict__ red) {
+__global__ void __launch_bounds__(128) lm_step_kernel(LmState* __restrict__ s, const double* __restrict__ red) {
     __shared__ LmState sh;
     __shared__ LmWork work;
     lm_step_block<M, KIND>(s, red, &sh, &work, threadIdx.x, blockDim.x);
 }
 
 // ---------------------------------------------------------------------------------------
+// All-reduce over NVLink peer memory, fused into the tail of the streaming kernel.
+// Executed by the last block of every rank's kernel (the ranks run on different GPUs, so they are
+// all resident).  Rank r stores its NACC sums into slot [set][r] of EVERY rank's exchange buffer
+// (plain stores to peer-mapped addresses travel over NVLink), publishes them with a release store
+// of the exchange counter, waits (acquire loads of its own buffer) until all slots carry that
+// counter and adds the slots in rank order: the totals are bit-identical on every rank, which
+// keeps the ranks' LM decisions -- and therefore their kernel sequences -- in lock step.
+// Two slot sets alternate so that a rank that runs ahead by one exchange cannot overwrite data a
+// slower rank still has to read.  The spin is bounded: on time-out the sums are poisoned with NaN
+// (the solve then stops with status 4) instead of hanging the GPU.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <int NACC>
+__device__ __forceinline__ void peer_exchange(const PeerArgs& peer, double* __restrict__ out) {
+    const int t = threadIdx.x;
+    const size_t set_off = (size_t)(peer.seq & 1ULL) * ACM_MAX_PEERS * ACM_PEER_SLOT_DOUBLES;
+    const size_t my_slot = set_off + (size_t)peer.rank * ACM_PEER_SLOT_DOUBLES;
+    __shared__ int timed_out;
+    if (t == 0) timed_out = 0;
+    // 1. my sums -> my slot in every rank's buffer
+    for (int i = t; i < NACC * peer.n_ranks; i += blockDim.x) {
+        const int r = i / NACC, k = i - r * NACC;
+        peer.bufs[r][my_slot + k] = __ldcg(out + k);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (t < peer.n_ranks) st_release_sys(reinterpret_cast<unsigned long long*>(peer.bufs[t] + my_slot + 64), peer.seq);
+    // 2. wait for every rank's slot in my own buffer
+    if (t < peer.n_ranks) {
+        const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(peer.bufs[peer.rank] + set_off + (size_t)t * ACM_PEER_SLOT_DOUBLES + 64);
+        const long long t0 = clock64();
+        while (ld_acquire_sys(flag) != peer.seq) {
+            if (clock64() - t0 > 4000000000LL) { timed_out = 1; break; }  // ~2 s
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    // 3. add the slots in rank order
+    if (t < NACC) {
+        const double* mine = peer.bufs[peer.rank] + set_off;
+        double tot = 0.0;
+        for (int r = 0; r < peer.n_ranks; ++r) tot += __ldcv(mine + (size_t)r * ACM_PEER_SLOT_DOUBLES + t);
+        out[t] = timed_out ? __longlong_as_double(0x7ff8000000000000LL) : tot;
+    }
+    __threadfence();
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------
 // linearize kernel
 // ---------------------------------------------------------------------------------------
 template <int M, int KIND, int BS>
-__global__ void __launch_bounds__(BS) linearize_kernel(LinParams hp, LmState* __restrict__ lm, int fuse_step, const double2* __restrict__ X,
+__global__ void __launch_bounds__(BS) linearize_kernel(LinParams hp, LmState* __restrict__ lm, int fuse_step, PeerArgs peer,
+                                                       const double2* __restrict__ X,
                                                         const double2* __restrict__ Y, const double2* __restrict__ Z,
                                                         const double2* __restrict__ U, const double2* __restrict__ V, size_t n,
                                                         double pen2x2, double* __restrict__ partials, double* __restrict__ out,
@@ -243,6 +324,11 @@ __global__ void __launch_bounds__(BS) linearize_kernel(LinParams hp, LmState* __
     if (GridReduce<NACC, 0, 0, BS>::run(acc, partials, out, ticket)) {
         // invalid points carry the residual (pen, pen): cost += pen^2 per invalid point
         if (threadIdx.x == 0 && pen2x2 != 0.0) out[LM_::COST] += pen2x2 * ((double)n - out[LM_::COUNT]);
+        if (peer.bufs) {
+            __threadfence();
+            __syncthreads();
+            peer_exchange<NACC>(peer, out);
+        }
         if (lm && fuse_step) {
             // single GPU: no all-reduce between the pass and the step, so the last block takes the
             // LM step right here (saves a launch and the global round trip of the sums)
@@ -256,8 +342,8 @@ __global__ void __launch_bounds__(BS) linearize_kernel(LinParams hp, LmState* __
 }
 
 template <int M, int KIND, int BS>
-static int32_t launch_linearize_bs(acm_ctx* ctx, const LinParams& hp, LmState* d_lm, int fuse_step, const acm_points* xyz,
-                                   const acm_points* uv, double invalid_penalty) {
+static int32_t launch_linearize_bs(acm_ctx* ctx, const LinParams& hp, LmState* d_lm, int fuse_step, const PeerArgs& peer,
+                                   const acm_points* xyz, const acm_points* uv, double invalid_penalty) {
     static int blocks_per_sm = 0;
     if (!blocks_per_sm) {
         int b = 0;
@@ -269,7 +355,7 @@ static int32_t launch_linearize_bs(acm_ctx* ctx, const LinParams& hp, LmState* d
     int32_t rc = acm_ensure_partials(ctx, (size_t)ctx->sm_count * 32 * 64);
     if (rc) return rc;
     linearize_kernel<M, KIND, BS><<<grid, BS, 0, ctx->stream>>>(
-        hp, d_lm, fuse_step, comp<double2>(xyz, 0), comp<double2>(xyz, 1), comp<double2>(xyz, 2), comp<double2>(uv, 0), comp<double2>(uv, 1), n,
+        hp, d_lm, fuse_step, peer, comp<double2>(xyz, 0), comp<double2>(xyz, 1), comp<double2>(xyz, 2), comp<double2>(uv, 0), comp<double2>(uv, 1), n,
         2.0 * invalid_penalty * invalid_penalty, ctx->d_partials, ctx->d_reduce, ctx->d_ticket);
     ACM_CHECK_LAUNCH(ctx);
     return ACM_OK;
@@ -279,16 +365,16 @@ static int32_t launch_linearize_bs(acm_ctx* ctx, const LinParams& hp, LmState* d
 // kernel past 128 registers/thread; 128-thread blocks then pack one more block per SM.
 // ACM_LIN_BLOCK=128|256 overrides (tuning aid).
 template <int M, int KIND>
-static int32_t launch_linearize(acm_ctx* ctx, const LinParams& hp, LmState* d_lm, int fuse_step, const acm_points* xyz,
-                                const acm_points* uv, double invalid_penalty) {
+static int32_t launch_linearize(acm_ctx* ctx, const LinParams& hp, LmState* d_lm, int fuse_step, const PeerArgs& peer,
+                                const acm_points* xyz, const acm_points* uv, double invalid_penalty) {
     static int bs = 0;
     if (!bs) {
         bs = (M == ACM_MODEL_KANNALA_BRANDT) ? 128 : 256;
         const char* e = getenv("ACM_LIN_BLOCK");
         if (e && (atoi(e) == 128 || atoi(e) == 256)) bs = atoi(e);
     }
-    if (bs == 128) return launch_linearize_bs<M, KIND, 128>(ctx, hp, d_lm, fuse_step, xyz, uv, invalid_penalty);
-    return launch_linearize_bs<M, KIND, 256>(ctx, hp, d_lm, fuse_step, xyz, uv, invalid_penalty);
+    if (bs == 128) return launch_linearize_bs<M, KIND, 128>(ctx, hp, d_lm, fuse_step, peer, xyz, uv, invalid_penalty);
+    return launch_linearize_bs<M, KIND, 256>(ctx, hp, d_lm, fuse_step, peer, xyz, uv, invalid_penalty);
 }
 
 #define ACM_DISPATCH_LIN(model, kind, ...)                                                                       \
@@ -332,16 +418,29 @@ static void make_lin_params(const acm_camera* cam, LinParams* p) {
     lin_derive(cam->model, *p);
 }
 
-static int32_t enqueue_linearize(acm_ctx* ctx, const acm_camera* cam, int32_t kind, LmState* d_lm, int fuse_step, const acm_points* xyz,
-                                 const acm_points* uv, double invalid_penalty, int* nacc) {
+// Enqueue one pass (+ the cross-rank sum).  With peers attached the sum happens inside the kernel
+// (and so can the LM step); otherwise an NCCL all-reduce follows when a communicator is attached.
+// *fused_step tells the caller whether the kernel also takes the LM step.
+static int32_t enqueue_linearize(acm_ctx* ctx, const acm_camera* cam, int32_t kind, LmState* d_lm, const acm_points* xyz,
+                                 const acm_points* uv, double invalid_penalty, int* nacc, int* fused_step) {
     LinParams hp;
     make_lin_params(cam, &hp);
+    PeerArgs peer{nullptr, 1, 0, 0ULL};
+    const bool use_peer = ctx->peer_n > 1 && !getenv("ACM_NO_PEER_EXCHANGE");
+    if (use_peer) {
+        peer.bufs = ctx->d_peer_ptrs; peer.n_ranks = ctx->peer_n; peer.rank = ctx->peer_rank;
+        peer.seq = ++ctx->peer_seq;
+    }
+    const bool need_nccl = !use_peer && ctx->comm && ctx->n_ranks > 1;
+    const int fuse = (d_lm && !need_nccl && !getenv("ACM_LM_NO_FUSE")) ? 1 : 0;
+    if (fused_step) *fused_step = fuse;
     ACM_DISPATCH_LIN(cam->model, kind, {
-        int32_t rc = launch_linearize<M, KIND>(ctx, hp, d_lm, fuse_step, xyz, uv, invalid_penalty);
+        int32_t rc = launch_linearize<M, KIND>(ctx, hp, d_lm, fuse, peer, xyz, uv, invalid_penalty);
         if (rc) return rc;
         *nacc = LinOps<M, KIND>::NACC;
     });
-    return acm_allreduce_sum_f64(ctx, ctx->d_reduce, (size_t)*nacc);
+    if (need_nccl) return acm_allreduce_sum_f64(ctx, ctx->d_reduce, (size_t)*nacc);
+    return ACM_OK;
 }
 
 static int32_t unpack_host(acm_ctx* ctx, const acm_camera* cam, int32_t kind, const double* r, acm_normal_equations* out) {
@@ -358,7 +457,7 @@ extern "C" int32_t acm_linearize_async(acm_ctx* ctx, const acm_camera* cam, int3
     int32_t rc = check_lin_args(ctx, cam, xyz, uv);
     if (rc) return rc;
     int nacc = 0;
-    return enqueue_linearize(ctx, cam, residual_kind, nullptr, 0, xyz, uv, 0.0, &nacc);
+    return enqueue_linearize(ctx, cam, residual_kind, nullptr, xyz, uv, 0.0, &nacc, nullptr);
 }
 
 extern "C" int32_t acm_linearize(acm_ctx* ctx, const acm_camera* cam, int32_t residual_kind, const acm_points* xyz, const acm_points* uv,
@@ -367,7 +466,7 @@ extern "C" int32_t acm_linearize(acm_ctx* ctx, const acm_camera* cam, int32_t re
     int32_t rc = check_lin_args(ctx, cam, xyz, uv);
     if (rc) return rc;
     int nacc = 0;
-    rc = enqueue_linearize(ctx, cam, residual_kind, nullptr, 0, xyz, uv, 0.0, &nacc);
+    rc = enqueue_linearize(ctx, cam, residual_kind, nullptr, xyz, uv, 0.0, &nacc, nullptr);
     if (rc) return rc;
     ACM_CUDA(ctx, cudaMemcpyAsync(ctx->h_reduce, ctx->d_reduce, nacc * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     ACM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -432,11 +531,11 @@ extern "C" int32_t acm_lm_solve(acm_ctx* ctx, const acm_camera* init, int32_t re
 
     int nacc = 0;
     auto one_iteration = [&]() -> int32_t {
-        const int fuse = (ctx->n_ranks == 1 && !getenv("ACM_LM_NO_FUSE")) ? 1 : 0;
-        int32_t r = enqueue_linearize(ctx, init, residual_kind, d, fuse, xyz, uv, cfg.invalid_penalty, &nacc);
+        int fuse = 0;
+        int32_t r = enqueue_linearize(ctx, init, residual_kind, d, xyz, uv, cfg.invalid_penalty, &nacc, &fuse);
         if (r) return r;
         if (!fuse) {
-            ACM_DISPATCH_LIN(init->model, residual_kind, (lm_step_kernel<M, KIND><<<1, 64, 0, ctx->stream>>>(d, ctx->d_reduce)));
+            ACM_DISPATCH_LIN(init->model, residual_kind, (lm_step_kernel<M, KIND><<<1, 128, 0, ctx->stream>>>(d, ctx->d_reduce)));
             ACM_CHECK_LAUNCH(ctx);
         }
         return ACM_OK;

@@ -42,3 +42,29 @@ def attach_communicator(ctx: Context) -> int:
     uid = broadcast_bytes(uid, 128, src=0)
     ctx.comm_init_rank(world, rank, uid)
     return world
+
+
+def all_gather_bytes(payload: bytes) -> bytes:
+    """Concatenation over ranks of equal-sized byte strings (default torch.distributed group)."""
+    import torch
+    import torch.distributed as dist
+    backend = dist.get_backend()
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    mine = torch.frombuffer(bytearray(payload), dtype=torch.uint8).to(dev)
+    out = [torch.zeros_like(mine) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, mine)
+    return b"".join(bytes(t.cpu().numpy().tobytes()) for t in out)
+
+
+def attach_peers(ctx: Context) -> int:
+    """NVLink peer exchange: every rank exports its exchange buffer (CUDA IPC handle), the handles
+    are all-gathered over torch.distributed and opened.  After this the cross-rank sum of the normal
+    equations and the LM step run inside the streaming kernel (no NCCL call per iteration)."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if world == 1:
+        return 1
+    handles = all_gather_bytes(ctx.peer_export())
+    ctx.peer_attach(world, rank, handles)
+    dist.barrier()
+    return world

@@ -113,6 +113,18 @@ class Context:
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
         self.check(_lib.acm_comm_init_rank(self._h, n_ranks, rank, buf))
 
+    def peer_export(self) -> bytes:
+        buf = (C.c_uint8 * 64)()
+        self.check(_lib.acm_peer_export(self._h, buf))
+        return bytes(buf)
+
+    def peer_attach(self, n_ranks: int, rank: int, handles: bytes):
+        buf = (C.c_uint8 * (64 * n_ranks)).from_buffer_copy(handles)
+        self.check(_lib.acm_peer_attach(self._h, n_ranks, rank, buf))
+
+    def peer_detach(self):
+        self.check(_lib.acm_peer_detach(self._h))
+
     def comm_size(self) -> int:
         return int(_lib.acm_comm_size(self._h))
 

@@ -42,7 +42,7 @@ def workload_config(n_gpus):
     return {"workload": "fused linearize (project + Jacobian + JtJ/Jtr), Double Sphere, pixel residual, f64 SoA",
             "camera_model": "double_sphere", "residual": "pixel", "points_per_gpu": N_POINTS, "global_points": N_POINTS * n_gpus,
             "correspondences": "X: seeded cone 85deg; uv = KannalaBrandt(samples/kannala_brandt.yaml).project(X)",
-            "l2_policy": "inputs (4 GB/GPU) larger than L2", "parallelism": f"dp{n_gpus} (points sharded, all-reduce of 29 f64)"}
+            "l2_policy": "inputs (4 GB/GPU) larger than L2", "parallelism": f"dp{n_gpus} (points sharded, all-reduce of 29 f64 fused into the kernel over NVLink peer memory)"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -152,7 +152,9 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     ctx = acm.Context(local_rank)
     if world > 1:
-        acm.attach_communicator(ctx)
+        acm.attach_communicator(ctx)          # NCCL: linear estimation, fallback all-reduce
+        if not args.no_peer:
+            acm.attach_peers(ctx)             # NVLink peer exchange fused into the streaming kernel
 
     def barrier():
         ctx.sync()
@@ -391,6 +393,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-lm", action="store_true")
+    ap.add_argument("--no-peer", action="store_true", help="N > 1: keep the NCCL all-reduce instead of the fused NVLink exchange")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -236,6 +236,16 @@ int32_t acm_comm_init_rank(acm_ctx* ctx, int32_t n_ranks, int32_t rank, const ui
 int32_t acm_comm_destroy(acm_ctx* ctx);
 int32_t acm_comm_size(const acm_ctx* ctx); /* 1 when no communicator is attached */
 
+/* Fused exchange over NVLink peer memory (one process per GPU on one NVSwitch box).  Every rank
+ * exports a small exchange buffer as a 64-byte CUDA IPC handle, the host gathers the handles of all
+ * ranks (any transport) and attaches them.  From then on the last block of the linearisation kernel
+ * stores its rank's normal equations straight into every peer's buffer, waits for the peers' and
+ * adds them in rank order -- pass, all-reduce and LM step are ONE kernel per iteration and every
+ * rank holds bit-identical sums.  Replaces the NCCL all-reduce of acm_linearize / acm_lm_solve. */
+int32_t acm_peer_export(acm_ctx* ctx, uint8_t handle[64]);
+int32_t acm_peer_attach(acm_ctx* ctx, int32_t n_ranks, int32_t rank, const uint8_t* handles /* n_ranks * 64 bytes */);
+int32_t acm_peer_detach(acm_ctx* ctx);
+
 #ifdef __cplusplus
 }
 #endif

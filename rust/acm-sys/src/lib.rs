@@ -146,4 +146,7 @@ extern "C" {
     pub fn acm_comm_init_rank(ctx: *mut acm_ctx, n_ranks: i32, rank: i32, id: *const u8) -> i32;
     pub fn acm_comm_destroy(ctx: *mut acm_ctx) -> i32;
     pub fn acm_comm_size(ctx: *const acm_ctx) -> i32;
+    pub fn acm_peer_export(ctx: *mut acm_ctx, handle: *mut u8) -> i32;
+    pub fn acm_peer_attach(ctx: *mut acm_ctx, n_ranks: i32, rank: i32, handles: *const u8) -> i32;
+    pub fn acm_peer_detach(ctx: *mut acm_ctx) -> i32;
 }

@@ -276,6 +276,38 @@ def test_linearize_matches_oracle(acm, ctx, O, cameras, name):
             cost.free()
 
 
+def test_empty_and_degenerate_inputs(acm, ctx, O, cameras):
+    """Empty point sets: zero normal equations, LM returns the (clamped) start, stats raise
+    ZeroProjectionPoints like the reference (error_metrics.rs:83-85)."""
+    ds = gpu_model(acm, ctx, cameras["double_sphere"])
+    empty3, empty2 = np.zeros((0, 3)), np.zeros((0, 2))
+    cost = acm.DoubleSphereOptimizationCost(ds, empty3, empty2)
+    H, g, c, nv = cost.linearize()
+    assert nv == 0 and c == 0.0 and not H.any() and not g.any()
+    start = ds.params().copy()
+    r = cost.optimize(bounds=None)
+    assert np.array_equal(r.parameters, start) and r.n_valid == 0
+    with pytest.raises(acm.ZeroProjectionPoints):
+        acm.compute_reprojection_error(ds, empty3, empty2)
+    uv, st = ds.project_batch(empty3)
+    assert uv.shape == (0, 2) and st.shape == (0,)
+    # every point invalid
+    behind = np.tile([0.0, 0.0, -1.0], (5, 1))
+    cost2 = acm.DoubleSphereOptimizationCost(ds, behind, np.zeros((5, 2)), residual_kind=0)
+    H, g, c, nv = cost2.linearize()
+    assert nv == 0 and c == 0.0 and not H.any()
+    # NaN coordinates are invalid points, not poison (oracle: status != Ok -> skipped)
+    pts = O.synth_points3(3, 0, 1001, cone("double_sphere"), False)
+    om = oracle_model(O, cameras["double_sphere"])
+    obs, _ = O.project(om, pts)
+    obs += 0.1
+    pts[::100] = np.nan
+    cost3 = acm.DoubleSphereOptimizationCost(ds, pts, obs, residual_kind=0)
+    H, g, c, nv = cost3.linearize()
+    Ho, go, co, nvo = O.linearize(om, 0, pts, obs)
+    assert nv == nvo == 1001 - 11 and np.all(np.isfinite(H)) and np.allclose(H, Ho, rtol=1e-9) and np.isclose(c, co, rtol=1e-9)
+
+
 def test_linearize_argument_errors(acm, ctx, O, cameras):
     kb = gpu_model(acm, ctx, cameras["kannala_brandt"])
     xyz = np.zeros((4, 3)) + [0.1, 0.1, 1.0]
