@@ -43,39 +43,50 @@ struct LmWork {
     double red[64];
 };
 
-__device__ __noinline__ bool chol_solve_work(int P, LmWork* w) {
-    double* L = w->L;
-#pragma unroll 1
+// Cholesky solve of the damped, Jacobi-scaled system (P <= 9) by one thread: operands are pulled
+// from the shared LmWork into registers once, the factorisation is fully unrolled (compile-time P),
+// the result goes back to w->st.  Reciprocals of the diagonal replace the divisions of the
+// substitutions (a dependent f64 division costs ~150 cycles).
+template <int P>
+__device__ __noinline__ bool chol_solve_work(LmWork* w) {
+    double L[P * (P + 1) / 2], inv[P], yv[P], x[P];
+#pragma unroll
+    for (int i = 0; i < P; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) L[i * (i + 1) / 2 + j] = w->A[i * P + j];
+#pragma unroll
     for (int i = 0; i < P; ++i) {
-#pragma unroll 1
+#pragma unroll
         for (int j = 0; j <= i; ++j) {
-            double sum = w->A[i * P + j];
-#pragma unroll 1
-            for (int k = 0; k < j; ++k) sum -= L[i * P + k] * L[j * P + k];
+            double sum = L[i * (i + 1) / 2 + j];
+#pragma unroll
+            for (int k = 0; k < j; ++k) sum -= L[i * (i + 1) / 2 + k] * L[j * (j + 1) / 2 + k];
             if (i == j) {
                 if (!(sum > 0.0)) return false;
                 const double d = sqrt(sum);
-                L[i * P + i] = d;
-                w->invdiag[i] = 1.0 / d;
+                L[i * (i + 1) / 2 + i] = d;
+                inv[i] = 1.0 / d;
             } else {
-                L[i * P + j] = sum * w->invdiag[j];
+                L[i * (i + 1) / 2 + j] = sum * inv[j];
             }
         }
     }
-#pragma unroll 1
+#pragma unroll
     for (int i = 0; i < P; ++i) {
         double sum = w->gs[i];
-#pragma unroll 1
-        for (int k = 0; k < i; ++k) sum -= L[i * P + k] * w->yv[k];
-        w->yv[i] = sum * w->invdiag[i];
+#pragma unroll
+        for (int k = 0; k < i; ++k) sum -= L[i * (i + 1) / 2 + k] * yv[k];
+        yv[i] = sum * inv[i];
     }
-#pragma unroll 1
+#pragma unroll
     for (int i = P - 1; i >= 0; --i) {
-        double sum = w->yv[i];
-#pragma unroll 1
-        for (int k = i + 1; k < P; ++k) sum -= L[k * P + i] * w->st[k];
-        w->st[i] = sum * w->invdiag[i];
+        double sum = yv[i];
+#pragma unroll
+        for (int k = i + 1; k < P; ++k) sum -= L[k * (k + 1) / 2 + i] * x[k];
+        x[i] = sum * inv[i];
     }
+#pragma unroll
+    for (int i = 0; i < P; ++i) w->st[i] = x[i];
     return true;
 }
 
@@ -167,7 +178,7 @@ __device__ __forceinline__ void lm_step_block(LmState* __restrict__ s, const dou
             if (tid < P) w->gs[tid] = -sh->g[tid] * w->invD[tid];
             __syncthreads();
             if (tid == 0) {
-                if (!chol_solve_work(P, w)) {
+                if (!chol_solve_work<P>(w)) {
                     sh->lambda *= sh->nu; sh->nu *= 2.0;
                     flag_ok = 0;
                     if (sh->lambda > 1e30) { sh->status = 4; sh->done = 1; flag_ok = -1; }
@@ -284,10 +295,12 @@ __global__ void __launch_bounds__(BS) linearize_kernel(LinParams hp, LmState* __
 
     LinParams p = hp;
     if (lm) {
-        if (lm->done) return;  // converged earlier in this enqueue batch
+        // one round trip: the done flag and the trial parameters are fetched together
+        const int done = lm->done;
         p.fx = lm->xt[0]; p.fy = lm->xt[1]; p.cx = lm->xt[2]; p.cy = lm->xt[3];
 #pragma unroll
         for (int k = 0; k < ND; ++k) p.d[k] = lm->xt[4 + k];
+        if (done) return;  // converged earlier in this enqueue batch
         lin_derive(M, p);
     }
 
