@@ -51,6 +51,7 @@ extern "C" int32_t acm_ctx_create(int32_t device, void* cuda_stream, acm_ctx** o
     ctx->d_partials = nullptr; ctx->partials_cap = 0; ctx->d_reduce = nullptr; ctx->d_ticket = nullptr; ctx->h_reduce = nullptr;
     ctx->d_lm = nullptr; ctx->h_lm = nullptr; ctx->d_stage[0] = ctx->d_stage[1] = nullptr; ctx->stage_cap = 0;
     ctx->h_stage = nullptr; ctx->h_stage_cap = 0;
+    ctx->cache3 = nullptr; ctx->cache2 = nullptr; ctx->cache_cap = 0;
     ctx->peer_local = nullptr; ctx->d_peer_ptrs = nullptr; ctx->peer_n = 0; ctx->peer_rank = 0; ctx->peer_seq = 0;
     for (int i = 0; i < ACM_MAX_PEERS; ++i) ctx->peer_mapped[i] = nullptr;
 #define CREATE_CUDA(call)                                                                                     \
@@ -85,6 +86,7 @@ extern "C" int32_t acm_ctx_destroy(acm_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     acm_comm_destroy(ctx);
     acm_peer_detach(ctx);
+    acm_points_destroy(ctx, ctx->cache3); acm_points_destroy(ctx, ctx->cache2);
     cudaFree(ctx->peer_local);
     cudaFree(ctx->d_partials); cudaFree(ctx->d_reduce); cudaFree(ctx->d_ticket); cudaFreeHost(ctx->h_reduce);
     cudaFree(ctx->d_lm); cudaFreeHost(ctx->h_lm);

@@ -60,6 +60,9 @@ struct acm_ctx {
     size_t stage_cap;
     void* h_stage;          // pinned staging for pageable host buffers
     size_t h_stage_cap;
+    acm_points* cache3;     // device buffers kept between *_host calls (grow-only)
+    acm_points* cache2;
+    size_t cache_cap;
     // NCCL
     void* comm;
     int n_ranks, rank;

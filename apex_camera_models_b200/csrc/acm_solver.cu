@@ -490,15 +490,24 @@ extern "C" int32_t acm_linearize_host(acm_ctx* ctx, const acm_camera* cam, int32
                                       size_t n, acm_normal_equations* out) {
     if (!ctx || !out) return ACM_ERR_INVALID_ARG;
     ACM_REQUIRE(ctx, cam && (n == 0 || (xyz_aos && uv_aos)), "linearize_host: null argument");
-    acm_points *xyz = nullptr, *uv = nullptr;
-    int32_t rc = acm_points_create(ctx, 3, n, ACM_F64, &xyz);
-    if (!rc) rc = acm_points_create(ctx, 2, n, ACM_F64, &uv);
-    if (!rc) rc = acm_points_upload_any(ctx, xyz, xyz_aos, n, 0);
+    // device buffers are kept between calls (grow-only): a 4 GB cudaMalloc/cudaFree pair per call
+    // would cost more than the kernel
+    if (ctx->cache_cap < n || !ctx->cache3) {
+        cudaStreamSynchronize(ctx->stream);
+        acm_points_destroy(ctx, ctx->cache3); acm_points_destroy(ctx, ctx->cache2);
+        ctx->cache3 = ctx->cache2 = nullptr; ctx->cache_cap = 0;
+        int32_t rc0 = acm_points_create(ctx, 3, n, ACM_F64, &ctx->cache3);
+        if (!rc0) rc0 = acm_points_create(ctx, 2, n, ACM_F64, &ctx->cache2);
+        if (rc0) { acm_points_destroy(ctx, ctx->cache3); ctx->cache3 = nullptr; return rc0; }
+        ctx->cache_cap = n;
+    }
+    acm_points* xyz = ctx->cache3; acm_points* uv = ctx->cache2;
+    xyz->n = n; uv->n = n;  // views of the first n points (the component stride is unchanged)
+    int32_t rc = acm_points_upload_any(ctx, xyz, xyz_aos, n, 0);
     if (!rc) rc = acm_points_upload_any(ctx, uv, uv_aos, n, 0);
     if (!rc) rc = acm_linearize(ctx, cam, residual_kind, xyz, uv, out);
     cudaStreamSynchronize(ctx->stream);
-    acm_points_destroy(ctx, xyz);
-    acm_points_destroy(ctx, uv);
+    xyz->n = ctx->cache_cap; uv->n = ctx->cache_cap;
     return rc;
 }
 

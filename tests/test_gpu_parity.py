@@ -308,6 +308,24 @@ def test_empty_and_degenerate_inputs(acm, ctx, O, cameras):
     assert nv == nvo == 1001 - 11 and np.all(np.isfinite(H)) and np.allclose(H, Ho, rtol=1e-9) and np.isclose(c, co, rtol=1e-9)
 
 
+def test_linearize_host_entry_point(acm, ctx, O, cameras):
+    """acm_linearize_host (the e2e path of bench.py: nalgebra-layout host buffers in, normal equations
+    out) equals the device-buffer path; the cached device staging survives growing and shrinking n."""
+    from apex_camera_models_b200 import _native as N
+    cam = cameras["double_sphere"]
+    m, om = gpu_model(acm, ctx, cam), oracle_model(O, cam)
+    block = m.camera_block()
+    for n in (1000, 9_000_001, 77, 0):
+        xyz, obs = _correspondences(O, om, "double_sphere", n) if n else (np.zeros((0, 3)), np.zeros((0, 2)))
+        ne = N.NormalEquations()
+        ctx.check(N.lib.acm_linearize_host(ctx.handle, C.byref(block), 0, xyz.ctypes.data_as(C.c_void_p), obs.ctypes.data_as(C.c_void_p), n, C.byref(ne)))
+        cost = acm.DoubleSphereOptimizationCost(m, xyz, obs, residual_kind=0)
+        H, g, c, nv = cost.linearize()
+        assert ne.n_valid == nv and ne.cost == c
+        assert np.array_equal(np.array(ne.H[:36]).reshape(6, 6), H) and np.array_equal(np.array(ne.g[:6]), g)
+        cost.free()
+
+
 def test_linearize_argument_errors(acm, ctx, O, cameras):
     kb = gpu_model(acm, ctx, cameras["kannala_brandt"])
     xyz = np.zeros((4, 3)) + [0.1, 0.1, 1.0]
