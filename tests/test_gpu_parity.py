@@ -104,6 +104,97 @@ def test_fused_round_trip_matches_oracle(acm, ctx, O, cameras, name):
         assert np.max(np.abs(ray[good] - d)) < 1e-5
 
 
+def _random_cameras(name, rng, count):
+    """Random parameter sets that exercise every branch of the validity tests (alpha on both sides
+    of 0.5, alpha > 1 for UCM/EUCM, negative xi, w near its bounds, KB without a resolution, ...)."""
+    out = []
+    for k in range(count):
+        W, H = int(rng.integers(64, 2000)), int(rng.integers(64, 1500))
+        f = float(rng.uniform(0.2, 1.5) * W)
+        intr = [f, f * float(rng.uniform(0.97, 1.03)), W * float(rng.uniform(0.4, 0.6)), H * float(rng.uniform(0.4, 0.6))]
+        if name == "pinhole":
+            d = []
+        elif name == "rad_tan":
+            d = [float(rng.uniform(-0.4, 0.2)), float(rng.uniform(-0.1, 0.2)), float(rng.uniform(-2e-3, 2e-3)), float(rng.uniform(-2e-3, 2e-3)), float(rng.uniform(-0.05, 0.05))]
+        elif name == "kannala_brandt":
+            d = [float(rng.uniform(-0.05, 0.05)), float(rng.uniform(-0.02, 0.02)), float(rng.uniform(-0.01, 0.01)), float(rng.uniform(-0.002, 0.002))]
+            if k % 4 == 3:
+                W = H = 0  # resolution unset: unproject skips the bounds test (kannala_brandt.rs:447-455)
+        elif name == "ucm":
+            d = [float(rng.choice([rng.uniform(0.05, 0.5), rng.uniform(0.5, 0.99), rng.uniform(1.0, 1.3), 0.5]))]
+        elif name == "eucm":
+            d = [float(rng.choice([rng.uniform(0.05, 0.5), rng.uniform(0.5, 0.99), rng.uniform(1.0, 1.2), 0.5])), float(rng.uniform(0.3, 2.5))]
+        elif name == "double_sphere":
+            d = [float(rng.choice([rng.uniform(0.05, 0.5), rng.uniform(0.5, 1.0), 0.5, 1.0])), float(rng.uniform(-0.6, 0.9))]
+        else:  # fov
+            d = [float(rng.choice([rng.uniform(0.05, 3.0), 1e-9, 3.0]))]
+        out.append({"model_id": MODELS.index(name), "params": intr + d, "width": W, "height": H})
+    return out
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_random_cameras_project_unproject(acm, ctx, O, cameras, name):
+    """Same bars as above on 24 random cameras per model: masks bit-exact, values bit-exact for the
+    arithmetic-only models and within 1e-9 for KB / FOV, fused round trip consistent."""
+    rng = np.random.default_rng(0xACE5 + MODELS.index(name))
+    n = 20_003
+    for k, cam in enumerate(_random_cameras(name, rng, 24)):
+        m, om = gpu_model(acm, ctx, cam), oracle_model(O, cam)
+        xyz = O.synth_points3(0xACE50002, 1000 * k, n, float(np.cos(np.deg2rad(rng.uniform(30.0, 120.0)))), True)
+        xyz[5::97] *= 1e-3      # points very close to the camera (den < 1e-3 branches)
+        xyz[7::101, :2] = 0.0   # on the optical axis (r == 0 branches of KB / FOV)
+        uv, st = m.project_batch(xyz)
+        uvo, sto = O.project(om, xyz)
+        assert np.array_equal(st, sto), (name, cam["params"])
+        assert_close_where_valid(uv, uvo, sto == 0, name)
+        Wp, Hp = (cam["width"] or 800), (cam["height"] or 600)
+        px = O.synth_pixels(0xACE50002, 1000 * k, n, Wp * 1.2, Hp * 1.2) - [0.1 * Wp, 0.1 * Hp]   # in and around the image
+        px[3::89] = cam["params"][2:4]                                                            # the principal point itself
+        px[4::89] = [cam["params"][2] + 0.5e-6 * cam["params"][0], cam["params"][3]]             # KB's 1e-6 hole
+        ray, st = m.unproject_batch(px)
+        rayo, sto = O.unproject(om, px)
+        assert np.array_equal(st, sto), (name, cam["params"])
+        # DS / EUCM can return NaN rays with status Ok (sqrt of a slightly negative radicand): NaN patterns must match too
+        assert np.array_equal(np.isnan(ray), np.isnan(rayo))
+        fin = (sto == 0) & ~np.isnan(rayo).any(axis=1)
+        if name in EXACT:
+            assert np.array_equal(ray[fin], rayo[fin])
+        else:
+            assert np.allclose(ray[fin], rayo[fin], rtol=RTOL, atol=1e-13)
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_random_cameras_linearize_and_jacobian(acm, ctx, O, cameras, name):
+    """Stress version of test_linearize_matches_oracle: random cameras, points on the axis and 1e-3
+    from the camera.  The bar is 2e-8 here instead of 1e-9: the published derivatives contain
+    d - z (UCM / EUCM) and d2 - g (DS), which cancel for near-axis points, so a 1-ulp difference in
+    sqrt (IEEE in the oracle, MUFU + Newton on the device) is amplified by z / (d - z) in those
+    columns -- in both implementations alike.  FOV with w -> 0 is left out for the same reason
+    (da/(r w) - a/(r w^2) cancels to 1e-8 at w = 1e-9)."""
+    rng = np.random.default_rng(0xBEEF + MODELS.index(name))
+    n = 5_001
+    STRESS_RTOL = 2e-8
+    for k, cam in enumerate(_random_cameras(name, rng, 8)):
+        if cam["width"] == 0:
+            cam["width"], cam["height"] = 640, 480
+        if name == "fov" and cam["params"][4] < 0.05:
+            cam["params"][4] = 0.05
+        m, om = gpu_model(acm, ctx, cam), oracle_model(O, cam)
+        xyz = O.synth_points3(0xACE50003, 500 * k, n, float(np.cos(np.deg2rad(rng.uniform(30.0, 110.0)))), True)
+        obs, _ = O.project(om, xyz)
+        obs = np.where(np.isnan(obs), 3.0, obs) + rng.normal(0.0, 0.5, (n, 2))
+        for kind in ((0, 1) if name in UNIFIED else (0,)):
+            cost = acm.OptimizationCost(m, xyz, obs, residual_kind=kind)
+            H, g, c, nv = cost.linearize()
+            Ho, go, co, nvo = O.linearize(om, kind, xyz, obs, nthreads=4)
+            assert nv == nvo, (name, cam["params"])
+            dg = np.sqrt(np.abs(np.diag(Ho))) + 1e-300
+            assert np.max(np.abs(H - Ho) / np.outer(dg, dg)) < STRESS_RTOL, (name, kind, cam["params"])
+            assert np.max(np.abs(g - go) / (dg * np.sqrt(2 * co) + 1e-300)) < STRESS_RTOL
+            assert abs(c - co) <= RTOL * co
+            cost.free()
+
+
 @pytest.mark.parametrize("n", [0, 1, 2, 3, 5, 255, 256, 257, 511, 513])
 def test_edge_sizes(acm, ctx, O, cameras, n):
     for name in ("double_sphere", "kannala_brandt"):
