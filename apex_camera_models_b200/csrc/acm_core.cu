@@ -52,6 +52,7 @@ extern "C" int32_t acm_ctx_create(int32_t device, void* cuda_stream, acm_ctx** o
     ctx->d_lm = nullptr; ctx->h_lm = nullptr; ctx->d_stage[0] = ctx->d_stage[1] = nullptr; ctx->stage_cap = 0;
     ctx->h_stage = nullptr; ctx->h_stage_cap = 0;
     ctx->cache3 = nullptr; ctx->cache2 = nullptr; ctx->cache_cap = 0;
+    ctx->d_scratch = nullptr; ctx->scratch_cap = 0;
     ctx->peer_local = nullptr; ctx->d_peer_ptrs = nullptr; ctx->peer_n = 0; ctx->peer_rank = 0; ctx->peer_seq = 0;
     for (int i = 0; i < ACM_MAX_PEERS; ++i) ctx->peer_mapped[i] = nullptr;
 #define CREATE_CUDA(call)                                                                                     \
@@ -88,6 +89,7 @@ extern "C" int32_t acm_ctx_destroy(acm_ctx* ctx) {
     acm_peer_detach(ctx);
     acm_points_destroy(ctx, ctx->cache3); acm_points_destroy(ctx, ctx->cache2);
     cudaFree(ctx->peer_local);
+    cudaFree(ctx->d_scratch);
     cudaFree(ctx->d_partials); cudaFree(ctx->d_reduce); cudaFree(ctx->d_ticket); cudaFreeHost(ctx->h_reduce);
     cudaFree(ctx->d_lm); cudaFreeHost(ctx->h_lm);
     cudaFree(ctx->d_stage[0]); cudaFree(ctx->d_stage[1]); cudaFreeHost(ctx->h_stage);
@@ -313,6 +315,16 @@ int32_t acm_ensure_host_stage(acm_ctx* ctx, size_t bytes) {
     cudaFreeHost(ctx->h_stage); ctx->h_stage = nullptr; ctx->h_stage_cap = 0;
     ACM_CUDA(ctx, cudaMallocHost(&ctx->h_stage, bytes));
     ctx->h_stage_cap = bytes;
+    return ACM_OK;
+}
+
+int32_t acm_ensure_scratch(acm_ctx* ctx, size_t bytes) {
+    if (ctx->scratch_cap >= bytes) return ACM_OK;
+    ACM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->d_scratch); ctx->d_scratch = nullptr; ctx->scratch_cap = 0;
+    const size_t want = bytes + bytes / 4;  // head room: the arena only ever grows
+    ACM_CUDA(ctx, cudaMalloc(&ctx->d_scratch, want));
+    ctx->scratch_cap = want;
     return ACM_OK;
 }
 

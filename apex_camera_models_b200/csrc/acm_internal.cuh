@@ -60,6 +60,8 @@ struct acm_ctx {
     size_t stage_cap;
     void* h_stage;          // pinned staging for pageable host buffers
     size_t h_stage_cap;
+    void* d_scratch;        // grow-only arena for the temporaries of the util entry points
+    size_t scratch_cap;
     acm_points* cache3;     // device buffers kept between *_host calls (grow-only)
     acm_points* cache2;
     size_t cache_cap;
@@ -112,6 +114,7 @@ int32_t acm_make_cam_params(acm_ctx* ctx, const acm_camera* cam, CamParams* out)
 int32_t acm_ensure_stage(acm_ctx* ctx, size_t bytes);
 int32_t acm_ensure_host_stage(acm_ctx* ctx, size_t bytes);
 int32_t acm_ensure_partials(acm_ctx* ctx, size_t doubles);
+int32_t acm_ensure_scratch(acm_ctx* ctx, size_t bytes);  // ctx->d_scratch holds >= bytes afterwards (256-byte aligned)
 int32_t acm_allreduce_sum_f64(acm_ctx* ctx, double* d_buf, size_t count);
 int32_t acm_points_upload_any(acm_ctx* ctx, acm_points* p, const double* host_aos, size_t n, size_t dst_offset);
 

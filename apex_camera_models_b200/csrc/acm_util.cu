@@ -128,13 +128,16 @@ extern "C" int32_t acm_reprojection_error(acm_ctx* ctx, const acm_camera* cam, c
     if (rc) return rc;
     rc = acm_ensure_partials(ctx, (size_t)ctx->sm_count * 32 * 64);
     if (rc) return rc;
-    double* d_E = nullptr;
-    SelectState* d_sel = nullptr;
-    ACM_CUDA(ctx, cudaMalloc(&d_E, n * sizeof(double)));
-    if (cudaMalloc(&d_sel, sizeof(SelectState)) != cudaSuccess) { cudaFree(d_E); return acm_fail(ctx, ACM_ERR_CUDA, "cudaMalloc failed"); }
+    // temporaries live in the context's grow-only arena (a cudaMalloc/cudaFree pair per call costs
+    // more than the kernels at 10 M points)
+    const size_t e_bytes = ((n * sizeof(double) + 255) / 256) * 256;
+    rc = acm_ensure_scratch(ctx, e_bytes + sizeof(SelectState));
+    if (rc) return rc;
+    double* d_E = static_cast<double*>(ctx->d_scratch);
+    SelectState* d_sel = reinterpret_cast<SelectState*>(static_cast<char*>(ctx->d_scratch) + e_bytes);
     int grid = grid_for(ctx, n, 256, 4);
     double* h = ctx->h_reduce;
-    auto cleanup = [&]() { cudaStreamSynchronize(ctx->stream); cudaFree(d_E); cudaFree(d_sel); };
+    auto cleanup = [&]() { cudaStreamSynchronize(ctx->stream); };
 #define UTIL_TRY(expr) do { int32_t _rc = (expr); if (_rc) { cleanup(); return _rc; } } while (0)
     auto launch1 = [&]() -> int32_t {
         ACM_DISPATCH_MODEL(cam->model, (reproj_pass1_kernel<M><<<grid, 256, 0, ctx->stream>>>(
@@ -254,39 +257,41 @@ extern "C" int32_t acm_sample_points(acm_ctx* ctx, const acm_camera* cam, size_t
     const int ncy = (int)round(sqrt((double)n_requested * (height / width)));
     const size_t total = (size_t)((long long)ncx * (long long)ncy);
     const double cell_w = width / (double)ncx, cell_h = height / (double)ncy;
-    acm_points *uvp = nullptr, *xyzp = nullptr, *tmp = nullptr;
+    acm_points *uvp = nullptr, *xyzp = nullptr;
     rc = acm_points_create(ctx, 2, total, ACM_F64, &uvp);
     if (!rc) rc = acm_points_create(ctx, 3, total, ACM_F64, &xyzp);
-    if (!rc) rc = acm_points_create(ctx, 3, total, ACM_F64, &tmp);
     const size_t nblk = (total + 255) / 256;
-    uint8_t* d_keep = nullptr; unsigned int* d_cnt = nullptr; unsigned long long* d_off = nullptr;
-    if (!rc && total > 0) {
-        cudaError_t e = cudaMalloc(&d_keep, total);
-        if (e == cudaSuccess) e = cudaMalloc(&d_cnt, nblk * sizeof(unsigned int));
-        if (e == cudaSuccess) e = cudaMalloc(&d_off, (nblk + 1) * sizeof(unsigned long long));
-        if (e != cudaSuccess) rc = acm_fail(ctx, ACM_ERR_CUDA, "sample_points: cudaMalloc failed: %s", cudaGetErrorString(e));
-    }
+    // temporaries (rays before compaction, keep flags, block counts / offsets) in the context's arena
+    auto up256 = [](size_t b) { return ((b + 255) / 256) * 256; };
+    const size_t ray_bytes = up256(total * sizeof(double)), keep_bytes = up256(total), cnt_bytes = up256(nblk * sizeof(unsigned int)),
+                 off_bytes = up256((nblk + 1) * sizeof(unsigned long long));
+    if (!rc) rc = acm_ensure_scratch(ctx, 3 * ray_bytes + keep_bytes + cnt_bytes + off_bytes);
     unsigned long long kept = 0;
     if (!rc && total > 0) {
+        char* base = static_cast<char*>(ctx->d_scratch);
+        double* RX = reinterpret_cast<double*>(base);
+        double* RY = reinterpret_cast<double*>(base + ray_bytes);
+        double* RZ = reinterpret_cast<double*>(base + 2 * ray_bytes);
+        uint8_t* d_keep = reinterpret_cast<uint8_t*>(base + 3 * ray_bytes);
+        unsigned int* d_cnt = reinterpret_cast<unsigned int*>(base + 3 * ray_bytes + keep_bytes);
+        unsigned long long* d_off = reinterpret_cast<unsigned long long*>(base + 3 * ray_bytes + keep_bytes + cnt_bytes);
         auto run = [&]() -> int32_t {
             ACM_DISPATCH_MODEL(cam->model, (sample_unproject_kernel<M><<<(unsigned)nblk, 256, 0, ctx->stream>>>(
-                c, ncx, total, cell_w, cell_h, comp<double>(tmp, 0), comp<double>(tmp, 1), comp<double>(tmp, 2), d_keep, d_cnt)))
+                c, ncx, total, cell_w, cell_h, RX, RY, RZ, d_keep, d_cnt)))
             ACM_CHECK_LAUNCH(ctx);
             scan_block_counts_kernel<<<1, 1024, 0, ctx->stream>>>(d_cnt, nblk, d_off, d_off + nblk);
             ACM_CHECK_LAUNCH(ctx);
-            sample_scatter_kernel<<<(unsigned)nblk, 256, 0, ctx->stream>>>(ncx, total, cell_w, cell_h, comp<double>(tmp, 0), comp<double>(tmp, 1),
-                                                                          comp<double>(tmp, 2), d_keep, d_off, comp<double>(uvp, 0), comp<double>(uvp, 1),
-                                                                          comp<double>(xyzp, 0), comp<double>(xyzp, 1), comp<double>(xyzp, 2));
+            sample_scatter_kernel<<<(unsigned)nblk, 256, 0, ctx->stream>>>(ncx, total, cell_w, cell_h, RX, RY, RZ, d_keep, d_off,
+                                                                          comp<double>(uvp, 0), comp<double>(uvp, 1), comp<double>(xyzp, 0),
+                                                                          comp<double>(xyzp, 1), comp<double>(xyzp, 2));
             ACM_CHECK_LAUNCH(ctx);
-            ACM_CUDA(ctx, cudaMemcpyAsync(&kept, d_off + nblk, sizeof(kept), cudaMemcpyDeviceToHost, ctx->stream));
+            ACM_CUDA(ctx, cudaMemcpyAsync(ctx->h_reduce, d_off + nblk, sizeof(kept), cudaMemcpyDeviceToHost, ctx->stream));
             ACM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            memcpy(&kept, ctx->h_reduce, sizeof(kept));
             return ACM_OK;
         };
         rc = run();
     }
-    cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_keep); cudaFree(d_cnt); cudaFree(d_off);
-    acm_points_destroy(ctx, tmp);
     if (rc) { acm_points_destroy(ctx, uvp); acm_points_destroy(ctx, xyzp); return rc; }
     uvp->n = (size_t)kept; xyzp->n = (size_t)kept;  // capacity stays `total`
     *uv_out = uvp; *xyz_out = xyzp; *n_kept = (size_t)kept;
