@@ -624,6 +624,33 @@ int32_t acm_allreduce_sum_f64(acm_ctx* ctx, double* d_buf, size_t count) {
     return ACM_OK;
 }
 
+int32_t acm_allreduce_sum_u64(acm_ctx* ctx, unsigned long long* d_buf, size_t count) {
+    if (ctx->n_ranks == 1) return ACM_OK;
+    if (!ctx->comm) return acm_fail(ctx, ACM_ERR_NCCL, "this operation needs an NCCL communicator (acm_comm_init_rank) when ranks > 1");
+    int r = g_nccl.AllReduce(d_buf, d_buf, count, /*ncclUint64*/ 5, /*ncclSum*/ 0, ctx->comm, ctx->stream);
+    if (r != 0) return acm_fail(ctx, ACM_ERR_NCCL, "ncclAllReduce: %s", nccl_err(r));
+    return ACM_OK;
+}
+
+// Bring the first `count` doubles of ctx->d_reduce of every rank to every host: afterwards
+// ctx->h_reduce holds [n_ranks][count] in rank order (stream synchronised).  Every rank writes its
+// vector into its own slot of a zero-padded buffer, so the all-reduce acts as an all-gather and
+// the caller can combine the slots in rank order -- identical bits on every rank.
+int32_t acm_rank_gather_to_host(acm_ctx* ctx, int count) {
+    const int R = ctx->n_ranks;
+    if (R > 1) {
+        if ((size_t)R * count > 1024) return acm_fail(ctx, ACM_ERR_INVALID_ARG, "too many ranks for the gather buffer");
+        ACM_CUDA(ctx, cudaMemcpyAsync(ctx->d_partials, ctx->d_reduce, count * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        ACM_CUDA(ctx, cudaMemsetAsync(ctx->d_reduce, 0, (size_t)R * count * sizeof(double), ctx->stream));
+        ACM_CUDA(ctx, cudaMemcpyAsync(ctx->d_reduce + (size_t)ctx->rank * count, ctx->d_partials, count * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        int32_t rc = acm_allreduce_sum_f64(ctx, ctx->d_reduce, (size_t)R * count);
+        if (rc) return rc;
+    }
+    ACM_CUDA(ctx, cudaMemcpyAsync(ctx->h_reduce, ctx->d_reduce, (size_t)R * count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    ACM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ACM_OK;
+}
+
 // ---------------------------------------------------------------------------------------
 // NVLink peer exchange buffers (CUDA IPC; one process per GPU)
 // ---------------------------------------------------------------------------------------

@@ -40,10 +40,9 @@ __global__ void __launch_bounds__(256) reproj_pass1_kernel(const __grid_constant
     GridReduce<3, 2, 0>::run(acc, partials, out, ticket);
 }
 
-// pass 2: sum (e - mean)^2 ; mean = out[1] / out[0] read from device memory
-__global__ void __launch_bounds__(256) reproj_pass2_kernel(const double* __restrict__ E, size_t n, const double* __restrict__ stats,
-                                                           double* partials, double* out, unsigned int* ticket) {
-    const double mean = stats[1] / stats[0];
+// pass 2: sum (e - mean)^2
+__global__ void __launch_bounds__(256) reproj_pass2_kernel(const double* __restrict__ E, size_t n, double mean, double* partials, double* out,
+                                                           unsigned int* ticket) {
     double acc[1] = {0.0};
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -57,7 +56,7 @@ __global__ void __launch_bounds__(256) reproj_pass2_kernel(const double* __restr
 struct SelectState {
     unsigned long long prefix;  // high bits fixed so far
     unsigned long long rank;    // rank still to find inside the prefix class
-    unsigned int hist[256];
+    unsigned long long hist[256];  // 64-bit so that the counts of all ranks can be summed in place
     int shift;                  // current digit position (56, 48, ..., 0)
 };
 
@@ -81,7 +80,7 @@ __global__ void __launch_bounds__(256) select_hist_kernel(const double* __restri
         if ((k & mask) == prefix) atomicAdd(&sh[(k >> shift) & 0xFF], 1u);
     }
     __syncthreads();
-    if (sh[threadIdx.x]) atomicAdd(&s->hist[threadIdx.x], sh[threadIdx.x]);
+    if (sh[threadIdx.x]) atomicAdd(&s->hist[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
 }
 
 __global__ void select_pick_kernel(SelectState* s) {
@@ -107,6 +106,10 @@ static int32_t select_kth(acm_ctx* ctx, const double* d_E, size_t n, unsigned lo
     for (int pass = 0; pass < 8; ++pass) {
         select_hist_kernel<<<grid, 256, 0, ctx->stream>>>(d_E, n, d_state);
         ACM_CHECK_LAUNCH(ctx);
+        if (ctx->n_ranks > 1) {  // histogram of the whole set: every rank then picks the same digit
+            int32_t rc = acm_allreduce_sum_u64(ctx, d_state->hist, 256);
+            if (rc) return rc;
+        }
         select_pick_kernel<<<1, 32, 0, ctx->stream>>>(d_state);
         ACM_CHECK_LAUNCH(ctx);
     }
@@ -122,7 +125,8 @@ extern "C" int32_t acm_reprojection_error(acm_ctx* ctx, const acm_camera* cam, c
     ACM_REQUIRE(ctx, xyz->dtype == ACM_F64 && uv->dtype == ACM_F64, "reprojection_error: f64 buffers required");
     memset(out, 0, sizeof(*out));
     const size_t n = xyz->n;
-    if (n == 0) return acm_fail(ctx, ACM_ERR_ZERO_PROJECTION_POINTS, "No valid projections");
+    // an empty shard still takes part in the collectives of a multi-rank call
+    if (n == 0 && ctx->n_ranks == 1) return acm_fail(ctx, ACM_ERR_ZERO_PROJECTION_POINTS, "No valid projections");
     CamParams c;
     int32_t rc = acm_make_cam_params(ctx, cam, &c);
     if (rc) return rc;
@@ -147,24 +151,32 @@ extern "C" int32_t acm_reprojection_error(acm_ctx* ctx, const acm_camera* cam, c
         return ACM_OK;
     };
     UTIL_TRY(launch1());
-    cudaError_t e = cudaMemcpyAsync(h, ctx->d_reduce, 5 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) { cleanup(); return acm_fail(ctx, ACM_ERR_CUDA, "reprojection_error: %s", cudaGetErrorString(e)); }
-    const double cnt = h[0], sum = h[1], sumsq = h[2], mx = h[3], mn = -h[4];
+    // with a communicator attached the point buffers are this rank's shard and the statistics are
+    // those of the whole set: plain sums are added in rank order, max / min combined, the radix
+    // select works on the all-reduced histogram
+    const int R = ctx->n_ranks;
+    UTIL_TRY(acm_rank_gather_to_host(ctx, 5));
+    double cnt = h[0], sum = h[1], sumsq = h[2], mx = h[3], mn = -h[4];
+    for (int r = 1; r < R; ++r) {
+        const double* v = h + 5 * r;
+        cnt += v[0]; sum += v[1]; sumsq += v[2]; mx = fmax(mx, v[3]); mn = fmin(mn, -v[4]);
+    }
     if (cnt == 0.0) { cleanup(); return acm_fail(ctx, ACM_ERR_ZERO_PROJECTION_POINTS, "No valid projections"); }
-    // d_reduce[0..2] still hold count/sum: pass 2 reads the mean from there, writes to d_reduce+8
-    reproj_pass2_kernel<<<grid, 256, 0, ctx->stream>>>(d_E, n, ctx->d_reduce, ctx->d_partials, ctx->d_reduce + 8, ctx->d_ticket);
+    const double mean = sum / cnt;
+    reproj_pass2_kernel<<<grid, 256, 0, ctx->stream>>>(d_E, n, mean, ctx->d_partials, ctx->d_reduce, ctx->d_ticket);
     ctx->launches++;
+    UTIL_TRY(acm_rank_gather_to_host(ctx, 1));
+    double ssd = h[0];
+    for (int r = 1; r < R; ++r) ssd += h[r];
     const unsigned long long m = (unsigned long long)cnt;
     UTIL_TRY(select_kth(ctx, d_E, n, m / 2, d_sel, h + 16));
     if (m % 2 == 0) UTIL_TRY(select_kth(ctx, d_E, n, m / 2 - 1, d_sel, h + 17));
-    e = cudaMemcpyAsync(h + 8, ctx->d_reduce + 8, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { cleanup(); return acm_fail(ctx, ACM_ERR_CUDA, "reprojection_error: %s", cudaGetErrorString(e)); }
 #undef UTIL_TRY
     out->count = m;
-    out->mean = sum / cnt;
-    out->stddev = sqrt(h[8] / cnt);
+    out->mean = mean;
+    out->stddev = sqrt(ssd / cnt);
     out->rmse = sqrt(sumsq / cnt);
     out->min = mn; out->max = mx;
     out->median = (m % 2 == 0) ? (h[17] + h[16]) / 2.0 : h[16];
@@ -176,14 +188,14 @@ extern "C" int32_t acm_reprojection_error(acm_ctx* ctx, const acm_camera* cam, c
 // sample_points (reference src/util/point_sampling.rs:46-120)
 // =======================================================================================
 template <int M>
-__global__ void __launch_bounds__(256) sample_unproject_kernel(const __grid_constant__ CamParams c, int ncx, size_t total, double cell_w,
-                                                               double cell_h, double* __restrict__ RX, double* __restrict__ RY,
-                                                               double* __restrict__ RZ, uint8_t* __restrict__ keep,
+__global__ void __launch_bounds__(256) sample_unproject_kernel(const __grid_constant__ CamParams c, int ncx, size_t first, size_t total,
+                                                               double cell_w, double cell_h, double* __restrict__ RX,
+                                                               double* __restrict__ RY, double* __restrict__ RZ, uint8_t* __restrict__ keep,
                                                                unsigned int* __restrict__ block_counts) {
-    const size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x;
+    const size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x;  // local cell; `first + idx` is its row-major grid index
     int k = 0;
     if (idx < total) {
-        const size_t i = idx / (size_t)ncx, j = idx % (size_t)ncx;
+        const size_t i = (first + idx) / (size_t)ncx, j = (first + idx) % (size_t)ncx;
         const double x = ((double)j + 0.5) * cell_w, y = ((double)i + 0.5) * cell_h;
         double rx, ry, rz;
         int st = CamModel<M>::unproject(c, x, y, rx, ry, rz);
@@ -221,7 +233,7 @@ __global__ void __launch_bounds__(1024) scan_block_counts_kernel(unsigned int* _
     if (threadIdx.x == 0) *total = carry;
 }
 
-__global__ void __launch_bounds__(256) sample_scatter_kernel(int ncx, size_t total, double cell_w, double cell_h, const double* __restrict__ RX,
+__global__ void __launch_bounds__(256) sample_scatter_kernel(int ncx, size_t first, size_t total, double cell_w, double cell_h, const double* __restrict__ RX,
                                                              const double* __restrict__ RY, const double* __restrict__ RZ,
                                                              const uint8_t* __restrict__ keep, const unsigned long long* __restrict__ offsets,
                                                              double* __restrict__ OU, double* __restrict__ OV, double* __restrict__ OX,
@@ -237,7 +249,7 @@ __global__ void __launch_bounds__(256) sample_scatter_kernel(int ncx, size_t tot
     for (int w = 0; w < warp; ++w) before += warp_cnt[w];
     if (k) {
         const size_t pos = (size_t)offsets[blockIdx.x] + before + __popc(ballot & ((1u << lane) - 1u));
-        const size_t i = idx / (size_t)ncx, j = idx % (size_t)ncx;
+        const size_t i = (first + idx) / (size_t)ncx, j = (first + idx) % (size_t)ncx;
         OU[pos] = ((double)j + 0.5) * cell_w; OV[pos] = ((double)i + 0.5) * cell_h;
         OX[pos] = RX[idx]; OY[pos] = RY[idx]; OZ[pos] = RZ[idx];
     }
@@ -245,9 +257,15 @@ __global__ void __launch_bounds__(256) sample_scatter_kernel(int ncx, size_t tot
 
 extern "C" int32_t acm_sample_points(acm_ctx* ctx, const acm_camera* cam, size_t n_requested, acm_points** uv_out, acm_points** xyz_out,
                                      size_t* n_kept) {
+    return acm_sample_points_shard(ctx, cam, n_requested, 0, 1, uv_out, xyz_out, n_kept);
+}
+
+extern "C" int32_t acm_sample_points_shard(acm_ctx* ctx, const acm_camera* cam, size_t n_requested, int32_t shard, int32_t n_shards,
+                                           acm_points** uv_out, acm_points** xyz_out, size_t* n_kept) {
     if (!ctx || !uv_out || !xyz_out || !n_kept) return ACM_ERR_INVALID_ARG;
     *uv_out = nullptr; *xyz_out = nullptr; *n_kept = 0;
     ACM_REQUIRE(ctx, cam && cam->width > 0 && cam->height > 0, "sample_points: camera resolution must be set");
+    ACM_REQUIRE(ctx, n_shards >= 1 && shard >= 0 && shard < n_shards, "sample_points: shard index out of range");
     CamParams c;
     int32_t rc = acm_make_cam_params(ctx, cam, &c);
     if (rc) return rc;
@@ -255,7 +273,11 @@ extern "C" int32_t acm_sample_points(acm_ctx* ctx, const acm_camera* cam, size_t
     const double width = (double)cam->width, height = (double)cam->height;
     const int ncx = (int)round(sqrt((double)n_requested * (width / height)));
     const int ncy = (int)round(sqrt((double)n_requested * (height / width)));
-    const size_t total = (size_t)((long long)ncx * (long long)ncy);
+    const size_t cells = (size_t)((long long)ncx * (long long)ncy);
+    // shard s owns the contiguous row-major cell range [s*cells/S, (s+1)*cells/S): concatenating the
+    // shards in order gives exactly the single-shard output
+    const size_t first = (size_t)(((unsigned __int128)cells * (unsigned)shard) / (unsigned)n_shards);
+    const size_t total = (size_t)(((unsigned __int128)cells * (unsigned)(shard + 1)) / (unsigned)n_shards) - first;
     const double cell_w = width / (double)ncx, cell_h = height / (double)ncy;
     acm_points *uvp = nullptr, *xyzp = nullptr;
     rc = acm_points_create(ctx, 2, total, ACM_F64, &uvp);
@@ -277,11 +299,11 @@ extern "C" int32_t acm_sample_points(acm_ctx* ctx, const acm_camera* cam, size_t
         unsigned long long* d_off = reinterpret_cast<unsigned long long*>(base + 3 * ray_bytes + keep_bytes + cnt_bytes);
         auto run = [&]() -> int32_t {
             ACM_DISPATCH_MODEL(cam->model, (sample_unproject_kernel<M><<<(unsigned)nblk, 256, 0, ctx->stream>>>(
-                c, ncx, total, cell_w, cell_h, RX, RY, RZ, d_keep, d_cnt)))
+                c, ncx, first, total, cell_w, cell_h, RX, RY, RZ, d_keep, d_cnt)))
             ACM_CHECK_LAUNCH(ctx);
             scan_block_counts_kernel<<<1, 1024, 0, ctx->stream>>>(d_cnt, nblk, d_off, d_off + nblk);
             ACM_CHECK_LAUNCH(ctx);
-            sample_scatter_kernel<<<(unsigned)nblk, 256, 0, ctx->stream>>>(ncx, total, cell_w, cell_h, RX, RY, RZ, d_keep, d_off,
+            sample_scatter_kernel<<<(unsigned)nblk, 256, 0, ctx->stream>>>(ncx, first, total, cell_w, cell_h, RX, RY, RZ, d_keep, d_off,
                                                                           comp<double>(uvp, 0), comp<double>(uvp, 1), comp<double>(xyzp, 0),
                                                                           comp<double>(xyzp, 1), comp<double>(xyzp, 2));
             ACM_CHECK_LAUNCH(ctx);
@@ -538,17 +560,8 @@ extern "C" int32_t acm_linear_estimation(acm_ctx* ctx, acm_camera* cam, const ac
     // host adds the slots in rank order (n_plain leading plain sums, then (hi, lo) pairs).
     auto fetch = [&](int count, int n_plain) -> int32_t {
         const int R = ctx->n_ranks;
-        if (R > 1) {
-            if ((size_t)R * count > 1024) return acm_fail(ctx, ACM_ERR_INVALID_ARG, "too many ranks for the gather buffer");
-            double* d_g = ctx->d_reduce;  // [R][count] lives after the first `count` doubles
-            ACM_CUDA(ctx, cudaMemcpyAsync(ctx->d_partials, ctx->d_reduce, count * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-            ACM_CUDA(ctx, cudaMemsetAsync(d_g, 0, (size_t)R * count * sizeof(double), ctx->stream));
-            ACM_CUDA(ctx, cudaMemcpyAsync(d_g + (size_t)ctx->rank * count, ctx->d_partials, count * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-            int32_t r2 = acm_allreduce_sum_f64(ctx, d_g, (size_t)R * count);
-            if (r2) return r2;
-        }
-        ACM_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_reduce, (size_t)R * count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        ACM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        int32_t r2 = acm_rank_gather_to_host(ctx, count);
+        if (r2) return r2;
         for (int r = 1; r < R; ++r) {
             const double* v = h + (size_t)r * count;
             for (int i = 0; i < n_plain; ++i) h[i] += v[i];

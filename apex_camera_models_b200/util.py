@@ -79,14 +79,18 @@ def undistort_map(camera_model: CameraModel, target_intrinsics: Intrinsics | Non
     return out
 
 
-def sample_points(camera_model: CameraModel, n: int, device: bool = False):
-    """`sample_points(Some(&model), n) -> (Matrix2xX, Matrix3xX)`: (points_2d, points_3d)."""
+def sample_points(camera_model: CameraModel, n: int, device: bool = False, shard: tuple[int, int] | None = None):
+    """`sample_points(Some(&model), n) -> (Matrix2xX, Matrix3xX)`: (points_2d, points_3d).
+
+    `shard=(rank, world)` returns that rank's contiguous slice of the grid (one slice per GPU; the
+    slices concatenated in rank order are the unsharded result)."""
     if camera_model is None:
         raise UtilError("Camera model does not exist")  # the reference panics on None (point_sampling.rs:53)
     ctx = camera_model.ctx
     cam = camera_model.camera_block()
     uv_h, xyz_h, kept = C.c_void_p(), C.c_void_p(), C.c_size_t()
-    ctx.check(_lib.acm_sample_points(ctx.handle, C.byref(cam), n, C.byref(uv_h), C.byref(xyz_h), C.byref(kept)))
+    rank, world = shard if shard is not None else (0, 1)
+    ctx.check(_lib.acm_sample_points_shard(ctx.handle, C.byref(cam), n, rank, world, C.byref(uv_h), C.byref(xyz_h), C.byref(kept)))
     uv = Points(ctx, 2, kept.value, _handle=uv_h)
     xyz = Points(ctx, 3, kept.value, _handle=xyz_h)
     if device:

@@ -216,6 +216,9 @@ typedef struct acm_projection_error {
     double rmse, min, max, mean, stddev, median;
     uint64_t count;
 } acm_projection_error;
+/* With a communicator attached (acm_comm_init_rank) xyz / uv are this rank's shard and the
+ * statistics are those of the whole set, identical on every rank: sums added in rank order, the
+ * median by a radix select over the all-reduced histogram (an empty shard is allowed). */
 int32_t acm_reprojection_error(acm_ctx* ctx, const acm_camera* cam, const acm_points* xyz, const acm_points* uv,
                                acm_projection_error* out);
 
@@ -223,6 +226,12 @@ int32_t acm_reprojection_error(acm_ctx* ctx, const acm_camera* cam, const acm_po
  * unproject -> keep Ok && z > 0, order preserved.  Creates two point buffers of *n_kept points. */
 int32_t acm_sample_points(acm_ctx* ctx, const acm_camera* cam, size_t n_requested, acm_points** uv_out,
                           acm_points** xyz_out, size_t* n_kept);
+/* The same for one of n_shards contiguous row-major slices of the grid (one per GPU): shard s
+ * unprojects cells [s*C/n_shards, (s+1)*C/n_shards) of the C = ncx*ncy grid cells, so the shards'
+ * outputs concatenated in order are bit-for-bit acm_sample_points' output.  No collective: the
+ * kept counts (*n_kept is this shard's) are all the host has to exchange. */
+int32_t acm_sample_points_shard(acm_ctx* ctx, const acm_camera* cam, size_t n_requested, int32_t shard, int32_t n_shards,
+                                acm_points** uv_out, acm_points** xyz_out, size_t* n_kept);
 
 /* ---- deterministic synthetic inputs, generated in HBM ------------ */
 int32_t acm_synth_points3(acm_ctx* ctx, uint64_t seed, size_t first_index, double cos_theta_max, int32_t adversarial, acm_points* xyz);

@@ -297,9 +297,10 @@ inline acm_projection_error compute_reprojection_error(const CameraModel& m, con
 }
 
 // util::sample_points (point_sampling.rs:46-120): returns (points_2d, points_3d) in nalgebra memory order
-inline std::pair<std::vector<double>, std::vector<double>> sample_points(const CameraModel& m, size_t n) {
+// (shard, n_shards): that contiguous slice of the grid, one per GPU
+inline std::pair<std::vector<double>, std::vector<double>> sample_points(const CameraModel& m, size_t n, int shard = 0, int n_shards = 1) {
     acm_camera c = m.block(); acm_points *uv = nullptr, *xyz = nullptr; size_t kept = 0;
-    m.ctx().check(acm_sample_points(m.ctx().handle(), &c, n, &uv, &xyz, &kept));
+    m.ctx().check(acm_sample_points_shard(m.ctx().handle(), &c, n, shard, n_shards, &uv, &xyz, &kept));
     Points U(m.ctx(), uv), X(m.ctx(), xyz);
     return {U.download(), X.download()};
 }

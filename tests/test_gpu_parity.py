@@ -6,6 +6,7 @@ Bars (BASELINE.json north_star): status masks, kept sets, remap indices and outp
 bit-exact; f64 values within 1e-9 relative; the f32-I/O path within 1e-4 px (or half an f32 ulp
 of the coordinate where that is larger).
 """
+import os
 import ctypes as C
 
 import numpy as np
@@ -685,3 +686,20 @@ def test_full_size_round_trip_and_linearity(acm, ctx, O, cameras):
     assert nvs == nv
     assert np.allclose(Hs, H, rtol=1e-12) and np.allclose(gs, g, rtol=1e-9, atol=1e-9 * np.abs(g).max()) and np.isclose(cs, c, rtol=1e-12)
     ctx.device_free(st); X.free(); UV.free()
+
+
+@pytest.mark.gpu
+def test_multi_gpu_converter_pipeline_matches_single_gpu():
+    """sample_points(shard) -> linear_estimation -> LM -> reprojection statistics on 2 GPUs (NCCL and
+    fused NVLink exchange) against the same pipeline on one GPU; needs two visible GPUs."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, ACM_CHECK_POINTS="200000")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(root, "scripts", "multi_gpu_check.py")], capture_output=True, text=True,
+                       timeout=600, env=env, cwd=root)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
