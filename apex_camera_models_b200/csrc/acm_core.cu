@@ -69,10 +69,10 @@ extern "C" int32_t acm_ctx_create(int32_t device, void* cuda_stream, acm_ctx** o
     CREATE_CUDA(cudaEventCreate(&ctx->t0));
     CREATE_CUDA(cudaEventCreate(&ctx->t1));
     for (int i = 0; i < 4; ++i) CREATE_CUDA(cudaEventCreateWithFlags(&ctx->chunk_ev[i], cudaEventDisableTiming));
-    CREATE_CUDA(cudaMalloc(&ctx->d_reduce, 1024 * sizeof(double)));
+    CREATE_CUDA(cudaMalloc(&ctx->d_reduce, 2048 * sizeof(double)));
     CREATE_CUDA(cudaMalloc(&ctx->d_ticket, 64 * sizeof(unsigned int)));
     CREATE_CUDA(cudaMemset(ctx->d_ticket, 0, 64 * sizeof(unsigned int)));
-    CREATE_CUDA(cudaMallocHost(&ctx->h_reduce, 1024 * sizeof(double)));
+    CREATE_CUDA(cudaMallocHost(&ctx->h_reduce, 2048 * sizeof(double)));
     CREATE_CUDA(cudaMalloc(&ctx->d_lm, 4096));
     CREATE_CUDA(cudaMemset(ctx->d_lm, 0, 4096));
     CREATE_CUDA(cudaMallocHost(&ctx->h_lm, 4096));

@@ -51,9 +51,9 @@ struct acm_ctx {
     // scratch owned by the context
     double* d_partials;     // per-block partial sums of the reduction kernels
     size_t partials_cap;    // in doubles
-    double* d_reduce;       // final reduced vector (<= 1024 doubles)
+    double* d_reduce;       // final reduced vector (2048 doubles; gathers use the first 1024)
     unsigned int* d_ticket; // last-block-done counters
-    double* h_reduce;       // pinned mirror of d_reduce
+    double* h_reduce;       // pinned mirror of d_reduce (2048 doubles)
     void* d_lm;             // LmState
     void* h_lm;             // pinned mirror
     void* d_stage[2];       // staging for host pipelines

@@ -421,49 +421,160 @@ __global__ void __launch_bounds__(256) linest_radtan_kernel(double fx, double fy
 }
 
 // --- FOV: grid search over w = i/100, i in [10, 300) (fov.rs:175-228) ----------------------------
-// blockIdx.y = candidate w; the points are swept once per candidate (L2 resident for the sizes the
-// converter uses).  out[2*iw] = error sum, out[2*iw+1] = finite count.
-__global__ void __launch_bounds__(256) linest_fov_kernel(double fx, double fy, double cx, double cy, const double* __restrict__ tan_half,
-                                                         const double* __restrict__ X, const double* __restrict__ Y, const double* __restrict__ Z,
-                                                         const double* __restrict__ U, const double* __restrict__ V, size_t n,
-                                                         double* __restrict__ block_out) {
-    const int iw = blockIdx.y;
-    const double w = (double)(iw + 10) / 100.0;
-    const double t = tan_half[iw];
-    double sum = 0.0, cnt = 0.0;
+// Two stages for large inputs (290 x N atan2 evaluations in f64 cost 20 ms at N = 10 M):
+//   1. `linest_fov_prefilter_kernel`: every candidate in float with cheap branch-free math; its mean
+//      errors, together with a rounding bound, shortlist the candidates that can still be the arg-min;
+//   2. `linest_fov_exact_kernel`: the reference arithmetic in f64 on the shortlist (or on all 290
+//      candidates for small inputs / whenever stage 1 saw a non-finite value).
+// Both carry C candidates per thread so that the points are swept 290 / C times, not 290 times.
+// block_out[(slot * gridDim.x + block) * 3 + {0: error sum, 1: finite count, 2: sum |u-cx| + |v-cy|}].
+constexpr int FOV_NV = 3;
+
+// exact stage: `cand` (nullptr = identity) lists indices iw into the w grid; blockIdx.y = group of C
+// consecutive list entries (the tail repeats the last one and is not stored)
+template <int C>
+__global__ void __launch_bounds__(256) linest_fov_exact_kernel(double fx, double fy, double cx, double cy, const double* __restrict__ tan_half,
+                                                               const int* __restrict__ cand, int n_cand, const double* __restrict__ X,
+                                                               const double* __restrict__ Y, const double* __restrict__ Z,
+                                                               const double* __restrict__ U, const double* __restrict__ V, size_t n,
+                                                               double* __restrict__ block_out) {
+    double t[C], w[C], sum[C], cnt[C];
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+        const int slot = min((int)blockIdx.y * C + k, n_cand - 1);
+        const int iw = cand ? cand[slot] : slot;
+        w[k] = (double)(iw + 10) / 100.0;
+        t[k] = tan_half[iw];
+        sum[k] = cnt[k] = 0.0;
+    }
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        double x = X[i], y = Y[i], z = Z[i];
-        double r2 = x * x + y * y, r = sqrt(r2);
-        double a = (z > 0.0 && r >= 0.0) ? acm_atan2_q1(2.0 * t * r, z) : atan2(2.0 * t * r, z);  // the grid search has no z guard
-        double rd = (r2 < ACM_SQRT_EPS) ? 2.0 * t / w : a / (r * w);
-        double mx = x * rd, my = y * rd;
-        double up = fx * mx + cx, vp = fy * my + cy;
-        double du = up - U[i], dv = vp - V[i];
-        double e = sqrt(du * du + dv * dv);
-        if (isfinite(e)) { sum += e; cnt += 1.0; }
+        const double x = X[i], y = Y[i], z = Z[i], u = U[i], v = V[i];
+        const double r2 = x * x + y * y, r = sqrt(r2);
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            double a = (z > 0.0 && r >= 0.0) ? acm_atan2_q1(2.0 * t[k] * r, z) : atan2(2.0 * t[k] * r, z);  // the grid search has no z guard
+            double rd = (r2 < ACM_SQRT_EPS) ? 2.0 * t[k] / w[k] : a / (r * w[k]);
+            double mx = x * rd, my = y * rd;
+            double up = fx * mx + cx, vp = fy * my + cy;
+            double du = up - u, dv = vp - v;
+            double e = sqrt(du * du + dv * dv);
+            if (isfinite(e)) { sum[k] += e; cnt[k] += 1.0; }
+        }
     }
-    __shared__ double sm[2][8];
+    __shared__ double sm[2][C][8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { sum += __shfl_down_sync(0xffffffffu, sum, o); cnt += __shfl_down_sync(0xffffffffu, cnt, o); }
-    if (lane == 0) { sm[0][warp] = sum; sm[1][warp] = cnt; }
+    for (int k = 0; k < C; ++k) {
+        double s_ = sum[k], c_ = cnt[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { s_ += __shfl_down_sync(0xffffffffu, s_, o); c_ += __shfl_down_sync(0xffffffffu, c_, o); }
+        if (lane == 0) { sm[0][k][warp] = s_; sm[1][k][warp] = c_; }
+    }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double s = 0.0, c = 0.0;
-        for (int k = 0; k < 8; ++k) { s += sm[0][k]; c += sm[1][k]; }
-        block_out[((size_t)iw * gridDim.x + blockIdx.x) * 2] = s;
-        block_out[((size_t)iw * gridDim.x + blockIdx.x) * 2 + 1] = c;
+    if (threadIdx.x < 2 * C) {
+        const int which = threadIdx.x / C, k = threadIdx.x % C;
+        const int slot = blockIdx.y * C + k;
+        if (slot < n_cand) {
+            double acc = 0.0;
+            for (int q = 0; q < 8; ++q) acc += sm[which][k][q];
+            block_out[((size_t)slot * gridDim.x + blockIdx.x) * FOV_NV + which] = acc;
+        }
+    }
+}
+
+// float pre-filter: candidates blockIdx.y * C .. + C of the full grid.  Non-finite errors are added
+// unconditionally, so they surface as a non-finite sum (the host then falls back to the exact search).
+// Per evaluation: branch-free atan2 (degree-7 polynomial in q^2 on [0, 1], 1.7e-7 absolute), MUFU
+// reciprocal / rsqrt; everything that does not depend on the candidate is hoisted.  Float partial sums
+// are flushed into doubles every 16 points, which bounds the accumulation error by 8 ulp.
+template <int C>
+__global__ void __launch_bounds__(256, 2) linest_fov_prefilter_kernel(double fx_, double fy_, double cx_, double cy_,
+                                                                      const double* __restrict__ tan_half, const double* __restrict__ X,
+                                                                      const double* __restrict__ Y, const double* __restrict__ Z,
+                                                                      const double* __restrict__ U, const double* __restrict__ V, size_t n,
+                                                                      double* __restrict__ block_out) {
+    float T2[C], inv_w[C], sum[C];
+    double dsum[C];
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+        const int iw = blockIdx.y * C + k;
+        T2[k] = (float)(2.0 * tan_half[iw]);
+        inv_w[k] = (float)(100.0 / (double)(iw + 10));
+        sum[k] = 0.0f; dsum[k] = 0.0;
+    }
+    float mag = 0.0f;
+    double dmag = 0.0, dcnt = 0.0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    int since_flush = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double xd = X[i], yd = Y[i], zd = Z[i], ud = U[i], vd = V[i];
+        const float x = (float)xd, y = (float)yd, z = (float)zd;
+        const float cxu = (float)(cx_ - ud), cyv = (float)(cy_ - vd);  // centred in f64 first
+        const float r2 = x * x + y * y;
+        const bool small = r2 < (float)ACM_SQRT_EPS;
+        const float r = sqrtf(r2);
+        const float inv_r = small ? 1.0f : __fdividef(1.0f, r);
+        const float gx = (float)fx_ * x * inv_r, gy = (float)fy_ * y * inv_r;
+        const float az = fabsf(z);
+        mag += fabsf(cxu) + fabsf(cyv);
+        dcnt += 1.0;
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            const float yv = T2[k] * r;                      // >= 0
+            const float mx = fmaxf(az, yv), mn = fminf(az, yv);
+            const float q = __fdividef(mn, mx);               // NaN for 0/0 -> reported as non-finite
+            const float s2 = q * q;
+            float p = -4.668773307e-03f;
+            p = fmaf(p, s2, 2.416618952e-02f);
+            p = fmaf(p, s2, -5.936710079e-02f);
+            p = fmaf(p, s2, 9.906096896e-02f);
+            p = fmaf(p, s2, -1.401658504e-01f);
+            p = fmaf(p, s2, 1.996923539e-01f);
+            p = fmaf(p, s2, -3.333195972e-01f);
+            p = fmaf(p, s2, 9.999998978e-01f);
+            float a = p * q;
+            a = (yv > az) ? 1.5707963267948966f - a : a;
+            a = (z < 0.0f) ? 3.14159265358979f - a : a;
+            const float ak = (small ? T2[k] : a) * inv_w[k];   // r2 < sqrt(EPS): rd = 2 t / w (fov.rs:205)
+            const float du = fmaf(gx, ak, cxu), dv = fmaf(gy, ak, cyv);
+            const float d2 = fmaf(du, du, dv * dv);
+            const float e = d2 > 0.0f ? d2 * rsqrtf(d2) : d2;  // 0 stays 0, NaN stays NaN, inf -> NaN
+            sum[k] += e;
+        }
+        if (++since_flush == 16) {
+            since_flush = 0;
+#pragma unroll
+            for (int k = 0; k < C; ++k) { dsum[k] += (double)sum[k]; sum[k] = 0.0f; }
+            dmag += (double)mag; mag = 0.0f;
+        }
+    }
+    __shared__ double sm[C + 2][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < C + 2; ++k) {
+        double s_ = k < C ? dsum[k < C ? k : 0] + (double)sum[k < C ? k : 0] : (k == C ? dcnt : dmag + (double)mag);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s_ += __shfl_down_sync(0xffffffffu, s_, o);
+        if (lane == 0) sm[k][warp] = s_;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3 * C) {
+        const int which = threadIdx.x / C, k = threadIdx.x % C;
+        const int row = which == 0 ? k : (which == 1 ? C : C + 1);
+        double acc = 0.0;
+        for (int q = 0; q < 8; ++q) acc += sm[row][q];
+        block_out[((size_t)(blockIdx.y * C + k) * gridDim.x + blockIdx.x) * FOV_NV + which] = acc;
     }
 }
 
 // sums the per-block (sum, count) pairs of every candidate in block order
 __global__ void linest_fov_sum_kernel(const double* __restrict__ block_out, int gx, int nvals, double* __restrict__ out) {
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;  // v = 2*iw + {0,1}
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;  // v = 3*slot + {0,1,2}
     if (v >= nvals) return;
-    const int iw = v >> 1, which = v & 1;
+    const int slot = v / 3, which = v % 3;
     double s = 0.0;
-    for (int b = 0; b < gx; ++b) s += block_out[((size_t)iw * gx + b) * 2 + which];
+    for (int b = 0; b < gx; ++b) s += block_out[((size_t)slot * gx + b) * 3 + which];
     out[v] = s;
 }
 
@@ -631,39 +742,101 @@ extern "C" int32_t acm_linear_estimation(acm_ctx* ctx, acm_camera* cam, const ac
         }
         case ACM_MODEL_FOV: {
             if (n < 2) return acm_fail(ctx, ACM_ERR_INVALID_PARAMS, "Need at least 2 point correspondences for linear estimation");
-            const int NW = 290;
+            constexpr int NW = 290, C32 = 10, C64 = 2, MAX_SHORT = 32;
+            static_assert(NW % C32 == 0, "the pre-filter has no tail group");
             int gx = grid_for(ctx, n, 256, 1);
             if (gx > 64) gx = 64;
-            double* d_tan = nullptr; double* d_blk = nullptr;
-            ACM_CUDA(ctx, cudaMalloc(&d_tan, NW * sizeof(double)));
-            if (cudaMalloc(&d_blk, (size_t)NW * gx * 2 * sizeof(double)) != cudaSuccess) { cudaFree(d_tan); return acm_fail(ctx, ACM_ERR_CUDA, "cudaMalloc failed"); }
-            double h_tan[NW];
+            const int gx_short = grid_for(ctx, n, 256, 4);  // the shortlist has few groups: more blocks along the points
+            // arena: tan table | candidate list | per-block (sum, count, magnitude) of every candidate
+            const size_t tan_bytes = 2560, cand_bytes = 1280;
+            const size_t blk_doubles = (size_t)FOV_NV * ((size_t)NW * gx > (size_t)MAX_SHORT * gx_short ? (size_t)NW * gx : (size_t)MAX_SHORT * gx_short);
+            rc = acm_ensure_scratch(ctx, tan_bytes + cand_bytes + blk_doubles * sizeof(double));
+            if (rc) return rc;
+            double* d_tan = static_cast<double*>(ctx->d_scratch);
+            int* d_cand = reinterpret_cast<int*>(static_cast<char*>(ctx->d_scratch) + tan_bytes);
+            double* d_blk = reinterpret_cast<double*>(static_cast<char*>(ctx->d_scratch) + tan_bytes + cand_bytes);
+            double* h_tan = h + 1024;  // pinned (2048 doubles); h[0 .. 870) receives the reduced sums
+            int* h_cand = reinterpret_cast<int*>(h + 1024 + 320);
             for (int i = 0; i < NW; ++i) h_tan[i] = tan(((double)(i + 10) / 100.0) / 2.0);  // host libm, as the reference
-            cudaError_t e = cudaMemcpyAsync(d_tan, h_tan, NW * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
-            if (e == cudaSuccess) {
-                linest_fov_kernel<<<dim3(gx, NW), 256, 0, ctx->stream>>>(fx, fy, cx, cy, d_tan, X, Y, Z, U, V, n, d_blk);
-                ctx->launches++;
-                e = cudaGetLastError();
+            ACM_CUDA(ctx, cudaMemcpyAsync(d_tan, h_tan, NW * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            // reduced (error sum, finite count, magnitude sum) of `n_cand` candidates -> h[3*slot + {0,1,2}]
+            auto evaluate = [&](bool f32, const int* cand_dev, int n_cand) -> int32_t {
+                int g = gx;
+                if (f32) {
+                    linest_fov_prefilter_kernel<C32><<<dim3(gx, NW / C32), 256, 0, ctx->stream>>>(fx, fy, cx, cy, d_tan, X, Y, Z, U, V, n, d_blk);
+                } else {
+                    if (n_cand <= MAX_SHORT) g = gx_short;
+                    linest_fov_exact_kernel<C64><<<dim3(g, (n_cand + C64 - 1) / C64), 256, 0, ctx->stream>>>(
+                        fx, fy, cx, cy, d_tan, cand_dev, n_cand, X, Y, Z, U, V, n, d_blk);
+                }
+                ACM_CHECK_LAUNCH(ctx);
+                linest_fov_sum_kernel<<<(3 * n_cand + 255) / 256, 256, 0, ctx->stream>>>(d_blk, g, 3 * n_cand, ctx->d_reduce);
+                ACM_CHECK_LAUNCH(ctx);
+                int32_t r2 = acm_allreduce_sum_f64(ctx, ctx->d_reduce, 3 * (size_t)n_cand);
+                if (r2) return r2;
+                ACM_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_reduce, 3 * (size_t)n_cand * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+                ACM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                return ACM_OK;
+            };
+            // Stage 1 (large inputs only): float pre-filter over all 290 candidates.  A candidate stays
+            // on the shortlist when its float mean minus its rounding bound does not exceed the
+            // smallest (float mean + bound).  Any non-finite float error, an empty or an oversized
+            // shortlist falls back to the exact search over every candidate.  The decision uses
+            // all-reduced sums, so every rank takes the same path.
+            int n_short = 0;
+            double n_total = (double)n;
+            if (ctx->n_ranks > 1 || n >= 200000) {
+                // the pre-filter is only worth its extra launches on large inputs; the global size decides
+                // so that all ranks agree
+                h[0] = (double)n;
+                if (ctx->n_ranks > 1) {
+                    ACM_CUDA(ctx, cudaMemcpyAsync(ctx->d_reduce, h, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+                    rc = acm_allreduce_sum_f64(ctx, ctx->d_reduce, 1);
+                    if (rc) return rc;
+                    ACM_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_reduce, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+                    ACM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                }
+                n_total = h[0];
             }
-            if (e == cudaSuccess) {
-                linest_fov_sum_kernel<<<(2 * NW + 255) / 256, 256, 0, ctx->stream>>>(d_blk, gx, 2 * NW, ctx->d_reduce);
-                ctx->launches++;
-                e = cudaGetLastError();
+            if (n_total >= 200000.0) {
+                rc = evaluate(true, nullptr, NW);
+                if (rc) return rc;
+                bool usable = true;
+                double lo[NW], best_hi = INFINITY;
+                for (int i = 0; i < NW && usable; ++i) {
+                    const double s_ = h[3 * i], cnt = h[3 * i + 1], mg = h[3 * i + 2];
+                    if (cnt != n_total || !isfinite(s_) || !isfinite(mg)) { usable = false; break; }
+                    // float error of one evaluation: <= ~17 ulp of (|u-cx| + |v-cy|) + ~20 ulp of e, the flushed
+                    // accumulation adds <= 8 ulp of the sum; 64 ulp of both leaves a factor 2-3 of margin
+                    const double mean = s_ / cnt, bound = 64.0 * 5.9604644775390625e-08 * (mg / cnt + mean);
+                    lo[i] = mean - bound;
+                    if (mean + bound < best_hi) best_hi = mean + bound;
+                }
+                if (usable) {
+                    for (int i = 0; i < NW; ++i)
+                        if (lo[i] <= best_hi) { if (n_short < MAX_SHORT) h_cand[n_short] = i; ++n_short; }
+                    if (n_short == 0 || n_short > MAX_SHORT) n_short = 0;
+                }
             }
-            int32_t rc2 = ACM_OK;
-            if (e == cudaSuccess) rc2 = acm_allreduce_sum_f64(ctx, ctx->d_reduce, 2 * NW);
-            if (e == cudaSuccess && !rc2) e = cudaMemcpyAsync(h, ctx->d_reduce, 2 * NW * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream); else cudaStreamSynchronize(ctx->stream);
             double best_w = 1.0, best_err = INFINITY;
-            if (e == cudaSuccess && !rc2) {
+            if (n_short > 0) {
+                ACM_CUDA(ctx, cudaMemcpyAsync(d_cand, h_cand, n_short * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+                int short_list[MAX_SHORT];
+                memcpy(short_list, h_cand, n_short * sizeof(int));
+                rc = evaluate(false, d_cand, n_short);
+                if (rc) return rc;
+                for (int k = 0; k < n_short; ++k) {  // ascending candidate order, first strict minimum wins (fov.rs:218-221)
+                    const double s_ = h[3 * k], cnt = h[3 * k + 1];
+                    if (cnt > 0.0) { double avg = s_ / cnt; if (avg < best_err) { best_err = avg; best_w = (double)(short_list[k] + 10) / 100.0; } }
+                }
+            } else {
+                rc = evaluate(false, nullptr, NW);
+                if (rc) return rc;
                 for (int i = 0; i < NW; ++i) {
-                    const double s_ = h[2 * i], cnt = h[2 * i + 1];
+                    const double s_ = h[3 * i], cnt = h[3 * i + 1];
                     if (cnt > 0.0) { double avg = s_ / cnt; if (avg < best_err) { best_err = avg; best_w = (double)(i + 10) / 100.0; } }
                 }
             }
-            cudaFree(d_tan); cudaFree(d_blk);
-            if (rc2) return rc2;
-            if (e != cudaSuccess) return acm_fail(ctx, ACM_ERR_CUDA, "fov linear_estimation: %s", cudaGetErrorString(e));
             double w = best_w;
             if (w <= 2.220446049250313e-16) w = 0.01; else if (w > 3.0) w = 3.0;
             cam->params[4] = w;

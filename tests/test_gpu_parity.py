@@ -456,6 +456,30 @@ def test_linear_estimation_matches_oracle(acm, ctx, O, cameras, name):
         assert abs(got[4] - load_golden("restated_kats.json")["lm_anchors_450"]["linear_alpha"]) < 1e-12
 
 
+@pytest.mark.parametrize("source", ["kannala_brandt", "fov_exact", "fov_with_nan"])
+def test_fov_grid_search_two_stage_matches_oracle(acm, ctx, O, cameras, source):
+    """Inputs above 200 k points take the float pre-filter + exact shortlist path of the FOV grid
+    search; the chosen w must be the oracle's (fov.rs:175-228 evaluates all 290 candidates)."""
+    n = 250_000
+    xyz = O.synth_points3(0xACE50009, 0, n, float(np.cos(np.deg2rad(80.0))), False)
+    if source == "kannala_brandt":
+        src = cameras["kannala_brandt"]
+    else:  # data generated by a FOV camera with w on the grid: the minimum is ~0 px, the bound must still hold
+        src = {"model_id": cameras["fov"]["model_id"], "params": cameras["kannala_brandt"]["params"][:4] + [0.93], "width": 512, "height": 512}
+    uv, st = O.project(oracle_model(O, src), xyz)
+    keep = st == 0
+    xyz, uv = np.ascontiguousarray(xyz[keep]), np.ascontiguousarray(uv[keep])
+    if source == "fov_with_nan":  # a non-finite error in the float stage forces the exact search over every candidate
+        uv[1234, 0] = np.nan
+    cam = {"model_id": cameras["fov"]["model_id"], "params": cameras["kannala_brandt"]["params"][:4] + [1.0], "width": 512, "height": 512}
+    m, om = gpu_model(acm, ctx, cam), oracle_model(O, cam)
+    m.linear_estimation(xyz, uv)
+    assert O.linear_estimation(om, xyz, uv) == 0
+    assert m.params()[4] == om.params()[4]
+    if source != "kannala_brandt":
+        assert m.params()[4] == 0.93
+
+
 def test_linear_estimation_rad_tan_and_errors(acm, ctx, O, cameras):
     """tests/parameter_estimation.rs: 50 sampled points -> Ok and non-zero k; n=2 -> Err; mismatch -> Err."""
     c = cameras["rad_tan"]
