@@ -53,6 +53,7 @@ extern "C" int32_t acm_ctx_create(int32_t device, void* cuda_stream, acm_ctx** o
     ctx->h_stage = nullptr; ctx->h_stage_cap = 0;
     ctx->cache3 = nullptr; ctx->cache2 = nullptr; ctx->cache_cap = 0;
     ctx->d_scratch = nullptr; ctx->scratch_cap = 0;
+    for (int i = 0; i < ACM_FREE_LIST; ++i) { ctx->free_ptr[i] = nullptr; ctx->free_bytes[i] = 0; }
     ctx->peer_local = nullptr; ctx->d_peer_ptrs = nullptr; ctx->peer_n = 0; ctx->peer_rank = 0; ctx->peer_seq = 0;
     for (int i = 0; i < ACM_MAX_PEERS; ++i) ctx->peer_mapped[i] = nullptr;
 #define CREATE_CUDA(call)                                                                                     \
@@ -81,6 +82,28 @@ extern "C" int32_t acm_ctx_create(int32_t device, void* cuda_stream, acm_ctx** o
     return ACM_OK;
 }
 
+static void acm_free_list_release(acm_ctx* ctx) {
+    for (int i = 0; i < ACM_FREE_LIST; ++i) {
+        if (ctx->free_ptr[i]) cudaFree(ctx->free_ptr[i]);
+        ctx->free_ptr[i] = nullptr; ctx->free_bytes[i] = 0;
+    }
+}
+
+int32_t acm_device_malloc(acm_ctx* ctx, void** out, size_t bytes) {
+    cudaError_t e = cudaMalloc(out, bytes ? bytes : 1);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        acm_free_list_release(ctx);
+        e = cudaMalloc(out, bytes ? bytes : 1);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *out = nullptr;
+        return acm_fail(ctx, ACM_ERR_CUDA, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    }
+    return ACM_OK;
+}
+
 extern "C" int32_t acm_ctx_destroy(acm_ctx* ctx) {
     if (!ctx) return ACM_OK;
     cudaSetDevice(ctx->device);
@@ -88,6 +111,7 @@ extern "C" int32_t acm_ctx_destroy(acm_ctx* ctx) {
     acm_comm_destroy(ctx);
     acm_peer_detach(ctx);
     acm_points_destroy(ctx, ctx->cache3); acm_points_destroy(ctx, ctx->cache2);
+    acm_free_list_release(ctx);
     cudaFree(ctx->peer_local);
     cudaFree(ctx->d_scratch);
     cudaFree(ctx->d_partials); cudaFree(ctx->d_reduce); cudaFree(ctx->d_ticket); cudaFreeHost(ctx->h_reduce);
@@ -258,7 +282,7 @@ int32_t acm_make_cam_params(acm_ctx* ctx, const acm_camera* cam, CamParams* c) {
 extern "C" int32_t acm_device_alloc(acm_ctx* ctx, size_t bytes, void** out) {
     if (!ctx || !out) return ACM_ERR_INVALID_ARG;
     ACM_CUDA(ctx, cudaSetDevice(ctx->device));
-    ACM_CUDA(ctx, cudaMalloc(out, bytes ? bytes : 1));
+    { int32_t rc = acm_device_malloc(ctx, out, bytes); if (rc) return rc; }
     return ACM_OK;
 }
 extern "C" int32_t acm_device_free(acm_ctx* ctx, void* p) {
@@ -323,7 +347,7 @@ int32_t acm_ensure_scratch(acm_ctx* ctx, size_t bytes) {
     ACM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(ctx->d_scratch); ctx->d_scratch = nullptr; ctx->scratch_cap = 0;
     const size_t want = bytes + bytes / 4;  // head room: the arena only ever grows
-    ACM_CUDA(ctx, cudaMalloc(&ctx->d_scratch, want));
+    { int32_t rc = acm_device_malloc(ctx, &ctx->d_scratch, want); if (rc) return rc; }
     ctx->scratch_cap = want;
     return ACM_OK;
 }
@@ -352,16 +376,49 @@ extern "C" int32_t acm_points_create(acm_ctx* ctx, int32_t dim, size_t n, int32_
     p->stride_bytes = ((n * es + 255) / 256) * 256;
     if (p->stride_bytes == 0) p->stride_bytes = 256;
     p->base = nullptr;
-    cudaError_t e = cudaSetDevice(ctx->device);
-    if (e == cudaSuccess) e = cudaMalloc(&p->base, p->stride_bytes * (size_t)dim);
-    if (e != cudaSuccess) { delete p; return acm_fail(ctx, ACM_ERR_CUDA, "cudaMalloc of %zu bytes failed: %s", p->stride_bytes * (size_t)dim, cudaGetErrorString(e)); }
+    const size_t need = p->stride_bytes * (size_t)dim;
+    // best fit from the free list: large enough, at most 50 % (+1 MiB) larger
+    int best = -1;
+    for (int i = 0; i < ACM_FREE_LIST; ++i)
+        if (ctx->free_ptr[i] && ctx->free_bytes[i] >= need && ctx->free_bytes[i] <= need + need / 2 + (1u << 20) &&
+            (best < 0 || ctx->free_bytes[i] < ctx->free_bytes[best]))
+            best = i;
+    if (best >= 0) {
+        p->base = ctx->free_ptr[best]; p->alloc_bytes = ctx->free_bytes[best];
+        ctx->free_ptr[best] = nullptr; ctx->free_bytes[best] = 0;
+    } else {
+        cudaError_t e = cudaSetDevice(ctx->device);
+        if (e != cudaSuccess) { delete p; return acm_fail(ctx, ACM_ERR_CUDA, "cudaSetDevice failed: %s", cudaGetErrorString(e)); }
+        int32_t rc = acm_device_malloc(ctx, &p->base, need);
+        if (rc) { delete p; return rc; }
+        p->alloc_bytes = need;
+    }
     *out = p;
     return ACM_OK;
 }
 
+// The buffer is idle once the compute stream has drained (uploads on the copy stream complete inside
+// the upload call), so it can be handed to the next acm_points_create without further ordering.
 extern "C" int32_t acm_points_destroy(acm_ctx* ctx, acm_points* p) {
     if (!p) return ACM_OK;
-    if (ctx) cudaStreamSynchronize(ctx->stream);
+    if (ctx) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamSynchronize(ctx->copy_stream);
+        // keep allocations up to 16 GiB each; a full list evicts its smallest entry
+        if (p->base && p->alloc_bytes <= ((size_t)16 << 30)) {
+            int slot = -1, smallest = 0;
+            for (int i = 0; i < ACM_FREE_LIST; ++i) {
+                if (!ctx->free_ptr[i]) { slot = i; break; }
+                if (ctx->free_bytes[i] < ctx->free_bytes[smallest]) smallest = i;
+            }
+            if (slot < 0 && ctx->free_bytes[smallest] < p->alloc_bytes) { cudaFree(ctx->free_ptr[smallest]); slot = smallest; }
+            if (slot >= 0) {
+                ctx->free_ptr[slot] = p->base; ctx->free_bytes[slot] = p->alloc_bytes;
+                delete p;
+                return ACM_OK;
+            }
+        }
+    }
     cudaFree(p->base);
     delete p;
     return ACM_OK;

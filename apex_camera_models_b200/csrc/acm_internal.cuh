@@ -30,7 +30,10 @@ struct acm_points {
     size_t n;
     size_t stride_bytes;  // distance between components, multiple of 256
     void* base;
+    size_t alloc_bytes;   // size of the allocation behind `base` (>= dim * stride_bytes)
 };
+
+#define ACM_FREE_LIST 8
 
 #define ACM_MAX_PEERS 8
 
@@ -62,6 +65,10 @@ struct acm_ctx {
     size_t h_stage_cap;
     void* d_scratch;        // grow-only arena for the temporaries of the util entry points
     size_t scratch_cap;
+    // destroyed point buffers are kept for the next acm_points_create of a similar size (a
+    // cudaMalloc / cudaFree pair costs milliseconds at 10 M points, the kernels around it microseconds)
+    void* free_ptr[ACM_FREE_LIST];
+    size_t free_bytes[ACM_FREE_LIST];
     acm_points* cache3;     // device buffers kept between *_host calls (grow-only)
     acm_points* cache2;
     size_t cache_cap;
@@ -111,6 +118,7 @@ void acm_set_global_error(const char* msg);
 
 // host helpers implemented in acm_core.cu
 int32_t acm_make_cam_params(acm_ctx* ctx, const acm_camera* cam, CamParams* out);
+int32_t acm_device_malloc(acm_ctx* ctx, void** out, size_t bytes);  // cudaMalloc; empties the free list and retries when out of memory
 int32_t acm_ensure_stage(acm_ctx* ctx, size_t bytes);
 int32_t acm_ensure_host_stage(acm_ctx* ctx, size_t bytes);
 int32_t acm_ensure_partials(acm_ctx* ctx, size_t doubles);
