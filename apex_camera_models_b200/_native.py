@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libacm.so")
+LIB_PATH = os.environ.get("ACM_LIB_PATH") or os.path.join(_HERE, "lib", "libacm.so")  # the override is a tuning aid (A/B of two builds)
 
 ACM_MAX_PARAMS = 9
 F64, F32 = 0, 1

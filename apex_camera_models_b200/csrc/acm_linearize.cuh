@@ -244,23 +244,23 @@ template <> struct Lin<ACM_MODEL_FOV, ACM_RESIDUAL_PIXEL> {
     static constexpr int ND = 1; static constexpr bool UNIT_C = true;
     static __device__ __forceinline__ bool eval(const LinParams& p, double x, double y, double z, double u, double v,
                                                 double& ru, double& rv, double* au, double* av) {
+        // branch-free: the r2 < sqrt(EPS) case (fov.rs:203-207, constant rd) is a select at the end
         const bool ok = z >= LIN_SQRT_EPS;
         z = ok ? z : 1.0;
         const double w = p.d[0], t = p.k0;
-        double r2 = x * x + y * y;
-        double rd, drd;
-        double iw = 1.0 / w;
-        if (r2 < LIN_SQRT_EPS) {
-            rd = 2.0 * t * iw;
-            drd = (1.0 + t * t) * iw - 2.0 * t * iw * iw;
-        } else {
-            double r = sqrt(r2);
-            double a = fast_atan2_q1(2.0 * t * r, z);
-            double da = z * r * (1.0 + t * t) / (4.0 * t * t * r2 + z * z);
-            double irw = iw / r;
-            rd = a * irw;
-            drd = (da - a * iw) * irw;
-        }
+        const double iw = fast_rcp(w), t2 = 2.0 * t, tt1 = fma(t, t, 1.0);   // loop-invariant
+        const double r2 = x * x + y * y;
+        const bool small = r2 < LIN_SQRT_EPS;
+        const double r2s = small ? 1.0 : r2;
+        double ir;
+        const double r = fast_sqrt<true>(r2s, ir);
+        const double a = fast_atan2_q1(t2 * r, z);
+        const double da = z * r * tt1 * fast_rcp(fma(t2 * t2, r2s, z * z));
+        const double irw = iw * ir;
+        double rd = a * irw;
+        double drd = (da - a * iw) * irw;
+        rd = small ? t2 * iw : rd;
+        drd = small ? (tt1 - t2 * iw) * iw : drd;
         double mx = x * rd, my = y * rd;
         ru = fma(p.fx, mx, p.cx) - u; rv = fma(p.fy, my, p.cy) - v;
         au[0] = mx; av[0] = my; au[1] = av[1] = 1.0;

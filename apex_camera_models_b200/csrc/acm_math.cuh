@@ -23,27 +23,28 @@ __device__ __forceinline__ double acm_rcp(double a) {
 // Operands whose magnitude would push the MUFU seed into its flush-to-zero range take the library
 // function (a branch that is practically never taken; GUARD = false drops it for the solver kernels,
 // whose streaming loop must stay one basic block and whose inputs are sane by construction).
+// The coefficients live in the constant bank: DFMA then reads them as c[bank][offset] operands,
+// whereas 64-bit literals are re-materialised (two UMOV / IMAD.MOV each) inside the streaming loops.
+static __constant__ double ACM_ATAN_C[14] = {
+    2.11353731576932463e-02, -4.34805221571646222e-02, 5.68834922680901064e-02, -6.64023393042940807e-02,
+    7.68995349630685748e-02, -9.09077307480841423e-02, 1.11111061804559458e-01, -1.42857141809764665e-01,
+    1.99999999988551114e-01, -3.33333333333284410e-01,
+    0.41421356237309503 /* tan(pi/8) */, 0.78539816339744828 /* pi/4 */, 1.5707963267948966 /* pi/2 */, 0.0};
+
 template <bool GUARD = true>
 __device__ __forceinline__ double acm_atan2_q1(double a, double b) {
     const bool swap = a > b;
     const double num = swap ? b : a, den = swap ? a : b;
     if (GUARD && !(den > 1e-280 && den < 1e280)) return atan2(a, b);
-    const bool hi = num > __dmul_rn(0.41421356237309503, den);
+    const bool hi = num > __dmul_rn(ACM_ATAN_C[10], den);
     const double n2 = hi ? __dsub_rn(num, den) : num;
     const double d2 = hi ? __dadd_rn(num, den) : den;
     const double t = __dmul_rn(n2, acm_rcp(d2));
     const double s = __dmul_rn(t, t);
-    double q = 2.11353731576932463e-02;
-    q = __fma_rn(q, s, -4.34805221571646222e-02);
-    q = __fma_rn(q, s, 5.68834922680901064e-02);
-    q = __fma_rn(q, s, -6.64023393042940807e-02);
-    q = __fma_rn(q, s, 7.68995349630685748e-02);
-    q = __fma_rn(q, s, -9.09077307480841423e-02);
-    q = __fma_rn(q, s, 1.11111061804559458e-01);
-    q = __fma_rn(q, s, -1.42857141809764665e-01);
-    q = __fma_rn(q, s, 1.99999999988551114e-01);
-    q = __fma_rn(q, s, -3.33333333333284410e-01);
+    double q = ACM_ATAN_C[0];
+#pragma unroll
+    for (int k = 1; k < 10; ++k) q = __fma_rn(q, s, ACM_ATAN_C[k]);
     double at = __fma_rn(__dmul_rn(t, s), q, t);
-    at = hi ? __dadd_rn(0.78539816339744828, at) : at;
-    return swap ? __dsub_rn(1.5707963267948966, at) : at;
+    at = hi ? __dadd_rn(ACM_ATAN_C[11], at) : at;
+    return swap ? __dsub_rn(ACM_ATAN_C[12], at) : at;
 }

@@ -382,7 +382,7 @@ static int32_t launch_linearize(acm_ctx* ctx, const LinParams& hp, LmState* d_lm
                                 const acm_points* xyz, const acm_points* uv, double invalid_penalty) {
     static int bs = 0;
     if (!bs) {
-        bs = (M == ACM_MODEL_KANNALA_BRANDT) ? 128 : 256;
+        bs = (M == ACM_MODEL_KANNALA_BRANDT || M == ACM_MODEL_FOV || M == ACM_MODEL_UCM) ? 128 : 256;  // measured, scripts/lin_bench.py
         const char* e = getenv("ACM_LIN_BLOCK");
         if (e && (atoi(e) == 128 || atoi(e) == 256)) bs = atoi(e);
     }
