@@ -8,6 +8,8 @@
 // per thread (2 f64 or 4 f32 points), grid-stride loop over a grid of sm_count * k blocks.
 #include <stdlib.h>
 
+#include <cuda.h>
+
 #include "acm_models.cuh"
 
 // ---------------------------------------------------------------------------------------
@@ -381,13 +383,11 @@ __device__ __forceinline__ void blend_exact_px(const uint8_t* p, int row_stride,
 // mapping was bound by L1 sector look-ups, 444 M per 8 frames).  The 96 output bytes of a patch row
 // are exchanged with two shuffles so that 24 lanes store one aligned word each.
 template <int M>
-__global__ void __launch_bounds__(256, 3) undistort_bilinear_fast_kernel(const __grid_constant__ CamParams c, double tfx, double tfy,
-                                                                      double tcx, double tcy, const uint8_t* __restrict__ in,
-                                                                      uint8_t* __restrict__ out, int W, int H, size_t n_frames) {
+__device__ __forceinline__ void undistort_patch_gather(const CamParams& c, double tfx, double tfy, double tcx, double tcy,
+                                                       const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int W, int H,
+                                                       size_t n_frames, const int x0, const int y0) {
     constexpr uint32_t TIE_E = 640u;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int x0 = blockIdx.x * 64 + (warp & 1) * 32;        // patch origin
-    const int y0 = blockIdx.y * 16 + (warp >> 1) * 4;
+    const int lane = threadIdx.x & 31;
     const int uo = x0 + lane;
     const size_t frame_bytes = (size_t)W * H * 3;
     const int row_stride = 3 * W;
@@ -478,6 +478,233 @@ __global__ void __launch_bounds__(256, 3) undistort_bilinear_fast_kernel(const _
     }
 }
 
+
+// grid-mapped: block = 64 x 16 output pixels, warp w owns the patch at (w & 1, w >> 1)
+template <int M>
+__global__ void __launch_bounds__(256, 3) undistort_bilinear_fast_kernel(const __grid_constant__ CamParams c, double tfx, double tfy,
+                                                                      double tcx, double tcy, const uint8_t* __restrict__ in,
+                                                                      uint8_t* __restrict__ out, int W, int H, size_t n_frames) {
+    const int warp = threadIdx.x >> 5;
+    undistort_patch_gather<M>(c, tfx, tfy, tcx, tcy, in, out, W, H, n_frames, blockIdx.x * 64 + (warp & 1) * 32, blockIdx.y * 16 + (warp >> 1) * 4);
+}
+
+// list-driven: the patches the TMA kernel below could not stage (source box larger than its tile)
+template <int M>
+__global__ void __launch_bounds__(256, 3) undistort_bilinear_list_kernel(const __grid_constant__ CamParams c, double tfx, double tfy,
+                                                                      double tcx, double tcy, const uint8_t* __restrict__ in,
+                                                                      uint8_t* __restrict__ out, int W, int H, size_t n_frames,
+                                                                      const uint32_t* __restrict__ list, const uint32_t* __restrict__ list_count) {
+    const uint32_t total = *list_count;
+    const uint32_t npx = (uint32_t)(W + 31) / 32u;
+    for (uint32_t e = blockIdx.x * 8u + (threadIdx.x >> 5); e < total; e += gridDim.x * 8u) {
+        const uint32_t pid = list[e];
+        undistort_patch_gather<M>(c, tfx, tfy, tcx, tcy, in, out, W, H, n_frames, (int)(pid % npx) * 32, (int)(pid / npx) * 4);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// TMA path (W % 16 == 0, 16-byte aligned frames): the gathers above are bound by load latency and L1
+// sector look-ups (ncu: long_scoreboard 4.6 per issue, 60 % of the LSU wavefront budget).  Here
+// every warp stages the SOURCE BOX of its 32 x 4 output patch -- UND_BOX_W bytes x UND_BOX_ROWS
+// rows, found once from the taps -- in shared memory with one `cp.async.bulk.tensor.3d` per frame
+// (tensor = [frame][row][byte] over the input batch), UND_STAGES frames ahead through a ring of
+// mbarriers.  The taps then come from shared memory at loop-invariant offsets, so the frame loop
+// has no global loads and no address arithmetic left.  The warp is producer and consumer of its
+// own ring, hence no "empty" barriers: the shuffles that exchange the finished pixels order every
+// lane's tile reads before lane 0 re-arms the stage.  Patches whose box does not fit are appended
+// to a list and handled by `undistort_bilinear_list_kernel`.
+// The blend also drops one instruction per channel: the upper 16 bits of the 24-bit weights go
+// through dp2a, the low byte plane through dp4a:  S = (dp2a(hi16) << 8) + dp4a(lo8) + 2^23.
+// ---------------------------------------------------------------------------------------
+#define UND_BOX_W 128
+#define UND_BOX_ROWS 10
+#define UND_STAGES 4
+
+__device__ __forceinline__ uint32_t und_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void und_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void und_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool und_mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void und_tma_load_3d(uint32_t dst, const void* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+template <int M>
+__global__ void __launch_bounds__(256, 3) undistort_bilinear_tma_kernel(const __grid_constant__ CamParams c, double tfx, double tfy,
+                                                                     double tcx, double tcy, const __grid_constant__ CUtensorMap in_map,
+                                                                     const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int W,
+                                                                     int H, int n_frames, uint32_t* __restrict__ list,
+                                                                     uint32_t* __restrict__ list_count) {
+    constexpr uint32_t TIE_E = 640u;
+    constexpr int TILE = UND_BOX_W * UND_BOX_ROWS;
+    // dynamic shared memory: tiles[8 warps][STAGES][TILE] | mbarriers[8][STAGES] | wx[4][256] | wy[4][256]
+    // (the f64 weights are only read by the rare exact re-blend; keeping them out of registers is what
+    // lets three blocks stay resident)
+    extern __shared__ __align__(128) uint8_t und_smem[];
+    uint8_t* const tiles = und_smem;
+    unsigned long long* const bars = reinterpret_cast<unsigned long long*>(und_smem + 8 * UND_STAGES * TILE);
+    double* const s_wx = reinterpret_cast<double*>(und_smem + 8 * UND_STAGES * TILE + 8 * UND_STAGES * 8);
+    double* const s_wy = s_wx + 4 * 256;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x0 = blockIdx.x * 64 + (warp & 1) * 32;        // patch origin
+    const int y0 = blockIdx.y * 16 + (warp >> 1) * 4;
+    if (x0 >= W || y0 >= H) return;                          // warp-uniform; nothing block-wide follows
+    const int uo = x0 + lane;
+    const size_t frame_bytes = (size_t)W * H * 3;
+    const int row_stride = 3 * W;
+    // Pixels without a sample keep all-zero weights: their blend is 2^23 >> 24 = 0 (black) and can never
+    // look like a tie, so the frame loop needs no per-pixel mode test.  `slow` marks the pixels that must
+    // always take the exact f64 expression (a weight of exactly 1).
+    int off[4];
+    uint32_t sel[4], wlo[4], w01[4], w23[4];
+    uint32_t valid = 0u, slow = 0u;
+    int bx_min = 0x7fffffff, bx_max = -1, by_min = 0x7fffffff, by_max = -1;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int vo = y0 + k;
+        double sx = 0.0, sy = 0.0;
+        int st = ACM_POINT_IS_OUTSIDE_IMAGE;
+        if (uo < W && vo < H) {
+            const double xn = ((double)uo - tcx) / tfx;
+            const double yn = ((double)vo - tcy) / tfy;
+            st = CamModel<M>::template project<true>(c, xn, yn, 1.0, sx, sy);
+        }
+        const Tap t = make_tap(sx, sy, st, W, H, ACM_INTERP_BILINEAR);
+        off[k] = t.off00;
+        s_wx[k * 256 + threadIdx.x] = t.wx; s_wy[k * 256 + threadIdx.x] = t.wy;
+        const double wxi = 1.0 - t.wx, wyi = 1.0 - t.wy;
+        uint32_t w00 = __double2uint_rn(wxi * wyi * 16777216.0), w10 = __double2uint_rn(t.wx * wyi * 16777216.0);
+        uint32_t w01_ = __double2uint_rn(wxi * t.wy * 16777216.0), w11 = __double2uint_rn(t.wx * t.wy * 16777216.0);
+        if (t.ok) {
+            valid |= 1u << k;
+            if ((w00 | w10 | w01_ | w11) >> 24) slow |= 1u << k;
+            const int ty = t.off00 / row_stride, tb = t.off00 - ty * row_stride;
+            bx_min = min(bx_min, tb); bx_max = max(bx_max, tb + 5);
+            by_min = min(by_min, ty); by_max = max(by_max, ty + 1);
+        } else {
+            w00 = w10 = w01_ = w11 = 0u;
+        }
+        // tap order [00, 10, 01, 11]: low byte plane for dp4a, upper 16 bits pairwise for dp2a
+        wlo[k] = (w00 & 0xFF) | ((w10 & 0xFF) << 8) | ((w01_ & 0xFF) << 16) | ((w11 & 0xFF) << 24);
+        w01[k] = ((w00 >> 8) & 0xFFFF) | (((w10 >> 8) & 0xFFFF) << 16);
+        w23[k] = ((w01_ >> 8) & 0xFFFF) | (((w11 >> 8) & 0xFFFF) << 16);
+        sel[k] = 0x3210u + 0x1111u * (uint32_t)(t.off00 & 3);
+    }
+    bx_min = __reduce_min_sync(0xffffffffu, bx_min); bx_max = __reduce_max_sync(0xffffffffu, bx_max);
+    by_min = __reduce_min_sync(0xffffffffu, by_min); by_max = __reduce_max_sync(0xffffffffu, by_max);
+    const bool any_valid = bx_max >= 0;
+    const int box_x = any_valid ? (bx_min & ~15) : 0, box_y = any_valid ? by_min : 0;
+    // the aligned 12-byte window of the right-most tap may reach 3 bytes past bx_max
+    if (any_valid && (bx_max + 3 - box_x >= UND_BOX_W || by_max - box_y >= UND_BOX_ROWS)) {
+        if (lane == 0) list[atomicAdd(list_count, 1u)] = (uint32_t)(y0 >> 2) * ((uint32_t)(W + 31) / 32u) + (uint32_t)(x0 >> 5);
+        return;
+    }
+    const uint32_t tile0 = und_smem_u32(tiles + warp * UND_STAGES * TILE), bar0 = und_smem_u32(bars + warp * UND_STAGES);
+    uint32_t so[4];  // shared-memory address of the aligned tap window in stage 0
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int ty = off[k] / row_stride, tb = off[k] - ty * row_stride;
+        so[k] = tile0 + (((valid >> k) & 1u) ? (uint32_t)((ty - box_y) * UND_BOX_W + ((tb - box_x) & ~3)) : 0u);
+    }
+    const int src_lane = (4 * lane) / 3;
+    const uint32_t out_sel = (lane % 3 == 0) ? 0x4210u : (lane % 3 == 1) ? 0x5421u : 0x6542u;
+    const int valid_px = min(32, W - x0);                     // multiple of 4 because W % 16 == 0
+    const int n_rows = (lane < 24 && 4 * lane + 3 < 3 * valid_px) ? min(4, H - y0) : 0;  // rows this lane stores
+    uint8_t* dst = out + ((size_t)y0 * W + x0) * 3 + 4 * lane;
+    if (lane == 0) {
+#pragma unroll
+        for (int sidx = 0; sidx < UND_STAGES; ++sidx) und_mbar_init(bar0 + 8 * sidx, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (any_valid) {
+#pragma unroll
+            for (int sidx = 0; sidx < UND_STAGES; ++sidx) {
+                if (sidx < n_frames) {
+                    und_mbar_expect_tx(bar0 + 8 * sidx, TILE);
+                    und_tma_load_3d(tile0 + sidx * TILE, &in_map, bar0 + 8 * sidx, box_x, box_y, sidx);
+                }
+            }
+        }
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t parity = 0;
+    const long long t_begin = clock64();
+    for (int f = 0; f < n_frames; ++f, dst += frame_bytes) {
+        uint32_t px[4] = {0u, 0u, 0u, 0u};  // [R G B .] per pixel
+        if (any_valid) {
+            const uint32_t bar = bar0 + 8 * stage;
+            int spins = 0;
+            while (!und_mbar_try_wait(bar, parity)) {
+                // a lost TMA must not hang the GPU: give up after ~2 s
+                if ((++spins & 255) == 0 && clock64() - t_begin > 4000000000LL) __trap();
+            }
+            const uint32_t stage_off = (uint32_t)(stage * TILE);
+            uint32_t redo = slow;
+            uint32_t tz[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint32_t a0, a1, a2, b0, b1, b2;
+                const uint32_t addr = so[k] + stage_off;
+                asm volatile("ld.shared.u32 %0, [%6];\n ld.shared.u32 %1, [%6+4];\n ld.shared.u32 %2, [%6+8];\n"
+                             "ld.shared.u32 %3, [%6+128];\n ld.shared.u32 %4, [%6+132];\n ld.shared.u32 %5, [%6+136];"
+                             : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(b0), "=r"(b1), "=r"(b2) : "r"(addr));
+                const uint32_t A = __byte_perm(a0, a1, sel[k]), B = __byte_perm(a1, a2, sel[k]);     // [r0 g0 b0 r1] [g1 b1 . .]
+                const uint32_t A2 = __byte_perm(b0, b1, sel[k]), B2 = __byte_perm(b1, b2, sel[k]);
+                const uint32_t PR = __byte_perm(A, A2, 0x7430);                                       // [r00 r10 r01 r11]
+                const uint32_t T0 = __byte_perm(A, B, 0x5241), T1 = __byte_perm(A2, B2, 0x5241);      // [g0 g1 b0 b1]
+                const uint32_t PG = __byte_perm(T0, T1, 0x5410), PB = __byte_perm(T0, T1, 0x7632);
+                const uint32_t sr = (__dp2a_hi(w23[k], PR, __dp2a_lo(w01[k], PR, 0u)) << 8) + __dp4a(PR, wlo[k], 1u << 23);
+                const uint32_t sg = (__dp2a_hi(w23[k], PG, __dp2a_lo(w01[k], PG, 0u)) << 8) + __dp4a(PG, wlo[k], 1u << 23);
+                const uint32_t sb = (__dp2a_hi(w23[k], PB, __dp2a_lo(w01[k], PB, 0u)) << 8) + __dp4a(PB, wlo[k], 1u << 23);
+                px[k] = __byte_perm(__byte_perm(sr, sg, 0x4473), sb, 0x4710);                         // [sr.3 sg.3 sb.3 .]
+                // distance of the 24-bit fraction to a rounding tie, scaled by 2^8 so that the 32-bit wrap does the
+                // masking: ((s + E) mod 2^24) < 2E  <=>  (s * 2^8 + E * 2^8) mod 2^32 < 2E * 2^8
+                tz[k] = min(min(sr * 256u + TIE_E * 256u, sg * 256u + TIE_E * 256u), sb * 256u + TIE_E * 256u);
+            }
+            if (min(min(tz[0], tz[1]), min(tz[2], tz[3])) < 2u * TIE_E * 256u) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) redo |= (tz[k] < 2u * TIE_E * 256u ? 1u : 0u) << k;
+            }
+            if (redo) {  // rare: redo these pixels with the reference's f64 expression from global memory
+                const uint8_t* src = in + (size_t)f * frame_bytes;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if ((redo >> k) & 1u) {
+                        // rebuild the byte offset of p00 from the tile address and the byte selector
+                        const uint32_t rel = so[k] - tile0;
+                        const int o00 = (box_y + (int)(rel / UND_BOX_W)) * row_stride + box_x + (int)(rel % UND_BOX_W) + (int)(sel[k] & 3u);
+                        uint8_t o[3];
+                        blend_exact_px(src + o00, row_stride, s_wx[k * 256 + threadIdx.x], s_wy[k * 256 + threadIdx.x], o);
+                        px[k] = o[0] | (o[1] << 8) | ((uint32_t)o[2] << 16);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t pa = __shfl_sync(0xffffffffu, px[k], src_lane);
+            const uint32_t pb = __shfl_sync(0xffffffffu, px[k], (src_lane + 1) & 31);
+            if (k < n_rows) __stcs(reinterpret_cast<uint32_t*>(dst + (size_t)k * row_stride), __byte_perm(pa, pb, out_sel));
+        }
+        // every lane's tile reads of this stage have been consumed by the shuffles above
+        if (any_valid && lane == 0 && f + UND_STAGES < n_frames) {
+            und_mbar_expect_tx(bar0 + 8 * stage, TILE);
+            und_tma_load_3d(tile0 + stage * TILE, &in_map, bar0 + 8 * stage, box_x, box_y, f + UND_STAGES);
+        }
+        if (++stage == UND_STAGES) { stage = 0; parity ^= 1u; }
+    }
+}
+
 template <int M>
 __global__ void __launch_bounds__(256) undistort_map_kernel(const __grid_constant__ CamParams c, double tfx, double tfy, double tcx,
                                                             double tcy, double* __restrict__ src_xy, int W, int H) {
@@ -489,6 +716,33 @@ __global__ void __launch_bounds__(256) undistort_map_kernel(const __grid_constan
     int st = CamModel<M>::template project<true>(c, xn, yn, 1.0, sx, sy);
     if (st != ACM_POINT_OK) sx = sy = acm_nan();
     reinterpret_cast<double2*>(src_xy)[i] = make_double2(sx, sy);
+}
+
+// Tensor map over the input batch as [frame][row][byte] (u8), box = UND_BOX_W bytes x UND_BOX_ROWS rows of
+// one frame.  cuTensorMapEncodeTiled comes from the driver through the runtime's entry-point query, so
+// libacm does not link against libcuda.  Returns false when the driver refuses (the caller then uses
+// the gather kernel).
+static bool make_frame_tensor_map(CUtensorMap* map, const uint8_t* d_in, int W, int H, size_t n_frames) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    static bool looked_up = false;
+    if (!looked_up) {
+        looked_up = true;
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            encode = reinterpret_cast<EncodeFn>(fn);
+        else
+            cudaGetLastError();
+    }
+    if (!encode) return false;
+    const cuuint64_t gdim[3] = {(cuuint64_t)3 * W, (cuuint64_t)H, (cuuint64_t)n_frames};
+    const cuuint64_t gstride[2] = {(cuuint64_t)3 * W, (cuuint64_t)3 * W * H};  // bytes, dims 1 and 2
+    const cuuint32_t box[3] = {UND_BOX_W, UND_BOX_ROWS, 1};
+    const cuuint32_t estride[3] = {1, 1, 1};
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(d_in), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 static int32_t check_undistort_args(acm_ctx* ctx, const acm_camera* cam, const double* target, double t[4]) {
@@ -514,9 +768,26 @@ extern "C" int32_t acm_undistort_rgb8(acm_ctx* ctx, const acm_camera* cam, const
     const int W = (int)cam->width, H = (int)cam->height;
     dim3 grid((W + 1023) / 1024, H);
     const bool aligned = ((reinterpret_cast<uintptr_t>(d_in) & 3) == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 3) == 0) && (W % 4 == 0);
+    const bool tma_ok = ((reinterpret_cast<uintptr_t>(d_in) & 15) == 0) && (W % 16 == 0) && n_frames < 0x7fffffffULL && !getenv("ACM_UNDISTORT_NO_TMA");
     if (interpolation == ACM_INTERP_BILINEAR && aligned && !getenv("ACM_UNDISTORT_GENERIC")) {
         dim3 fgrid((W + 63) / 64, (H + 15) / 16);
-        ACM_DISPATCH_MODEL(cam->model, (undistort_bilinear_fast_kernel<M><<<fgrid, 256, 0, ctx->stream>>>(c, t[0], t[1], t[2], t[3], d_in, d_out, W, H, n_frames)))
+        CUtensorMap map;
+        if (tma_ok && make_frame_tensor_map(&map, d_in, W, H, n_frames)) {
+            // leftover list: [count][patch ids], one id per 32 x 4 patch at most
+            const size_t n_patches = (size_t)((W + 31) / 32) * (size_t)((H + 3) / 4);
+            rc = acm_ensure_scratch(ctx, 256 + n_patches * sizeof(uint32_t));
+            if (rc) return rc;
+            uint32_t* d_count = static_cast<uint32_t*>(ctx->d_scratch);
+            uint32_t* d_list = d_count + 64;
+            ACM_CUDA(ctx, cudaMemsetAsync(d_count, 0, sizeof(uint32_t), ctx->stream));
+            constexpr int und_smem_bytes = 8 * UND_STAGES * UND_BOX_W * UND_BOX_ROWS + 8 * UND_STAGES * 8 + 2 * 4 * 256 * 8;
+            ACM_DISPATCH_MODEL(cam->model, (cudaFuncSetAttribute(undistort_bilinear_tma_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, und_smem_bytes)))
+            ACM_DISPATCH_MODEL(cam->model, (undistort_bilinear_tma_kernel<M><<<fgrid, 256, und_smem_bytes, ctx->stream>>>(c, t[0], t[1], t[2], t[3], map, d_in, d_out, W, H, (int)n_frames, d_list, d_count)))
+            ACM_CHECK_LAUNCH(ctx);
+            ACM_DISPATCH_MODEL(cam->model, (undistort_bilinear_list_kernel<M><<<ctx->sm_count * 3, 256, 0, ctx->stream>>>(c, t[0], t[1], t[2], t[3], d_in, d_out, W, H, n_frames, d_list, d_count)))
+        } else {
+            ACM_DISPATCH_MODEL(cam->model, (undistort_bilinear_fast_kernel<M><<<fgrid, 256, 0, ctx->stream>>>(c, t[0], t[1], t[2], t[3], d_in, d_out, W, H, n_frames)))
+        }
     } else {
         ACM_DISPATCH_MODEL(cam->model, (undistort_kernel<M><<<grid, 256, 0, ctx->stream>>>(c, t[0], t[1], t[2], t[3], d_in, d_out, W, H, n_frames, interpolation)))
     }

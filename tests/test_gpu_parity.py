@@ -655,6 +655,19 @@ def test_undistort_bytes_and_remap_indices(acm, ctx, O, cameras, name, W, H):
         acm.undistort_image(np.zeros((H + 1, W, 3), np.uint8), m)
 
 
+def test_undistort_many_frames_ring_wraparound(acm, ctx, O, cameras):
+    """The TMA path keeps 4 frames in flight per warp: 11 frames take every stage through three
+    phases of its mbarrier; the bytes of every frame must still equal the oracle's."""
+    cam = dict(cameras["kannala_brandt"]); W, H = 512, 512
+    m, om = gpu_model(acm, ctx, cam), oracle_model(O, cam)
+    F = 11
+    frames = O.synth_bytes(0xACE50006, 0, F * W * H * 3).reshape(F, H, W, 3)
+    out = acm.undistort_images(frames, m)
+    for f in range(F):
+        ref = O.undistort_rgb8(om, cam["params"][:4], frames[f], 1, nthreads=4)
+        assert np.array_equal(out[f], ref), f"frame {f}: {(out[f] != ref).sum()} bytes differ"
+
+
 # ------------------------------------------------------------------ BASELINE sizes: properties -----
 def test_full_size_round_trip_and_linearity(acm, ctx, O, cameras):
     """100 M synthetic points (BASELINE configs 2 and 3): project -> unproject returns the input
