@@ -517,8 +517,11 @@ __global__ void __launch_bounds__(256, 3) undistort_bilinear_list_kernel(const _
 // through dp2a, the low byte plane through dp4a:  S = (dp2a(hi16) << 8) + dp4a(lo8) + 2^23.
 // ---------------------------------------------------------------------------------------
 #define UND_BOX_W 128
-#define UND_BOX_ROWS 10
+#define UND_BOX_ROWS 10      // tallest box (the shared-memory tile holds this many rows)
+#define UND_MIN_ROWS 4       // one tensor map per box height UND_MIN_ROWS .. UND_BOX_ROWS: a warp fetches only the rows it needs
 #define UND_STAGES 4
+
+struct UndMaps { CUtensorMap m[UND_BOX_ROWS - UND_MIN_ROWS + 1]; };
 
 __device__ __forceinline__ uint32_t und_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void und_mbar_init(uint32_t bar, uint32_t count) {
@@ -538,9 +541,9 @@ __device__ __forceinline__ void und_tma_load_3d(uint32_t dst, const void* map, u
                  ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
-template <int M>
+template <int M, bool NEAREST>
 __global__ void __launch_bounds__(256, 3) undistort_bilinear_tma_kernel(const __grid_constant__ CamParams c, double tfx, double tfy,
-                                                                     double tcx, double tcy, const __grid_constant__ CUtensorMap in_map,
+                                                                     double tcx, double tcy, const __grid_constant__ UndMaps in_maps,
                                                                      const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int W,
                                                                      int H, int n_frames, uint32_t* __restrict__ list,
                                                                      uint32_t* __restrict__ list_count) {
@@ -578,18 +581,18 @@ __global__ void __launch_bounds__(256, 3) undistort_bilinear_tma_kernel(const __
             const double yn = ((double)vo - tcy) / tfy;
             st = CamModel<M>::template project<true>(c, xn, yn, 1.0, sx, sy);
         }
-        const Tap t = make_tap(sx, sy, st, W, H, ACM_INTERP_BILINEAR);
+        const Tap t = make_tap(sx, sy, st, W, H, NEAREST ? ACM_INTERP_NEAREST : ACM_INTERP_BILINEAR);
         off[k] = t.off00;
-        s_wx[k * 256 + threadIdx.x] = t.wx; s_wy[k * 256 + threadIdx.x] = t.wy;
+        if (!NEAREST) { s_wx[k * 256 + threadIdx.x] = t.wx; s_wy[k * 256 + threadIdx.x] = t.wy; }
         const double wxi = 1.0 - t.wx, wyi = 1.0 - t.wy;
         uint32_t w00 = __double2uint_rn(wxi * wyi * 16777216.0), w10 = __double2uint_rn(t.wx * wyi * 16777216.0);
         uint32_t w01_ = __double2uint_rn(wxi * t.wy * 16777216.0), w11 = __double2uint_rn(t.wx * t.wy * 16777216.0);
         if (t.ok) {
             valid |= 1u << k;
-            if ((w00 | w10 | w01_ | w11) >> 24) slow |= 1u << k;
+            if (!NEAREST && ((w00 | w10 | w01_ | w11) >> 24)) slow |= 1u << k;
             const int ty = t.off00 / row_stride, tb = t.off00 - ty * row_stride;
-            bx_min = min(bx_min, tb); bx_max = max(bx_max, tb + 5);
-            by_min = min(by_min, ty); by_max = max(by_max, ty + 1);
+            bx_min = min(bx_min, tb); bx_max = max(bx_max, tb + (NEAREST ? 2 : 5));
+            by_min = min(by_min, ty); by_max = max(by_max, ty + (NEAREST ? 0 : 1));
         } else {
             w00 = w10 = w01_ = w11 = 0u;
         }
@@ -609,6 +612,9 @@ __global__ void __launch_bounds__(256, 3) undistort_bilinear_tma_kernel(const __
         return;
     }
     const uint32_t tile0 = und_smem_u32(tiles + warp * UND_STAGES * TILE), bar0 = und_smem_u32(bars + warp * UND_STAGES);
+    const int box_rows = any_valid ? max(by_max - box_y + 1, UND_MIN_ROWS) : UND_MIN_ROWS;
+    const CUtensorMap* const in_map = &in_maps.m[box_rows - UND_MIN_ROWS];
+    const uint32_t box_bytes = (uint32_t)(box_rows * UND_BOX_W);
     uint32_t so[4];  // shared-memory address of the aligned tap window in stage 0
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -629,8 +635,8 @@ __global__ void __launch_bounds__(256, 3) undistort_bilinear_tma_kernel(const __
 #pragma unroll
             for (int sidx = 0; sidx < UND_STAGES; ++sidx) {
                 if (sidx < n_frames) {
-                    und_mbar_expect_tx(bar0 + 8 * sidx, TILE);
-                    und_tma_load_3d(tile0 + sidx * TILE, &in_map, bar0 + 8 * sidx, box_x, box_y, sidx);
+                    und_mbar_expect_tx(bar0 + 8 * sidx, box_bytes);
+                    und_tma_load_3d(tile0 + sidx * TILE, in_map, bar0 + 8 * sidx, box_x, box_y, sidx);
                 }
             }
         }
@@ -651,6 +657,15 @@ __global__ void __launch_bounds__(256, 3) undistort_bilinear_tma_kernel(const __
             const uint32_t stage_off = (uint32_t)(stage * TILE);
             uint32_t redo = slow;
             uint32_t tz[4];
+            if (NEAREST) {  // the sample is the pixel itself (undistort.rs:79-90): 3 bytes out of two aligned words
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    uint32_t a0, a1;
+                    const uint32_t addr = so[k] + stage_off;
+                    asm volatile("ld.shared.u32 %0, [%2];\n ld.shared.u32 %1, [%2+4];" : "=r"(a0), "=r"(a1) : "r"(addr));
+                    px[k] = ((valid >> k) & 1u) ? (__byte_perm(a0, a1, sel[k]) & 0xFFFFFFu) : 0u;
+                }
+            } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 uint32_t a0, a1, a2, b0, b1, b2;
@@ -675,6 +690,7 @@ __global__ void __launch_bounds__(256, 3) undistort_bilinear_tma_kernel(const __
 #pragma unroll
                 for (int k = 0; k < 4; ++k) redo |= (tz[k] < 2u * TIE_E * 256u ? 1u : 0u) << k;
             }
+            }
             if (redo) {  // rare: redo these pixels with the reference's f64 expression from global memory
                 const uint8_t* src = in + (size_t)f * frame_bytes;
 #pragma unroll
@@ -698,10 +714,40 @@ __global__ void __launch_bounds__(256, 3) undistort_bilinear_tma_kernel(const __
         }
         // every lane's tile reads of this stage have been consumed by the shuffles above
         if (any_valid && lane == 0 && f + UND_STAGES < n_frames) {
-            und_mbar_expect_tx(bar0 + 8 * stage, TILE);
-            und_tma_load_3d(tile0 + stage * TILE, &in_map, bar0 + 8 * stage, box_x, box_y, f + UND_STAGES);
+            und_mbar_expect_tx(bar0 + 8 * stage, box_bytes);
+            und_tma_load_3d(tile0 + stage * TILE, in_map, bar0 + 8 * stage, box_x, box_y, f + UND_STAGES);
         }
         if (++stage == UND_STAGES) { stage = 0; parity ^= 1u; }
+    }
+}
+
+// nearest-neighbour leftovers of the TMA kernel (patches whose source box does not fit its tile):
+// one warp per listed patch, byte loads / stores -- never on the hot path
+template <int M>
+__global__ void __launch_bounds__(256) undistort_list_generic_kernel(const __grid_constant__ CamParams c, double tfx, double tfy, double tcx,
+                                                                     double tcy, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
+                                                                     int W, int H, size_t n_frames, int interp,
+                                                                     const uint32_t* __restrict__ list, const uint32_t* __restrict__ list_count) {
+    const uint32_t total = *list_count;
+    const uint32_t npx = (uint32_t)(W + 31) / 32u;
+    const int lane = threadIdx.x & 31;
+    const size_t frame_bytes = (size_t)W * H * 3;
+    for (uint32_t e = blockIdx.x * 8u + (threadIdx.x >> 5); e < total; e += gridDim.x * 8u) {
+        const uint32_t pid = list[e];
+        const int uo = (int)(pid % npx) * 32 + lane, y0 = (int)(pid / npx) * 4;
+        for (int k = 0; k < 4; ++k) {
+            const int vo = y0 + k;
+            if (uo >= W || vo >= H) continue;
+            double sx = 0.0, sy = 0.0;
+            const double xn = ((double)uo - tcx) / tfx, yn = ((double)vo - tcy) / tfy;
+            const int st = CamModel<M>::template project<true>(c, xn, yn, 1.0, sx, sy);
+            const Tap t = make_tap(sx, sy, st, W, H, interp);
+            for (size_t f = 0; f < n_frames; ++f) {
+                uint8_t* d = out + f * frame_bytes + ((size_t)vo * W + uo) * 3;
+                const uint8_t* p = in + f * frame_bytes + t.off00;
+                d[0] = t.ok ? __ldg(p) : 0; d[1] = t.ok ? __ldg(p + 1) : 0; d[2] = t.ok ? __ldg(p + 2) : 0;
+            }
+        }
     }
 }
 
@@ -722,7 +768,7 @@ __global__ void __launch_bounds__(256) undistort_map_kernel(const __grid_constan
 // one frame.  cuTensorMapEncodeTiled comes from the driver through the runtime's entry-point query, so
 // libacm does not link against libcuda.  Returns false when the driver refuses (the caller then uses
 // the gather kernel).
-static bool make_frame_tensor_map(CUtensorMap* map, const uint8_t* d_in, int W, int H, size_t n_frames) {
+static bool make_frame_tensor_map(CUtensorMap* map, const uint8_t* d_in, int W, int H, size_t n_frames, int box_rows) {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
     static EncodeFn encode = nullptr;
@@ -739,7 +785,7 @@ static bool make_frame_tensor_map(CUtensorMap* map, const uint8_t* d_in, int W, 
     if (!encode) return false;
     const cuuint64_t gdim[3] = {(cuuint64_t)3 * W, (cuuint64_t)H, (cuuint64_t)n_frames};
     const cuuint64_t gstride[2] = {(cuuint64_t)3 * W, (cuuint64_t)3 * W * H};  // bytes, dims 1 and 2
-    const cuuint32_t box[3] = {UND_BOX_W, UND_BOX_ROWS, 1};
+    const cuuint32_t box[3] = {UND_BOX_W, (cuuint32_t)box_rows, 1};
     const cuuint32_t estride[3] = {1, 1, 1};
     return encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(d_in), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -769,25 +815,34 @@ extern "C" int32_t acm_undistort_rgb8(acm_ctx* ctx, const acm_camera* cam, const
     dim3 grid((W + 1023) / 1024, H);
     const bool aligned = ((reinterpret_cast<uintptr_t>(d_in) & 3) == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 3) == 0) && (W % 4 == 0);
     const bool tma_ok = ((reinterpret_cast<uintptr_t>(d_in) & 15) == 0) && (W % 16 == 0) && n_frames < 0x7fffffffULL && !getenv("ACM_UNDISTORT_NO_TMA");
-    if (interpolation == ACM_INTERP_BILINEAR && aligned && !getenv("ACM_UNDISTORT_GENERIC")) {
+    UndMaps map;
+    const bool generic = getenv("ACM_UNDISTORT_GENERIC") != nullptr;
+    bool have_maps = aligned && !generic && tma_ok;
+    for (int r = UND_MIN_ROWS; have_maps && r <= UND_BOX_ROWS; ++r) have_maps = make_frame_tensor_map(&map.m[r - UND_MIN_ROWS], d_in, W, H, n_frames, r);
+    if (have_maps) {
         dim3 fgrid((W + 63) / 64, (H + 15) / 16);
-        CUtensorMap map;
-        if (tma_ok && make_frame_tensor_map(&map, d_in, W, H, n_frames)) {
-            // leftover list: [count][patch ids], one id per 32 x 4 patch at most
-            const size_t n_patches = (size_t)((W + 31) / 32) * (size_t)((H + 3) / 4);
-            rc = acm_ensure_scratch(ctx, 256 + n_patches * sizeof(uint32_t));
-            if (rc) return rc;
-            uint32_t* d_count = static_cast<uint32_t*>(ctx->d_scratch);
-            uint32_t* d_list = d_count + 64;
-            ACM_CUDA(ctx, cudaMemsetAsync(d_count, 0, sizeof(uint32_t), ctx->stream));
-            constexpr int und_smem_bytes = 8 * UND_STAGES * UND_BOX_W * UND_BOX_ROWS + 8 * UND_STAGES * 8 + 2 * 4 * 256 * 8;
-            ACM_DISPATCH_MODEL(cam->model, (cudaFuncSetAttribute(undistort_bilinear_tma_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, und_smem_bytes)))
-            ACM_DISPATCH_MODEL(cam->model, (undistort_bilinear_tma_kernel<M><<<fgrid, 256, und_smem_bytes, ctx->stream>>>(c, t[0], t[1], t[2], t[3], map, d_in, d_out, W, H, (int)n_frames, d_list, d_count)))
+        // leftover list: [count][patch ids], one id per 32 x 4 patch at most
+        const size_t n_patches = (size_t)((W + 31) / 32) * (size_t)((H + 3) / 4);
+        rc = acm_ensure_scratch(ctx, 256 + n_patches * sizeof(uint32_t));
+        if (rc) return rc;
+        uint32_t* d_count = static_cast<uint32_t*>(ctx->d_scratch);
+        uint32_t* d_list = d_count + 64;
+        ACM_CUDA(ctx, cudaMemsetAsync(d_count, 0, sizeof(uint32_t), ctx->stream));
+        constexpr int und_smem_bytes = 8 * UND_STAGES * UND_BOX_W * UND_BOX_ROWS + 8 * UND_STAGES * 8 + 2 * 4 * 256 * 8;
+        if (interpolation == ACM_INTERP_BILINEAR) {
+            ACM_DISPATCH_MODEL(cam->model, (cudaFuncSetAttribute(undistort_bilinear_tma_kernel<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, und_smem_bytes)))
+            ACM_DISPATCH_MODEL(cam->model, (undistort_bilinear_tma_kernel<M, false><<<fgrid, 256, und_smem_bytes, ctx->stream>>>(c, t[0], t[1], t[2], t[3], map, d_in, d_out, W, H, (int)n_frames, d_list, d_count)))
             ACM_CHECK_LAUNCH(ctx);
             ACM_DISPATCH_MODEL(cam->model, (undistort_bilinear_list_kernel<M><<<ctx->sm_count * 3, 256, 0, ctx->stream>>>(c, t[0], t[1], t[2], t[3], d_in, d_out, W, H, n_frames, d_list, d_count)))
         } else {
-            ACM_DISPATCH_MODEL(cam->model, (undistort_bilinear_fast_kernel<M><<<fgrid, 256, 0, ctx->stream>>>(c, t[0], t[1], t[2], t[3], d_in, d_out, W, H, n_frames)))
+            ACM_DISPATCH_MODEL(cam->model, (cudaFuncSetAttribute(undistort_bilinear_tma_kernel<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, und_smem_bytes)))
+            ACM_DISPATCH_MODEL(cam->model, (undistort_bilinear_tma_kernel<M, true><<<fgrid, 256, und_smem_bytes, ctx->stream>>>(c, t[0], t[1], t[2], t[3], map, d_in, d_out, W, H, (int)n_frames, d_list, d_count)))
+            ACM_CHECK_LAUNCH(ctx);
+            ACM_DISPATCH_MODEL(cam->model, (undistort_list_generic_kernel<M><<<ctx->sm_count * 3, 256, 0, ctx->stream>>>(c, t[0], t[1], t[2], t[3], d_in, d_out, W, H, n_frames, interpolation, d_list, d_count)))
         }
+    } else if (interpolation == ACM_INTERP_BILINEAR && aligned && !generic) {
+        dim3 fgrid((W + 63) / 64, (H + 15) / 16);
+        ACM_DISPATCH_MODEL(cam->model, (undistort_bilinear_fast_kernel<M><<<fgrid, 256, 0, ctx->stream>>>(c, t[0], t[1], t[2], t[3], d_in, d_out, W, H, n_frames)))
     } else {
         ACM_DISPATCH_MODEL(cam->model, (undistort_kernel<M><<<grid, 256, 0, ctx->stream>>>(c, t[0], t[1], t[2], t[3], d_in, d_out, W, H, n_frames, interpolation)))
     }
