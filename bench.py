@@ -288,6 +288,35 @@ def run_ours(args):
               "params": [float(v) for v in r.parameters], "final_cost": r.final_cost, "points_per_gpu": m}
         Xl.free(); Ul.free()
 
+    # --- undistort (BASELINE config 5): 4096x4096 KB fisheye frames (sample intrinsics x8), 32 frames per GPU resident in
+    # HBM = the per-GPU share of the 256-frame batch on 8 GPUs; frames shard over the ranks, no collective
+    und = None
+    if not args.no_undistort:
+        Wd = Hd = 4096
+        kb8 = acm.KannalaBrandtModel(acm.Intrinsics(*(v * 8 for v in KB_SAMPLE[:4])), acm.Resolution(Wd, Hd), KB_SAMPLE[4:], ctx=ctx)
+        cam8 = kb8.camera_block()
+        F = 32
+        fb = Wd * Hd * 3
+        d_in = ctx.device_alloc(fb * F); d_out = ctx.device_alloc(fb * F)
+        ctx.check(lib.acm_synth_bytes(ctx.handle, 0xACE50005, rank * F * fb, C.c_void_p(d_in), fb * F))
+        und = {"workload": "undistort 4096x4096 RGB8 KB fisheye frames, 32 per GPU resident in HBM (256-frame batch at 8 GPUs)", "frames_per_gpu": F}
+        for interp, name in ((1, "bilinear"), (0, "nearest")):
+            f_und = lambda: ctx.check(lib.acm_undistort_rgb8(ctx.handle, C.byref(cam8), None, C.c_void_p(d_in), C.c_void_p(d_out), F, interp))
+            for _ in range(3):
+                f_und()
+            barrier()
+            ctx.timer_start()
+            for _ in range(5):
+                f_und()
+            ms_u = ctx.timer_stop() / 5
+            barrier()
+            if dist is not None:
+                t = torch.tensor([ms_u], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms_u = float(t.item())
+            und[name] = {"ms": ms_u, "frames_s": F * world / ms_u * 1e3, "gb_s_per_gpu": 2 * fb * F / ms_u / 1e6, "us_per_frame": ms_u / F * 1e3}
+        ctx.device_free(d_in); ctx.device_free(d_out)
+
     if rank == 0:
         sampler.stop()
         peaks = {}
@@ -309,7 +338,7 @@ def run_ours(args):
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                              "kernel": "linearize_kernel<DOUBLE_SPHERE, PIXEL>", "algorithmic_bytes_per_launch": n * BYTES_PER_POINT,
                              "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0},
-                "e2e": e2e, "lm_conversion": lm,
+                "e2e": e2e, "lm_conversion": lm, "undistort_batch": und,
                 "check": {"n_valid": int(ne.n_valid), "cost": float(ne.cost), "H00": float(ne.H[0])}}
         if world == 1 and not args.no_cpu:
             v1, reps, el = cpu_baseline(args.cpu_points, 10.0, 1)
@@ -364,18 +393,6 @@ def run_extras(acm, N, lib, ctx, X, UV, n):
                           "round_trip_fused_ms": ms3, "round_trip_fused_gb_s": n * 66 / ms3 / 1e6}
     out["project_unproject_100M_f64"] = pu
     ctx.device_free(st); ctx.device_free(st2); UV2.free(); X2.free()
-    # undistort (BASELINE config 5): 4096x4096 KB fisheye (sample intrinsics x8), 32 frames resident in HBM
-    # = the per-GPU share of the 256-frame batch on 8 GPUs
-    W = H = 4096
-    kb8 = acm.KannalaBrandtModel(acm.Intrinsics(*(v * 8 for v in KB_SAMPLE[:4])), acm.Resolution(W, H), KB_SAMPLE[4:], ctx=ctx)
-    cam = kb8.camera_block()
-    F = 32
-    fb = W * H * 3
-    d_in = ctx.device_alloc(fb * F); d_out = ctx.device_alloc(fb * F)
-    ctx.check(lib.acm_synth_bytes(ctx.handle, 0xACE50005, 0, C.c_void_p(d_in), fb * F))
-    ms = timeit(lambda: ctx.check(lib.acm_undistort_rgb8(ctx.handle, C.byref(cam), None, C.c_void_p(d_in), C.c_void_p(d_out), F, 1)), reps=5)
-    out["undistort_4096x4096_kb_bilinear"] = {"frames": F, "ms": ms, "frames_s": F / ms * 1e3, "gb_s": 2 * fb * F / ms / 1e6}
-    ctx.device_free(d_in); ctx.device_free(d_out)
     return out
 
 
@@ -393,6 +410,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-lm", action="store_true")
+    ap.add_argument("--no-undistort", action="store_true")
     ap.add_argument("--no-peer", action="store_true", help="N > 1: keep the NCCL all-reduce instead of the fused NVLink exchange")
     args = ap.parse_args()
     if args.impl == "reference":
