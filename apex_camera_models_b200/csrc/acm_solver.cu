@@ -281,6 +281,22 @@ __device__ __forceinline__ void peer_exchange(const PeerArgs& peer, double* __re
 // ---------------------------------------------------------------------------------------
 // linearize kernel
 // ---------------------------------------------------------------------------------------
+// Per-model streaming configuration, measured on 100 M points (scripts/lin_bench.py; GB/s register
+// prefetch -> cp.async ring): DEPTH > 0 = every thread keeps that many packets in flight in a
+// shared-memory ring fed by cp.async; 0 = the next packet is prefetched into registers.
+//   DS 5.88 -> 6.24 TB/s (3 deep), EUCM 5.63 -> 5.79, UCM 5.83 -> 6.47 (2 deep), FOV 4.50 -> 4.97
+//   (3 deep, 128 threads), RadTan 4.09 -> 4.25 (2 deep); KB (160+ registers) and Pinhole (already at
+//   7.1 TB/s) are faster without the ring.
+template <int M> struct LinStream { static constexpr int DEPTH = 0, BLOCK = 256; };
+#ifndef ACM_LIN_NO_RING  // A/B aid: -DACM_LIN_NO_RING builds every model with the register prefetch
+template <> struct LinStream<ACM_MODEL_DOUBLE_SPHERE> { static constexpr int DEPTH = 3, BLOCK = 256; };
+template <> struct LinStream<ACM_MODEL_EUCM> { static constexpr int DEPTH = 3, BLOCK = 256; };
+template <> struct LinStream<ACM_MODEL_UCM> { static constexpr int DEPTH = 2, BLOCK = 256; };
+template <> struct LinStream<ACM_MODEL_FOV> { static constexpr int DEPTH = 3, BLOCK = 128; };
+template <> struct LinStream<ACM_MODEL_RADTAN> { static constexpr int DEPTH = 2, BLOCK = 256; };
+#endif
+template <> struct LinStream<ACM_MODEL_KANNALA_BRANDT> { static constexpr int DEPTH = 0, BLOCK = 128; };
+
 template <int M, int KIND, int BS>
 __global__ void __launch_bounds__(BS) linearize_kernel(LinParams hp, LmState* __restrict__ lm, int fuse_step, PeerArgs peer,
                                                        const double2* __restrict__ X,
@@ -308,12 +324,47 @@ __global__ void __launch_bounds__(BS) linearize_kernel(LinParams hp, LmState* __
 #pragma unroll
     for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
 
-    // Software-pipelined stream: the five 16-byte loads of the next pair of points are in flight
-    // while the current pair is evaluated, so that the few resident warps (accumulators cost
-    // registers) still keep enough bytes in flight to cover the HBM latency.
     const size_t npairs = n >> 1;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr int DEPTH = LinStream<M>::DEPTH;
+    if constexpr (DEPTH > 0) {
+    // cp.async ring: every thread keeps DEPTH packets (5 x 16 B each) in flight in its own
+    // shared-memory slots -- deeper than a register prefetch could afford -- and reads them back with
+    // five conflict-free LDS.128.  Only the owning thread touches a slot, so wait_group is all the
+    // synchronisation needed.  ring[stage][array][thread].
+    extern __shared__ double2 lin_ring[];
+    const double2* const src[5] = {X, Y, Z, U, V};
+    auto issue = [&](int stage, size_t idx) {
+        if (idx < npairs) {
+#pragma unroll
+            for (int a = 0; a < 5; ++a) {
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&lin_ring[(stage * 5 + a) * BS + threadIdx.x]);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src[a] + idx) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#pragma unroll
+    for (int s = 0; s < DEPTH; ++s) issue(s, i + (size_t)s * stride);
+    int stage = 0;
+#pragma unroll 1
+    while (i < npairs) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH > 0 ? DEPTH - 1 : 0) : "memory");
+        const double2 x = lin_ring[(stage * 5 + 0) * BS + threadIdx.x], y = lin_ring[(stage * 5 + 1) * BS + threadIdx.x],
+                      z = lin_ring[(stage * 5 + 2) * BS + threadIdx.x], u = lin_ring[(stage * 5 + 3) * BS + threadIdx.x],
+                      v = lin_ring[(stage * 5 + 4) * BS + threadIdx.x];
+        LM_::point(acc, p, x.x, y.x, z.x, u.x, v.x);
+        LM_::point(acc, p, x.y, y.y, z.y, u.y, v.y);
+        issue(stage, i + (size_t)DEPTH * stride);  // after the packet has been consumed
+        stage = (stage + 1 == DEPTH) ? 0 : stage + 1;
+        i += stride;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else {
+    // Software-pipelined stream: the five 16-byte loads of the next pair of points are in flight
+    // while the current pair is evaluated, so that the few resident warps (accumulators cost
+    // registers) still keep enough bytes in flight to cover the HBM latency.
     double2 x, y, z, u, v;
     if (i < npairs) { x = __ldcs(X + i); y = __ldcs(Y + i); z = __ldcs(Z + i); u = __ldcs(U + i); v = __ldcs(V + i); }
 #pragma unroll 1
@@ -325,6 +376,7 @@ __global__ void __launch_bounds__(BS) linearize_kernel(LinParams hp, LmState* __
         LM_::point(acc, p, x.y, y.y, z.y, u.y, v.y);
         x = x2; y = y2; z = z2; u = u2; v = v2;
         i = nx;
+    }
     }
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
         const size_t t = n - 1;
@@ -358,16 +410,18 @@ template <int M, int KIND, int BS>
 static int32_t launch_linearize_bs(acm_ctx* ctx, const LinParams& hp, LmState* d_lm, int fuse_step, const PeerArgs& peer,
                                    const acm_points* xyz, const acm_points* uv, double invalid_penalty) {
     static int blocks_per_sm = 0;
+    constexpr size_t ring_bytes = (size_t)LinStream<M>::DEPTH * 5 * BS * sizeof(double2);
     if (!blocks_per_sm) {
         int b = 0;
-        ACM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, linearize_kernel<M, KIND, BS>, BS, 0));
+        if (ring_bytes > 0) ACM_CUDA(ctx, cudaFuncSetAttribute(linearize_kernel<M, KIND, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes));
+        ACM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, linearize_kernel<M, KIND, BS>, BS, ring_bytes));
         blocks_per_sm = b > 0 ? b : 1;
     }
     const size_t n = xyz->n;
     int grid = grid_for(ctx, (n >> 1) + 1, BS, blocks_per_sm);
     int32_t rc = acm_ensure_partials(ctx, (size_t)ctx->sm_count * 32 * 64);
     if (rc) return rc;
-    linearize_kernel<M, KIND, BS><<<grid, BS, 0, ctx->stream>>>(
+    linearize_kernel<M, KIND, BS><<<grid, BS, ring_bytes, ctx->stream>>>(
         hp, d_lm, fuse_step, peer, comp<double2>(xyz, 0), comp<double2>(xyz, 1), comp<double2>(xyz, 2), comp<double2>(uv, 0), comp<double2>(uv, 1), n,
         2.0 * invalid_penalty * invalid_penalty, ctx->d_partials, ctx->d_reduce, ctx->d_ticket);
     ACM_CHECK_LAUNCH(ctx);
@@ -382,7 +436,7 @@ static int32_t launch_linearize(acm_ctx* ctx, const LinParams& hp, LmState* d_lm
                                 const acm_points* xyz, const acm_points* uv, double invalid_penalty) {
     static int bs = 0;
     if (!bs) {
-        bs = (M == ACM_MODEL_KANNALA_BRANDT || M == ACM_MODEL_FOV || M == ACM_MODEL_UCM) ? 128 : 256;  // measured, scripts/lin_bench.py
+        bs = LinStream<M>::BLOCK;
         const char* e = getenv("ACM_LIN_BLOCK");
         if (e && (atoi(e) == 128 || atoi(e) == 256)) bs = atoi(e);
     }
