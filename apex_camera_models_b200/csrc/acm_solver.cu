@@ -285,20 +285,27 @@ __device__ __forceinline__ void peer_exchange(const PeerArgs& peer, double* __re
 // prefetch -> cp.async ring): DEPTH > 0 = every thread keeps that many packets in flight in a
 // shared-memory ring fed by cp.async; 0 = the next packet is prefetched into registers.
 //   DS 5.88 -> 6.24 TB/s (3 deep), EUCM 5.63 -> 5.79, UCM 5.83 -> 6.47 (2 deep), FOV 4.50 -> 4.97
-//   (3 deep, 128 threads), RadTan 4.09 -> 4.25 (2 deep); KB (160+ registers) and Pinhole (already at
-//   7.1 TB/s) are faster without the ring.
-template <int M> struct LinStream { static constexpr int DEPTH = 0, BLOCK = 256; };
+//   (3 deep, 128 threads), RadTan 4.09 -> 4.25 (2 deep); Pinhole (already at 7.1 TB/s) is faster without the ring.
+// MIN_BLOCKS > 1 caps the registers through __launch_bounds__.
+template <int M> struct LinStreamDefault { static constexpr int DEPTH = 0, BLOCK = 256, MIN_BLOCKS = 0; };
 #ifndef ACM_LIN_NO_RING  // A/B aid: -DACM_LIN_NO_RING builds every model with the register prefetch
-template <> struct LinStream<ACM_MODEL_DOUBLE_SPHERE> { static constexpr int DEPTH = 3, BLOCK = 256; };
-template <> struct LinStream<ACM_MODEL_EUCM> { static constexpr int DEPTH = 3, BLOCK = 256; };
-template <> struct LinStream<ACM_MODEL_UCM> { static constexpr int DEPTH = 2, BLOCK = 256; };
-template <> struct LinStream<ACM_MODEL_FOV> { static constexpr int DEPTH = 3, BLOCK = 128; };
-template <> struct LinStream<ACM_MODEL_RADTAN> { static constexpr int DEPTH = 2, BLOCK = 256; };
+template <> struct LinStreamDefault<ACM_MODEL_DOUBLE_SPHERE> { static constexpr int DEPTH = 3, BLOCK = 256, MIN_BLOCKS = 0; };
+template <> struct LinStreamDefault<ACM_MODEL_EUCM> { static constexpr int DEPTH = 3, BLOCK = 256, MIN_BLOCKS = 0; };
+template <> struct LinStreamDefault<ACM_MODEL_UCM> { static constexpr int DEPTH = 2, BLOCK = 256, MIN_BLOCKS = 0; };
+template <> struct LinStreamDefault<ACM_MODEL_FOV> { static constexpr int DEPTH = 3, BLOCK = 128, MIN_BLOCKS = 0; };
+template <> struct LinStreamDefault<ACM_MODEL_RADTAN> { static constexpr int DEPTH = 2, BLOCK = 256, MIN_BLOCKS = 0; };
 #endif
-template <> struct LinStream<ACM_MODEL_KANNALA_BRANDT> { static constexpr int DEPTH = 0, BLOCK = 128; };
+// KB (37 accumulators, 162 registers): 3 blocks of 128 threads with the register prefetch.  Capping it at 128
+// registers (MIN_BLOCKS = 4, ring 2 deep, 24-byte spill) measured +12 % on one box and -9 % on another, so the
+// spill-free configuration stays.
+template <> struct LinStreamDefault<ACM_MODEL_KANNALA_BRANDT> { static constexpr int DEPTH = 0, BLOCK = 128, MIN_BLOCKS = 0; };
+template <int M> struct LinStream : LinStreamDefault<M> {};
+#ifdef ACM_EXP_MODEL  // tuning aid: -DACM_EXP_MODEL=<id> -DACM_EXP_DEPTH= -DACM_EXP_BLOCK= -DACM_EXP_MINB= overrides one model
+template <> struct LinStream<ACM_EXP_MODEL> { static constexpr int DEPTH = ACM_EXP_DEPTH, BLOCK = ACM_EXP_BLOCK, MIN_BLOCKS = ACM_EXP_MINB; };
+#endif
 
 template <int M, int KIND, int BS>
-__global__ void __launch_bounds__(BS) linearize_kernel(LinParams hp, LmState* __restrict__ lm, int fuse_step, PeerArgs peer,
+__global__ void __launch_bounds__(BS, (BS == LinStream<M>::BLOCK ? LinStream<M>::MIN_BLOCKS : 0)) linearize_kernel(LinParams hp, LmState* __restrict__ lm, int fuse_step, PeerArgs peer,
                                                        const double2* __restrict__ X,
                                                         const double2* __restrict__ Y, const double2* __restrict__ Z,
                                                         const double2* __restrict__ U, const double2* __restrict__ V, size_t n,
