@@ -1,0 +1,216 @@
+"""`camera_converter` on the GPU path (reference bin/camera_converter.rs): load one model from YAML,
+sample correspondences from it, fit every other model (linear estimate -> Levenberg-Marquardt) and
+report the reprojection statistics and the five-region validation.
+
+    python -m apex_camera_models_b200.camera_converter -i kb -p samples/kannala_brandt.yaml -n 500
+    torchrun --nproc-per-node 8 -m apex_camera_models_b200.camera_converter -i kb -p kb.yaml -n 10000000
+
+Flags are the reference's (`-i/--input-model`, `-p/--input-path`, `-n/--num-points`, `-m/--image-path`;
+camera_converter.rs:66-83).  Under torchrun every rank samples its slice of the grid and the fits run on
+the sharded correspondences (normal equations and statistics are combined inside libacm).  The image
+quality diagnostics of the reference (PSNR / SSIM of rendered dot images) are not
+part of this path; `--image-path` is accepted and ignored with a notice.
+"""
+from __future__ import annotations
+
+import argparse
+import math
+import os
+import sys
+import time
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import distributed as D
+from .camera import (CameraModel, DoubleSphereModel, EucmModel, FovModel, Intrinsics, KannalaBrandtModel, PinholeModel, RadTanModel,
+                     UcmModel)
+from .errors import AcmError
+from .optimization import OptimizationCost
+from .runtime import Context, default_context
+from .util import ProjectionError, compute_reprojection_error, sample_points
+
+# camera_converter.rs:86-124
+INPUT_ALIASES = {
+    "kb": KannalaBrandtModel, "kannala_brandt": KannalaBrandtModel, "ds": DoubleSphereModel, "double_sphere": DoubleSphereModel,
+    "radtan": RadTanModel, "rad_tan": RadTanModel, "ucm": UcmModel, "unified": UcmModel, "eucm": EucmModel,
+    "extended_unified": EucmModel, "fov": FovModel, "field_of_view": FovModel, "pinhole": PinholeModel,
+}
+# target order and initial distortion of bin/camera_converter.rs (:364-370 DS, :507-511 KB, :644-650 RadTan, :787-792 UCM,
+# :918-924 EUCM, :1051-1056 FOV)
+TARGETS = [
+    ("Double Sphere", DoubleSphereModel, [0.5, 0.1]),
+    ("Kannala-Brandt", KannalaBrandtModel, [0.0, 0.0, 0.0, 0.0]),
+    ("Radial-Tangential", RadTanModel, [0.0, 0.0, 0.0, 0.0, 0.0]),
+    ("Unified Camera Model", UcmModel, [0.5]),
+    ("Extended Unified Camera Model", EucmModel, [0.5, 1.0]),
+    ("Field-of-View", FovModel, [1.0]),
+]
+REGIONS = [("Center", 0.5), ("Near Center", 0.55), ("Mid Region", 0.65), ("Edge Region", 0.8), ("Far Edge", 0.95)]  # validation.rs:106-112
+
+
+@dataclass
+class ValidationResults:  # validation.rs:21-42
+    region_errors: list
+    average_error: float
+    max_error: float
+    status: str
+    region_data: list = field(default_factory=list)
+
+
+@dataclass
+class ConversionMetrics:  # reporting.rs ConversionMetrics
+    model: CameraModel
+    model_name: str
+    final_reprojection_error: ProjectionError
+    initial_reprojection_error: ProjectionError
+    optimization_time_ms: float
+    convergence_status: str
+    validation_results: ValidationResults
+    iterations: int = 0
+
+
+def load_input_model(model_type: str, path: str, ctx: Context | None = None) -> CameraModel:
+    cls = INPUT_ALIASES.get(model_type.lower())
+    if cls is None:
+        raise ValueError(f"Unsupported input model type: {model_type}. Supported types: kb, ds, radtan, ucm, eucm, pinhole, fov")
+    return cls.load_from_yaml(path, ctx=ctx)
+
+
+def validate_conversion_accuracy(output_model: CameraModel, input_model: CameraModel) -> ValidationResults:
+    """validation.rs:93-213: five test pixels on the diagonal -> unproject with the input model ->
+    project with both -> distance; EXCELLENT < 0.001 px, GOOD < 0.1 px."""
+    res = input_model.get_resolution()
+    w, h = float(res.width), float(res.height)
+    px = np.array([[w * f, h * f] for _, f in REGIONS])
+    rays, st_u = input_model.unproject_batch(px)
+    uv_in, st_a = input_model.project_batch(rays)
+    uv_out, st_b = output_model.project_batch(rays)
+    errors, data, total, worst, valid = [], [], 0.0, 0.0, 0
+    for i, (name, _) in enumerate(REGIONS):
+        if st_u[i] == 0 and st_a[i] == 0 and st_b[i] == 0:
+            e = float(np.hypot(*(uv_in[i] - uv_out[i])))
+            total += e; worst = max(worst, e); valid += 1
+            errors.append(e)
+            data.append((name, tuple(uv_in[i]), tuple(uv_out[i]), e))
+        else:
+            errors.append(math.nan)
+            data.append((name, None, None, math.nan))
+    avg = total / valid if valid else math.nan
+    status = "NEEDS IMPROVEMENT" if math.isnan(avg) else "EXCELLENT" if avg < 0.001 else "GOOD" if avg < 0.1 else "NEEDS IMPROVEMENT"
+    return ValidationResults(errors, avg, worst, status, data)
+
+
+def convert(input_model: CameraModel, name: str, cls, init, points_3d, points_2d) -> ConversionMetrics:
+    """One `convert_to_*` of the reference (camera_converter.rs:355-488 and clones): target initialised with
+    the input intrinsics / resolution, initial error, linear estimate, LM with the converter's bounds and
+    tolerances ("Linear Only" when the solver reports an error), final error, validation."""
+    t0 = time.perf_counter()
+    model = cls(input_model.get_intrinsics(), input_model.get_resolution(), init, ctx=input_model.ctx)
+    initial = compute_reprojection_error(model, points_3d, points_2d)
+    model.linear_estimation(points_3d, points_2d)
+    status, iterations = "Converged", 0
+    try:
+        # the reference reports "Converged" for every Ok(..) of the solver, whatever its stop reason (:417-446)
+        iterations = OptimizationCost(model, points_3d, points_2d).optimize().iterations
+    except AcmError:
+        status = "Linear Only"
+    elapsed = (time.perf_counter() - t0) * 1e3
+    final = compute_reprojection_error(model, points_3d, points_2d)
+    try:
+        val = validate_conversion_accuracy(model, input_model)
+    except AcmError:
+        val = ValidationResults([math.nan] * 5, math.nan, math.nan, "NEEDS IMPROVEMENT")
+    return ConversionMetrics(model, name, final, initial, elapsed, status, val, iterations)
+
+
+def convert_all(input_model: CameraModel, num_points: int, shard=None, log=print):
+    uv, xyz = sample_points(input_model, num_points, device=True, shard=shard)
+    kept = len(uv)
+    metrics = []
+    for name, cls, init in TARGETS:
+        if cls is type(input_model):
+            continue
+        try:
+            metrics.append(convert(input_model, name, cls, init, xyz, uv))
+        except AcmError as e:  # the reference skips a target whose conversion returns Err (camera_converter.rs:232-241)
+            log(f"  {name}: skipped ({e})")
+    return kept, metrics, (uv, xyz)
+
+
+def _fmt_params(m: CameraModel) -> str:
+    i = m.get_intrinsics()
+    dist = ", ".join(f"{n}={v:.6g}" for n, v in zip(m.DISTORTION_NAMES, m.get_distortion()))
+    return f"fx={i.fx:.4f} fy={i.fy:.4f} cx={i.cx:.4f} cy={i.cy:.4f}" + (f" | {dist}" if dist else "")
+
+
+def main(argv=None) -> int:
+    ap = argparse.ArgumentParser(prog="camera_converter", description="Camera model conversion tool (GPU path of apex-camera-models)")
+    ap.add_argument("-i", "--input-model", required=True, help="kb, ds, radtan, ucm, eucm, fov, pinhole")
+    ap.add_argument("-p", "--input-path", required=True, help="input model YAML")
+    ap.add_argument("-n", "--num-points", type=int, default=500)
+    ap.add_argument("-m", "--image-path", default=None)
+    ap.add_argument("-o", "--output-dir", default="output", help="converted models are written here as <model>.yaml")
+    args = ap.parse_args(argv)
+
+    rank, local, world = D.env_rank_world()
+    ctx = default_context() if world == 1 else Context(local)
+    shard = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        D.attach_communicator(ctx)
+        D.attach_peers(ctx)
+        shard = (rank, world)
+    say = print if rank == 0 else (lambda *a, **k: None)
+
+    say("CAMERA MODEL CONVERTER - B200 path of apex-camera-models")
+    say("=========================================================")
+    say(f"Input model: {args.input_model.lower()} -> converting to all supported target models")
+    say(f"Input file: {args.input_path}")
+    say(f"Sample points: {args.num_points}" + (f" (sharded over {world} GPUs)" if world > 1 else ""))
+    if args.image_path:
+        say("Input image: ignored (image-quality diagnostics are outside the GPU path)")
+    input_model = load_input_model(args.input_model, args.input_path, ctx)
+    say(f"\nInput {input_model.get_model_name()} parameters: {_fmt_params(input_model)}")
+    res = input_model.get_resolution()
+    say(f"Resolution: {res.width}x{res.height}")
+
+    t0 = time.perf_counter()
+    kept, metrics, pts = convert_all(input_model, args.num_points, shard, say)
+    total_ms = (time.perf_counter() - t0) * 1e3
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([kept], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        kept = int(t.item())
+    say(f"\nValid 3D-2D correspondences: {kept} / {args.num_points}")
+    say("\nCONVERSION RESULTS")
+    say(f"{'Target model':32s} {'initial px':>12s} {'final px':>12s} {'rmse':>10s} {'max':>10s} {'median':>10s} {'iters':>6s} {'ms':>9s}  status / validation")
+    for m in metrics:
+        f, i0, v = m.final_reprojection_error, m.initial_reprojection_error, m.validation_results
+        say(f"{m.model_name:32s} {i0.mean:12.6f} {f.mean:12.6f} {f.rmse:10.6f} {f.max:10.6f} {f.median:10.6f} {m.iterations:6d} {m.optimization_time_ms:9.3f}  "
+            f"{m.convergence_status} / {v.status} (avg {v.average_error:.6f} px)")
+    say("")
+    for m in metrics:
+        say(f"{m.model_name}: {_fmt_params(m.model)}")
+    say(f"\nTotal (sampling + {len(metrics)} conversions): {total_ms:.2f} ms")
+    if rank == 0 and args.output_dir:
+        os.makedirs(args.output_dir, exist_ok=True)
+        for m in metrics:
+            m.model.save_to_yaml(os.path.join(args.output_dir, m.model.get_model_name() + ".yaml"))
+        say(f"Converted models written to {args.output_dir}/")
+    for p in pts:
+        p.free()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

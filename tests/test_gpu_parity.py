@@ -740,3 +740,55 @@ def test_multi_gpu_converter_pipeline_matches_single_gpu():
                         "--master-port", "29533", os.path.join(root, "scripts", "multi_gpu_check.py")], capture_output=True, text=True,
                        timeout=600, env=env, cwd=root)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+KB_YAML = """cam0:
+  camera_model: kannala_brandt
+  intrinsics: [{fx}, {fy}, {cx}, {cy}]
+  distortion: [{k1}, {k2}, {k3}, {k4}]
+  resolution: [512, 512]
+"""
+
+
+@pytest.mark.gpu
+def test_camera_converter_cli_config1(acm, cameras, tmp_path, capsys):
+    """BASELINE config 1: `camera_converter --input-model kb --input-path samples/kannala_brandt.yaml
+    --num-points 500` through the GPU path; 450 correspondences, README figures (README.md:161-166)."""
+    from apex_camera_models_b200 import camera_converter as cc
+    p = cameras["kannala_brandt"]["params"]
+    y = tmp_path / "kb.yaml"
+    y.write_text(KB_YAML.format(fx=p[0], fy=p[1], cx=p[2], cy=p[3], k1=p[4], k2=p[5], k3=p[6], k4=p[7]))
+    out_dir = tmp_path / "out"
+    assert cc.main(["-i", "kb", "-p", str(y), "-n", "500", "-o", str(out_dir)]) == 0
+    text = capsys.readouterr().out
+    assert "Valid 3D-2D correspondences: 450 / 500" in text
+    kb = cc.load_input_model("kb", str(y))
+    kept, metrics, pts = cc.convert_all(kb, 500)
+    assert kept == 450
+    by = {m.model_name: m for m in metrics}
+    assert [m.model_name for m in metrics] == ["Double Sphere", "Radial-Tangential", "Unified Camera Model",
+                                               "Extended Unified Camera Model", "Field-of-View"]  # KB is the input
+    assert abs(by["Double Sphere"].final_reprojection_error.mean - 0.0077324) < 2e-6      # README "0.008 px"
+    assert abs(by["Unified Camera Model"].final_reprojection_error.mean - 0.1452208) < 2e-6  # README "0.145 px"
+    assert abs(by["Double Sphere"].initial_reprojection_error.mean - 10.0321) < 1e-3      # README "+10.02 px"
+    assert by["Double Sphere"].validation_results.status in ("EXCELLENT", "GOOD")
+    assert by["Radial-Tangential"].final_reprojection_error.mean > 50.0                   # README: "EXPECTED" failure on fisheye input
+    ds = acm.DoubleSphereModel.load_from_yaml(str(out_dir / "double_sphere.yaml"))
+    assert np.allclose(ds.params(), by["Double Sphere"].model.params(), rtol=0, atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_image_undistort_cli(acm, ctx, O, cameras, tmp_path):
+    """bin/image_undistort.rs flags through the GPU path: PNG in, PNG out, bytes equal to the oracle's."""
+    from PIL import Image
+    from apex_camera_models_b200 import image_undistort as iu
+    p = cameras["kannala_brandt"]["params"]
+    y = tmp_path / "kb.yaml"
+    y.write_text(KB_YAML.format(fx=p[0], fy=p[1], cx=p[2], cy=p[3], k1=p[4], k2=p[5], k3=p[6], k4=p[7]))
+    img = O.synth_bytes(0xACE50007, 0, 512 * 512 * 3).reshape(512, 512, 3)
+    Image.fromarray(img, "RGB").save(tmp_path / "in.png")
+    assert iu.main(["-i", str(tmp_path / "in.png"), "-c", str(y), "-o", str(tmp_path / "out.png"), "-m", "kb", "--target-fx", "150.0"]) == 0
+    got = np.asarray(Image.open(tmp_path / "out.png").convert("RGB"))
+    cam = dict(cameras["kannala_brandt"])
+    ref = O.undistort_rgb8(oracle_model(O, cam), [150.0, p[1], p[2], p[3]], img, 1, nthreads=4)
+    assert np.array_equal(got, ref)
