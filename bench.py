@@ -392,7 +392,24 @@ def run_extras(acm, N, lib, ctx, X, UV, n):
         pu[names[mid]] = {"project_ms": ms, "project_gb_s": n * 41 / ms / 1e6, "unproject_ms": ms2, "unproject_gb_s": n * 41 / ms2 / 1e6,
                           "round_trip_fused_ms": ms3, "round_trip_fused_gb_s": n * 66 / ms3 / 1e6}
     out["project_unproject_100M_f64"] = pu
-    ctx.device_free(st); ctx.device_free(st2); UV2.free(); X2.free()
+    UV2.free(); X2.free()
+    # f32 I/O (BASELINE config 2 "f64 and f32"): 21 / 21 / 34 B per point, arithmetic still f64 so the masks stay exact
+    pu32 = {}
+    Xf = acm.Points(ctx, 3, n, N.F32); UVf = acm.Points(ctx, 2, n, N.F32); X2f = acm.Points(ctx, 3, n, N.F32)
+    ctx.check(lib.acm_synth_points3(ctx.handle, SEED, 0, COS_MAX, 0, Xf.handle))
+    for mid in range(7):
+        m = acm.MODEL_CLASSES[mid](acm.Intrinsics(*intr), acm.Resolution(512, 512), dist_init[mid], ctx=ctx)
+        cam = m.camera_block()
+        ms = timeit(lambda: ctx.check(lib.acm_project(ctx.handle, C.byref(cam), Xf.handle, UVf.handle, C.c_void_p(st))))
+        ctx.check(lib.acm_synth_pixels(ctx.handle, 7, 0, 512.0, 512.0, UVf.handle))
+        ms2 = timeit(lambda: ctx.check(lib.acm_unproject(ctx.handle, C.byref(cam), UVf.handle, X2f.handle, C.c_void_p(st))))
+        ms3 = timeit(lambda: ctx.check(lib.acm_project_unproject(ctx.handle, C.byref(cam), Xf.handle, UVf.handle, X2f.handle, C.c_void_p(st), C.c_void_p(st2))))
+        pu32[names[mid]] = {"project_ms": ms, "project_gpts_s": n / ms / 1e6, "project_gb_s": n * 21 / ms / 1e6, "unproject_ms": ms2,
+                            "unproject_gpts_s": n / ms2 / 1e6, "unproject_gb_s": n * 21 / ms2 / 1e6, "round_trip_fused_ms": ms3,
+                            "round_trip_fused_gpts_s": n / ms3 / 1e6, "round_trip_fused_gb_s": n * 34 / ms3 / 1e6}
+    out["project_unproject_100M_f32"] = pu32
+    Xf.free(); UVf.free(); X2f.free()
+    ctx.device_free(st); ctx.device_free(st2)
     return out
 
 
