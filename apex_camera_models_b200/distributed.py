@@ -19,6 +19,34 @@ def env_rank_world() -> tuple[int, int, int]:
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
 
+def bind_to_gpu_numa(local_rank: int) -> list[int] | None:
+    """Pin this process to the CPUs the driver reports as local to GPU `local_rank` (NVML affinity), so that
+    pinned host buffers allocated afterwards land on that NUMA node and the H2D streams of the ranks do not
+    share one socket's memory controllers / inter-socket link.  Returns the CPU list, or None when NVML or
+    the affinity call is unavailable (nothing changed)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        # honour CUDA_VISIBLE_DEVICES: map the local ordinal to the physical index when it is a plain list
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = local_rank
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if local_rank < len(ids) and ids[local_rank].isdigit():
+                index = int(ids[local_rank])
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None
+
+
 def broadcast_bytes(payload: bytes | None, nbytes: int, src: int = 0) -> bytes:
     """Broadcast a fixed-size byte string over the default torch.distributed group (any backend)."""
     import torch

@@ -150,6 +150,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    numa_cpus = None
+    if world > 1 and not args.no_numa_bind:
+        numa_cpus = acm.distributed.bind_to_gpu_numa(local_rank)   # pinned e2e buffers then sit next to their GPU
     ctx = acm.Context(local_rank)
     if world > 1:
         acm.attach_communicator(ctx)          # NCCL: linear estimation, fallback all-reduce
@@ -251,7 +254,8 @@ def run_ours(args):
             el = float(t.item())
         e2e = {"value": ne_pts * world * k / el, "unit": UNIT, "h2d_bytes_per_step": ne_pts * BYTES_PER_POINT,
                "d2h_bytes_per_step": 29 * 8, "steps": k, "points_per_gpu": ne_pts,
-               "api": "acm_linearize_host (pinned nalgebra-layout AoS f64 -> chunked H2D + AoS->SoA + fused pass -> normal equations)"}
+               "api": "acm_linearize_host (pinned nalgebra-layout AoS f64 -> chunked H2D + AoS->SoA + fused pass -> normal equations)",
+               "numa_bound_cpus": len(numa_cpus) if numa_cpus else None}
         ctx.pinned_free(hx); ctx.pinned_free(hu)
 
     extras = None
@@ -428,6 +432,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-lm", action="store_true")
     ap.add_argument("--no-undistort", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true")
     ap.add_argument("--no-peer", action="store_true", help="N > 1: keep the NCCL all-reduce instead of the fused NVLink exchange")
     args = ap.parse_args()
     if args.impl == "reference":
