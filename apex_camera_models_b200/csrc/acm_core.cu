@@ -3,6 +3,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdlib.h>
+#include <cmath>
 
 #include <new>
 
@@ -234,6 +235,14 @@ int32_t acm_make_cam_params(acm_ctx* ctx, const acm_camera* cam, CamParams* c) {
     c->W = (double)cam->width; c->H = (double)cam->height;
     c->has_resolution = (cam->width > 0 && cam->height > 0) ? 1 : 0;
     c->model = cam->model;
+    {   // reciprocals for the exact division by the (kernel-invariant) focal lengths, see acm_div_by()
+        volatile double one = 1.0, fx = c->fx, fy = c->fy;
+        c->ifx = one / fx; c->ify = one / fy;
+        int ex = 0, ey = 0;
+        const bool okx = std::isnormal(c->fx) && (frexp(c->fx, &ex), ex >= -99 && ex <= 101);
+        const bool oky = std::isnormal(c->fy) && (frexp(c->fy, &ey), ey >= -99 && ey <= 101);
+        c->fast_div = (okx && oky) ? 1 : 0;
+    }
     // per-model constants, in the reference's operation order (volatile: no host-side contraction)
     volatile double alpha = c->d[0];
     switch (cam->model) {

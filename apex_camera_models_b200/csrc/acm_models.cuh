@@ -19,10 +19,53 @@ __device__ __forceinline__ bool acm_outside(const CamParams& c, double u, double
 }
 
 // nalgebra normalize(): n = sqrt((x*x + y*y) + z*z), each component divided by n
-__device__ __forceinline__ void acm_normalize(double x, double y, double z, double& ox, double& oy, double& oz) {
+__device__ __forceinline__ void acm_normalize_ieee(double x, double y, double z, double& ox, double& oy, double& oz) {
     double n = sqrt(x * x + y * y + z * z);
     ox = x / n; oy = y / n; oz = z / n;
 }
+
+// --- exact decisions, fast tails -----------------------------------------------------------
+// unproject has two kinds of arithmetic.  Everything a validity test (or a branch between two
+// formulas) depends on is evaluated exactly as the reference does -- separately rounded IEEE
+// operations in the reference's order -- so the status bytes are bit-exact.  Three rewrites there
+// are bit-IDENTICAL, not approximations: (u - cx) / fx through acm_div_by() with the host's RN(1/fx);
+// RadTan's four divisions by one determinant through ONE IEEE reciprocal + acm_div_by(); and
+// `sqrt(s) < t` / `sqrt(s) > t` as `s < S` / `s > S'` with the exact double thresholds of the
+// correctly rounded sqrt.  What follows the last test only has to meet the 1e-9 relative bar of the
+// values; there the IEEE divisions and square roots (three divisions in normalize() alone) become a
+// MUFU-seeded reciprocal / rsqrt (<= 2 ulp, acm_math.cuh).  unproject<true> keeps IEEE tails: sample_points uses it, so the
+// correspondences handed to the solver stay bit-identical to the reference's for the arithmetic-only models;
+// -DACM_IEEE_TAILS makes it the default everywhere (A/B aid).
+#ifdef ACM_IEEE_TAILS
+#define ACM_TAIL_DEFAULT true
+#else
+#define ACM_TAIL_DEFAULT false
+#endif
+template <bool IEEE>
+__device__ __forceinline__ void acm_normalize(double x, double y, double z, double& ox, double& oy, double& oz) {
+    if (IEEE) { acm_normalize_ieee(x, y, z, ox, oy, oz); return; }
+    const double inv = acm_rsqrt(__fma_rn(z, z, __fma_rn(y, y, __dmul_rn(x, x))));
+    ox = x * inv; oy = y * inv; oz = z * inv;
+}
+template <bool IEEE> __device__ __forceinline__ double acm_tail_div(double a, double b) { return IEEE ? a / b : a * acm_rcp(b); }
+template <bool IEEE> __device__ __forceinline__ double acm_tail_sqrt(double a) {
+    if (IEEE) return sqrt(a);
+    double inv;
+    return acm_sqrt_inv(a, inv);
+}
+
+// (u - cx) / fx, (v - cy) / fy: bit-identical to the IEEE division (see acm_div_by)
+__device__ __forceinline__ double acm_mx(const CamParams& c, double u) {
+    const double a = u - c.cx;
+    return c.fast_div ? acm_div_by(a, c.fx, c.ifx) : a / c.fx;
+}
+__device__ __forceinline__ double acm_my(const CamParams& c, double v) {
+    const double a = v - c.cy;
+    return c.fast_div ? acm_div_by(a, c.fy, c.ify) : a / c.fy;
+}
+#define ACM_SQRT_LT_1EM6 0x1.19799812dea10p-40  // sqrt(s) <  1e-6   <=>  s <  this   (correctly rounded sqrt)
+#define ACM_SQRT_GT_1EM6 0x1.19799812dea11p-40  // sqrt(s) >  1e-6   <=>  s >  this
+#define ACM_SQRT_GT_2M26 0x1.0000000000001p-52  // sqrt(s) >  2^-26  <=>  s >  this
 
 template <int M> struct CamModel;
 
@@ -36,11 +79,12 @@ template <> struct CamModel<ACM_MODEL_PINHOLE> {
         if (BOUNDS && acm_outside(c, u, v)) return ACM_PROJECTION_OUTSIDE_IMAGE;
         return ACM_POINT_OK;
     }
+    template <bool IEEE = ACM_TAIL_DEFAULT>
     static __device__ __forceinline__ int unproject(const CamParams& c, double u, double v, double& rx, double& ry, double& rz) {
         if (acm_outside(c, u, v)) return ACM_POINT_IS_OUTSIDE_IMAGE;
-        double mx = (u - c.cx) / c.fx, my = (v - c.cy) / c.fy;
+        double mx = acm_mx(c, u), my = acm_my(c, v);
         double r2 = mx * mx + my * my;
-        double ninv = 1.0 / sqrt(1.0 + r2);
+        double ninv = 1.0 / sqrt(1.0 + r2);   // IEEE: the kernel is HBM-bound either way, and the values stay bit-identical
         rx = mx * ninv; ry = my * ninv; rz = ninv;
         return ACM_POINT_OK;
     }
@@ -64,10 +108,11 @@ template <> struct CamModel<ACM_MODEL_RADTAN> {
         if (BOUNDS && acm_outside(c, u, v)) return ACM_PROJECTION_OUTSIDE_IMAGE;
         return ACM_POINT_OK;
     }
+    template <bool IEEE = ACM_TAIL_DEFAULT>
     static __device__ int unproject(const CamParams& c, double u, double v, double& rx, double& ry, double& rz) {
         if (acm_outside(c, u, v)) return ACM_POINT_IS_OUTSIDE_IMAGE;
         const double k1 = c.d[0], k2 = c.d[1], p1 = c.d[2], p2 = c.d[3], k3 = c.d[4];
-        const double tx = (u - c.cx) / c.fx, ty = (v - c.cy) / c.fy;
+        const double tx = acm_mx(c, u), ty = acm_my(c, v);
         double px = tx, py = ty;
         for (int it = 0; it < 100; ++it) {
             double x = px, y = py;
@@ -78,7 +123,7 @@ template <> struct CamModel<ACM_MODEL_RADTAN> {
             double xe = x * rad + 2.0 * p1 * x * y + p2 * (r2 + 2.0 * x * x);
             double ye = y * rad + p1 * (r2 + 2.0 * y * y) + 2.0 * p2 * x * y;
             double ex = xe - tx, ey = ye - ty;
-            if (sqrt(ex * ex + ey * ey) < 1e-6) break;
+            if (ex * ex + ey * ey < ACM_SQRT_LT_1EM6) break;   // error.norm() < 1e-6, rad_tan.rs:460
             double dr_dx = 2.0 * x, dr_dy = 2.0 * y;
             double common = k1 + 2.0 * k2 * r2 + 3.0 * k3 * r4;
             double drad_dx = common * dr_dx, drad_dy = common * dr_dy;
@@ -88,14 +133,19 @@ template <> struct CamModel<ACM_MODEL_RADTAN> {
             double j11 = rad + y * drad_dy + p1 * (dr_dy + 4.0 * y) + 2.0 * p2 * x;
             double det = j00 * j11 - j10 * j01;   // nalgebra Matrix2::try_inverse
             if (det == 0.0) return ACM_POINT_NUMERICAL_ERROR;
-            double i00 = j11 / det, i01 = -j01 / det, i10 = -j10 / det, i11 = j00 / det;
+            double i00, i01, i10, i11;
+            if (acm_exp_ok(det)) {   // one IEEE reciprocal, four bit-identical quotients
+                const double idet = 1.0 / det;
+                i00 = acm_div_by(j11, det, idet); i01 = acm_div_by(-j01, det, idet);
+                i10 = acm_div_by(-j10, det, idet); i11 = acm_div_by(j00, det, idet);
+            } else { i00 = j11 / det; i01 = -j01 / det; i10 = -j10 / det; i11 = j00 / det; }
             double dx = i00 * ex + i01 * ey;
             double dy = i10 * ex + i11 * ey;
             px -= dx; py -= dy;
-            if (sqrt(dx * dx + dy * dy) < 1e-6) break;
+            if (dx * dx + dy * dy < ACM_SQRT_LT_1EM6) break;   // delta.norm() < 1e-6, rad_tan.rs:500
             if (it == 99) return ACM_POINT_NUMERICAL_ERROR;
         }
-        acm_normalize(px, py, 1.0, rx, ry, rz);
+        acm_normalize<IEEE>(px, py, 1.0, rx, ry, rz);
         return ACM_POINT_OK;
     }
 };
@@ -120,11 +170,12 @@ template <> struct CamModel<ACM_MODEL_KANNALA_BRANDT> {
         v = c.fy * thd * yr + c.cy;
         return ACM_POINT_OK;  // no image-bounds test in the reference
     }
+    template <bool IEEE = ACM_TAIL_DEFAULT>
     static __device__ int unproject(const CamParams& c, double u, double v, double& rx, double& ry, double& rz) {
         if (c.has_resolution && acm_outside(c, u, v)) return ACM_POINT_IS_OUTSIDE_IMAGE;
         const double k1 = c.d[0], k2 = c.d[1], k3 = c.d[2], k4 = c.d[3];
-        double mx = (u - c.cx) / c.fx, my = (v - c.cy) / c.fy;
-        double ru = sqrt(mx * mx + my * my);
+        double mx = acm_mx(c, u), my = acm_my(c, v);
+        double ru = sqrt(mx * mx + my * my);   // IEEE: ru enters the Newton iteration and its convergence tests
         ru = fmin(ru, 3.14159265358979323846 / 2.0);
         double th = ru;
         bool converged = true;
@@ -145,10 +196,16 @@ template <> struct CamModel<ACM_MODEL_KANNALA_BRANDT> {
         }
         if (!converged) return ACM_POINT_NUMERICAL_ERROR;
         double xc, yc;
-        if (fabs(ru) < ACM_EPS) { xc = 0.0; yc = 0.0; } else { xc = mx / ru; yc = my / ru; }
+        if (IEEE) {
+            if (fabs(ru) < ACM_EPS) { xc = 0.0; yc = 0.0; } else { xc = mx / ru; yc = my / ru; }
+        } else {
+            const double iru = acm_rcp(ru);
+            const bool axis = fabs(ru) < ACM_EPS;
+            xc = axis ? 0.0 : mx * iru; yc = axis ? 0.0 : my * iru;
+        }
         double st, ct;
         sincos(th, &st, &ct);
-        acm_normalize(st * xc, st * yc, ct, rx, ry, rz);
+        acm_normalize<IEEE>(st * xc, st * yc, ct, rx, ry, rz);
         return ACM_POINT_OK;
     }
 };
@@ -167,18 +224,19 @@ template <> struct CamModel<ACM_MODEL_UCM> {
         v = c.fy * (y / den) + c.cy;
         return ACM_POINT_OK;
     }
+    template <bool IEEE = ACM_TAIL_DEFAULT>
     static __device__ __forceinline__ int unproject(const CamParams& c, double u, double v, double& rx, double& ry, double& rz) {
         const double alpha = c.d[0];
         double gamma = 1.0 - alpha;
         double xi = c.k2;
-        double mx = (u - c.cx) / c.fx * gamma, my = (v - c.cy) / c.fy * gamma;
+        double mx = acm_mx(c, u) * gamma, my = acm_my(c, v) * gamma;
         double r2 = mx * mx + my * my;
-        double num = xi + sqrt(1.0 + (1.0 - xi * xi) * r2);
         double den = 1.0 - r2;
         bool cond = (alpha > 0.5) ? (r2 <= c.k1) : true;
         if (den < ACM_PRECISION || !cond) return ACM_POINT_IS_OUTSIDE_IMAGE;
-        double coeff = num / den;
-        acm_normalize(coeff * mx, coeff * my, coeff - xi, rx, ry, rz);
+        double num = xi + acm_tail_sqrt<IEEE>(1.0 + (1.0 - xi * xi) * r2);
+        double coeff = acm_tail_div<IEEE>(num, den);
+        acm_normalize<IEEE>(coeff * mx, coeff * my, coeff - xi, rx, ry, rz);
         return ACM_POINT_OK;
     }
 };
@@ -198,19 +256,19 @@ template <> struct CamModel<ACM_MODEL_EUCM> {
         v = c.fy * (y / den) + c.cy;
         return ACM_POINT_OK;
     }
+    template <bool IEEE = ACM_TAIL_DEFAULT>
     static __device__ __forceinline__ int unproject(const CamParams& c, double u, double v, double& rx, double& ry, double& rz) {
         const double alpha = c.d[0], beta = c.d[1];
-        double mx = (u - c.cx) / c.fx, my = (v - c.cy) / c.fy;
+        double mx = acm_mx(c, u), my = acm_my(c, v);
         double r2 = mx * mx + my * my;
         double gamma = 1.0 - alpha;
         double num = 1.0 - r2 * alpha * alpha * beta;
         double det = 1.0 - (alpha - gamma) * beta * r2;
-        double den = gamma + alpha * sqrt(det);
         bool cond = !(alpha > 0.5 && r2 > c.k1);
         if (det < ACM_PRECISION || !cond) return ACM_POINT_IS_OUTSIDE_IMAGE;
-        double mz = num / den;
-        double norm = sqrt(mx * mx + my * my + mz * mz);
-        rx = mx / norm; ry = my / norm; rz = mz / norm;
+        double den = gamma + alpha * acm_tail_sqrt<IEEE>(det);
+        double mz = acm_tail_div<IEEE>(num, den);
+        acm_normalize<IEEE>(mx, my, mz, rx, ry, rz);
         return ACM_POINT_OK;
     }
 };
@@ -232,21 +290,31 @@ template <> struct CamModel<ACM_MODEL_DOUBLE_SPHERE> {
         v = c.fy * (y / den) + c.cy;
         return ACM_POINT_OK;
     }
+    template <bool IEEE = ACM_TAIL_DEFAULT>
     static __device__ __forceinline__ int unproject(const CamParams& c, double u, double v, double& rx, double& ry, double& rz) {
         const double alpha = c.d[0], xi = c.d[1];
         double gamma = 1.0 - alpha;
-        double mx = (u - c.cx) / c.fx, my = (v - c.cy) / c.fy;
+        double mx = acm_mx(c, u), my = acm_my(c, v);
         double r2 = (mx * mx) + (my * my);
         bool cond = true;
         if (alpha > 0.5) { if (r2 > c.k1) cond = false; }
         if (alpha != 0.0 && !cond) return ACM_POINT_IS_OUTSIDE_IMAGE;
-        double mz = (1.0 - alpha * alpha * r2) / (alpha * sqrt(1.0 - (2.0 * alpha - 1.0) * r2) + gamma);
+        // mz feeds the last validity test (den < PRECISION).  The fast quotient is within 4 ulp, so den is
+        // within ~1e-15 relative of the reference's; only inside a 1e-12 band around the threshold (never
+        // reached with 0 < alpha <= 1, where r2 < 1e-3 implies mz ~ 1) is mz redone with IEEE operations.
+        const double mz_num = 1.0 - alpha * alpha * r2, mz_arg = 1.0 - (2.0 * alpha - 1.0) * r2;
+        double mz = acm_tail_div<IEEE>(mz_num, alpha * acm_tail_sqrt<IEEE>(mz_arg) + gamma);
         double mz2 = mz * mz;
-        double num = mz * xi + sqrt(mz2 + (1.0 - xi * xi) * r2);
         double den = mz2 + r2;
+        if (!IEEE && fabs(den - ACM_PRECISION) < 1e-12) {
+            mz = mz_num / (alpha * sqrt(mz_arg) + gamma);
+            mz2 = mz * mz;
+            den = mz2 + r2;
+        }
         if (den < ACM_PRECISION) return ACM_POINT_IS_OUTSIDE_IMAGE;
-        double coeff = num / den;
-        acm_normalize(coeff * mx, coeff * my, coeff * mz - xi, rx, ry, rz);
+        double num = mz * xi + acm_tail_sqrt<IEEE>(mz2 + (1.0 - xi * xi) * r2);
+        double coeff = acm_tail_div<IEEE>(num, den);
+        acm_normalize<IEEE>(coeff * mx, coeff * my, coeff * mz - xi, rx, ry, rz);
         return ACM_POINT_OK;
     }
 };
@@ -268,20 +336,33 @@ template <> struct CamModel<ACM_MODEL_FOV> {
         v = c.fy * my + c.cy;
         return ACM_POINT_OK;
     }
+    template <bool IEEE = ACM_TAIL_DEFAULT>
     static __device__ __forceinline__ int unproject(const CamParams& c, double u, double v, double& rx, double& ry, double& rz) {
         const double w = c.d[0];
         double mul2 = c.k0 * 2.0;
-        double mx = (u - c.cx) / c.fx, my = (v - c.cy) / c.fy;
+        double mx = acm_mx(c, u), my = acm_my(c, v);
         double r2 = mx * mx + my * my;
-        double rd = sqrt(r2);
         double x, y;
-        if (mul2 > ACM_SQRT_EPS && rd > ACM_SQRT_EPS) {
+        if (IEEE) {
+            double rd = sqrt(r2);
+            if (mul2 > ACM_SQRT_EPS && rd > ACM_SQRT_EPS) {
+                double s, co;
+                sincos(rd * w, &s, &co);
+                double ru = s / (rd * mul2);
+                x = mx * ru / co; y = my * ru / co;
+            } else { x = mx; y = my; }
+        }
+        // the branch (two formulas that do NOT agree at the seam, fov.rs:349-357) is decided exactly:
+        // sqrt(r2) > sqrt(EPS)  <=>  r2 > ACM_SQRT_GT_2M26; the values behind it need 1e-9 only
+        else if (mul2 > ACM_SQRT_EPS && r2 > ACM_SQRT_GT_2M26) {
+            double ird;
+            const double rd = acm_sqrt_inv(r2, ird);
             double s, co;
             sincos(rd * w, &s, &co);
-            double ru = s / (rd * mul2);
-            x = mx * ru / co; y = my * ru / co;
+            const double k = s * ird * acm_rcp(mul2 * co);   // (sin / (rd mul2)) / cos
+            x = mx * k; y = my * k;
         } else { x = mx; y = my; }
-        acm_normalize(x, y, 1.0, rx, ry, rz);
+        acm_normalize<IEEE>(x, y, 1.0, rx, ry, rz);
         return ACM_POINT_OK;
     }
 };

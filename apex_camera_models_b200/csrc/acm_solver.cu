@@ -147,7 +147,7 @@ __device__ __forceinline__ void lm_step_block(LmState* __restrict__ s, const dou
     if (sh->done) return;
     if (tid == 0) {
         double cost_t, cnt;
-        LinOps<M, KIND>::unpack(w->red, w->Ht, w->gt, &cost_t, &cnt);
+        LinOps<M, KIND>::unpack(w->red, sh->xt, w->Ht, w->gt, &cost_t, &cnt);  // the pass ran at the trial point xt
         s_cost_t = cost_t; s_cnt = cnt;
         flag_accept = lm_decide(P, sh, w, cost_t) ? 1 : 0;
     }
@@ -285,7 +285,8 @@ __device__ __forceinline__ void peer_exchange(const PeerArgs& peer, double* __re
 // prefetch -> cp.async ring): DEPTH > 0 = every thread keeps that many packets in flight in a
 // shared-memory ring fed by cp.async; 0 = the next packet is prefetched into registers.
 //   DS 5.88 -> 6.24 TB/s (3 deep), EUCM 5.63 -> 5.79, UCM 5.83 -> 6.47 (2 deep), FOV 4.50 -> 4.97
-//   (3 deep, 128 threads), RadTan 4.09 -> 4.25 (2 deep); Pinhole (already at 7.1 TB/s) is faster without the ring.
+//   (3 deep, 128 threads), RadTan 4.09 -> 4.25 (2 deep; 5.1 with the structured accumulation; 128-thread blocks capped at 168
+//   registers for 12 warps/SM measured 4.2-4.8); Pinhole (already at 7.1 TB/s) is faster without the ring.
 // MIN_BLOCKS > 1 caps the registers through __launch_bounds__.
 template <int M> struct LinStreamDefault { static constexpr int DEPTH = 0, BLOCK = 256, MIN_BLOCKS = 0; };
 #ifndef ACM_LIN_NO_RING  // A/B aid: -DACM_LIN_NO_RING builds every model with the register prefetch
@@ -295,10 +296,10 @@ template <> struct LinStreamDefault<ACM_MODEL_UCM> { static constexpr int DEPTH 
 template <> struct LinStreamDefault<ACM_MODEL_FOV> { static constexpr int DEPTH = 3, BLOCK = 128, MIN_BLOCKS = 0; };
 template <> struct LinStreamDefault<ACM_MODEL_RADTAN> { static constexpr int DEPTH = 2, BLOCK = 256, MIN_BLOCKS = 0; };
 #endif
-// KB (37 accumulators, 162 registers): 3 blocks of 128 threads with the register prefetch.  Capping it at 128
-// registers (MIN_BLOCKS = 4, ring 2 deep, 24-byte spill) measured +12 % on one box and -9 % on another, so the
-// spill-free configuration stays.
-template <> struct LinStreamDefault<ACM_MODEL_KANNALA_BRANDT> { static constexpr int DEPTH = 0, BLOCK = 128, MIN_BLOCKS = 0; };
+// KB (37 accumulators, 166 registers): 3 blocks of 128 threads.  Same-box A/B (scripts/ab_lin.sh; boxes of the pool differ by
+// up to 40 % on this FP64-bound kernel, so only same-box comparisons count): register prefetch 4.42 TB/s, ring 1 deep 3.95,
+// 2 deep 4.51, 3 deep 4.59; capped at 128 registers (MIN_BLOCKS = 4, 36-byte spill) 4.19.
+template <> struct LinStreamDefault<ACM_MODEL_KANNALA_BRANDT> { static constexpr int DEPTH = 3, BLOCK = 128, MIN_BLOCKS = 0; };
 template <int M> struct LinStream : LinStreamDefault<M> {};
 #ifdef ACM_EXP_MODEL  // tuning aid: -DACM_EXP_MODEL=<id> -DACM_EXP_DEPTH= -DACM_EXP_BLOCK= -DACM_EXP_MINB= overrides one model
 template <> struct LinStream<ACM_EXP_MODEL> { static constexpr int DEPTH = ACM_EXP_DEPTH, BLOCK = ACM_EXP_BLOCK, MIN_BLOCKS = ACM_EXP_MINB; };
@@ -521,7 +522,7 @@ static int32_t unpack_host(acm_ctx* ctx, const acm_camera* cam, int32_t kind, co
     memset(out, 0, sizeof(*out));
     out->n_params = cam->n_params;
     double cnt = 0.0;
-    ACM_DISPATCH_LIN(cam->model, kind, (LinOps<M, KIND>::unpack(r, out->H, out->g, &out->cost, &cnt)));
+    ACM_DISPATCH_LIN(cam->model, kind, (LinOps<M, KIND>::unpack(r, cam->params, out->H, out->g, &out->cost, &cnt)));
     out->n_valid = (uint64_t)cnt;
     return ACM_OK;
 }

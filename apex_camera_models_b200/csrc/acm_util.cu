@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(256) sample_unproject_kernel(const __grid_cons
         const size_t i = (first + idx) / (size_t)ncx, j = (first + idx) % (size_t)ncx;
         const double x = ((double)j + 0.5) * cell_w, y = ((double)i + 0.5) * cell_h;
         double rx, ry, rz;
-        int st = CamModel<M>::unproject(c, x, y, rx, ry, rz);
+        int st = CamModel<M>::template unproject<true>(c, x, y, rx, ry, rz);  // IEEE tails: the solver's inputs stay bit-identical
         k = (st == ACM_POINT_OK && rz > 0.0) ? 1 : 0;
         RX[idx] = rx; RY[idx] = ry; RZ[idx] = rz;
         keep[idx] = (uint8_t)k;

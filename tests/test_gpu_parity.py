@@ -17,7 +17,13 @@ from conftest import load_golden, oracle_model
 pytestmark = pytest.mark.gpu
 
 MODELS = ["pinhole", "rad_tan", "kannala_brandt", "ucm", "eucm", "double_sphere", "fov"]
-EXACT = {"pinhole", "rad_tan", "ucm", "eucm", "double_sphere"}  # +,-,*,/,sqrt only => bit-exact values
+EXACT = {"pinhole", "rad_tan", "ucm", "eucm", "double_sphere"}  # project: +,-,*,/,sqrt only => bit-exact values
+# unproject: everything a validity test depends on is evaluated exactly (status bytes bit-exact); the
+# arithmetic AFTER the last test (normalisation, final quotients / roots) uses <= 2 ulp reciprocals, so
+# the values of the arithmetic-only models agree within a few ulp instead of bit for bit (pinhole: still
+# bit for bit).  The bar of the contract is 1e-9 relative; these kernels are held to 1e-13.
+UNPROJECT_EXACT = {"pinhole"}
+ULP_RTOL, ULP_ATOL = 1e-13, 1e-13
 UNIFIED = {"ucm", "eucm", "double_sphere"}
 RTOL = 1e-9
 
@@ -48,6 +54,8 @@ def assert_close_where_valid(a, b, ok, name, exact_names=EXACT):
     assert np.array_equal(np.isnan(a), np.isnan(b))
     if name in exact_names:
         assert np.array_equal(a[ok], b[ok]), f"{name}: values are not bit-identical"
+    elif name in EXACT:  # arithmetic-only model on the unproject side: a few ulp
+        assert np.allclose(a[ok], b[ok], rtol=ULP_RTOL, atol=ULP_ATOL), f"{name}: {np.nanmax(np.abs(a[ok] - b[ok]))}"
     else:
         assert np.allclose(a[ok], b[ok], rtol=RTOL, atol=1e-13)
 
@@ -76,7 +84,7 @@ def test_unproject_matches_oracle(acm, ctx, O, cameras, name):
     ray, st = m.unproject_batch(px)
     rayo, sto = O.unproject(om, px)
     assert np.array_equal(st, sto)
-    assert_close_where_valid(ray, rayo, sto == 0, name)
+    assert_close_where_valid(ray, rayo, sto == 0, name, UNPROJECT_EXACT)
 
 
 @pytest.mark.parametrize("name", MODELS)
@@ -94,7 +102,7 @@ def test_fused_round_trip_matches_oracle(acm, ctx, O, cameras, name):
     rayo, suo = O.unproject(om, uv[ok])  # unproject what the device projected (KB / FOV differ in the last ulps)
     assert np.array_equal(su[ok], suo) and np.array_equal(su[~ok], spo[~ok])
     good = np.zeros(n, bool); good[np.flatnonzero(ok)[suo == 0]] = True
-    assert_close_where_valid(ray[ok], rayo, suo == 0, name)
+    assert_close_where_valid(ray[ok], rayo, suo == 0, name, UNPROJECT_EXACT)
     assert np.all(np.isnan(ray[~good]))
     # the direction comes back (the sample UCM / EUCM cameras have alpha > 1, for which the reference's
     # unproject is not the exact inverse: ucm.rs:614-616 uses 1e-4 at one point, tests/ use dot > 0.99)
@@ -158,8 +166,10 @@ def test_random_cameras_project_unproject(acm, ctx, O, cameras, name):
         # DS / EUCM can return NaN rays with status Ok (sqrt of a slightly negative radicand): NaN patterns must match too
         assert np.array_equal(np.isnan(ray), np.isnan(rayo))
         fin = (sto == 0) & ~np.isnan(rayo).any(axis=1)
-        if name in EXACT:
+        if name in UNPROJECT_EXACT:
             assert np.array_equal(ray[fin], rayo[fin])
+        elif name in EXACT:
+            assert np.allclose(ray[fin], rayo[fin], rtol=ULP_RTOL, atol=ULP_ATOL), np.nanmax(np.abs(ray[fin] - rayo[fin]))
         else:
             assert np.allclose(ray[fin], rayo[fin], rtol=RTOL, atol=1e-13)
 
@@ -210,7 +220,7 @@ def test_edge_sizes(acm, ctx, O, cameras, n):
         ray, st = m.unproject_batch(px)
         rayo, sto = O.unproject(om, px)
         assert ray.shape == (n, 3) and np.array_equal(st, sto)
-        assert_close_where_valid(ray, rayo, sto == 0, name)
+        assert_close_where_valid(ray, rayo, sto == 0, name, UNPROJECT_EXACT)
 
 
 @pytest.mark.parametrize("name", MODELS)
