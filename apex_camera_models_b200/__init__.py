@@ -19,6 +19,9 @@ from .optimization import (DoubleSphereOptimizationCost, EucmOptimizationCost, F
                            UcmOptimizationCost, CONVERTER_BOUNDS, CANONICAL_RESIDUAL)
 from .util import (InterpolationMethod, ProjectionError, compute_reprojection_error, sample_points, undistort_image,
                    undistort_images, undistort_map)
+from .image_quality import (ImageQualityMetrics, calculate_psnr, calculate_ssim, compute_image_quality_metrics,
+                            create_combined_projection_image, create_combined_projection_image_on_reference,
+                            create_projection_image, model_projection_visualization)
 from .distributed import attach_communicator, attach_peers, shard_range
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -43,6 +43,10 @@ class LMResult(C.Structure):
                 ("elapsed_ms", C.c_double)]
 
 
+class ImageQuality(C.Structure):
+    _fields_ = [("psnr", C.c_double), ("ssim", C.c_double), ("n_points", C.c_uint64)]
+
+
 class ProjectionError(C.Structure):
     _fields_ = [("rmse", C.c_double), ("min", C.c_double), ("max", C.c_double), ("mean", C.c_double),
                 ("stddev", C.c_double), ("median", C.c_double), ("count", C.c_uint64)]
@@ -100,6 +104,10 @@ SIGNATURES = {
     "acm_reprojection_error": (C.c_int32, [_vp, _cam, _vp, _vp, C.POINTER(ProjectionError)]),
     "acm_sample_points": (C.c_int32, [_vp, _cam, C.c_size_t, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_size_t)]),
     "acm_sample_points_shard": (C.c_int32, [_vp, _cam, C.c_size_t, C.c_int32, C.c_int32, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_size_t)]),
+    "acm_image_psnr": (C.c_int32, [_vp, _vp, _vp, C.c_uint32, C.c_uint32, _dp]),
+    "acm_image_ssim": (C.c_int32, [_vp, _vp, _vp, C.c_uint32, C.c_uint32, _dp]),
+    "acm_draw_points_rgb8": (C.c_int32, [_vp, _vp, _vp, C.c_uint8, C.c_uint8, C.c_uint8, _vp, C.c_uint32, C.c_uint32]),
+    "acm_image_quality_metrics": (C.c_int32, [_vp, _cam, _cam, _vp, C.c_uint32, C.c_uint32, _vp, _vp, C.POINTER(ImageQuality)]),
     "acm_synth_points3": (C.c_int32, [_vp, C.c_uint64, C.c_size_t, C.c_double, C.c_int32, _vp]),
     "acm_synth_pixels": (C.c_int32, [_vp, C.c_uint64, C.c_size_t, C.c_double, C.c_double, _vp]),
     "acm_synth_bytes": (C.c_int32, [_vp, C.c_uint64, C.c_size_t, _vp, C.c_size_t]),

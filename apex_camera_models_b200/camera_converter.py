@@ -8,8 +8,9 @@ report the reprojection statistics and the five-region validation.
 Flags are the reference's (`-i/--input-model`, `-p/--input-path`, `-n/--num-points`, `-m/--image-path`;
 camera_converter.rs:66-83).  Under torchrun every rank samples its slice of the grid and the fits run on
 the sharded correspondences (normal equations and statistics are combined inside libacm).  The image
-quality diagnostics of the reference (PSNR / SSIM of rendered dot images) are not
-part of this path; `--image-path` is accepted and ignored with a notice.
+quality diagnostics of the reference (PSNR / SSIM of the rendered projection images)
+run on the GPU as well (image_quality.py); `--image-path` is the optional reference image the projections
+are drawn on, and the display images go to `<output-dir>/<model>_projection.png` like the reference's.
 """
 from __future__ import annotations
 
@@ -26,6 +27,7 @@ from . import distributed as D
 from .camera import (CameraModel, DoubleSphereModel, EucmModel, FovModel, Intrinsics, KannalaBrandtModel, PinholeModel, RadTanModel,
                      UcmModel)
 from .errors import AcmError
+from .image_quality import ImageQualityMetrics, compute_image_quality_metrics
 from .optimization import OptimizationCost
 from .runtime import Context, default_context
 from .util import ProjectionError, compute_reprojection_error, sample_points
@@ -68,6 +70,7 @@ class ConversionMetrics:  # reporting.rs ConversionMetrics
     convergence_status: str
     validation_results: ValidationResults
     iterations: int = 0
+    image_quality: "ImageQualityMetrics | None" = None   # reporting.rs:36-37
 
 
 def load_input_model(model_type: str, path: str, ctx: Context | None = None) -> CameraModel:
@@ -101,7 +104,23 @@ def validate_conversion_accuracy(output_model: CameraModel, input_model: CameraM
     return ValidationResults(errors, avg, worst, status, data)
 
 
-def convert(input_model: CameraModel, name: str, cls, init, points_3d, points_2d) -> ConversionMetrics:
+def _load_rgb(path: str) -> np.ndarray:
+    """Decode the optional reference image (`--image-path`; load_image, image_quality.rs:225-230).  File decoding is
+    host work outside the GPU path: PIL when the environment has it."""
+    from PIL import Image
+    return np.asarray(Image.open(path).convert("RGB"), dtype=np.uint8)
+
+
+def _save_png(path: str, img: np.ndarray) -> bool:
+    try:
+        from PIL import Image
+    except ImportError:
+        return False
+    Image.fromarray(img).save(path)
+    return True
+
+
+def convert(input_model: CameraModel, name: str, cls, init, points_3d, points_2d, reference_image=None, output_dir=None) -> ConversionMetrics:
     """One `convert_to_*` of the reference (camera_converter.rs:355-488 and clones): target initialised with
     the input intrinsics / resolution, initial error, linear estimate, LM with the converter's bounds and
     tolerances ("Linear Only" when the solver reports an error), final error, validation."""
@@ -121,10 +140,20 @@ def convert(input_model: CameraModel, name: str, cls, init, points_3d, points_2d
         val = validate_conversion_accuracy(model, input_model)
     except AcmError:
         val = ValidationResults([math.nan] * 5, math.nan, math.nan, "NEEDS IMPROVEMENT")
-    return ConversionMetrics(model, name, final, initial, elapsed, status, val, iterations)
+    # compute_image_quality_metrics (camera_converter.rs:465-473; an Err is logged and becomes None)
+    quality = None
+    try:
+        want = output_dir is not None
+        res = compute_image_quality_metrics(input_model, model, points_3d, reference_image, return_image=want)
+        quality, img = res if want else (res, None)
+        if img is not None:  # save_model_projection_image (image_quality.rs:521-536): output/<model>_projection.png
+            _save_png(os.path.join(output_dir, model.get_model_name().lower().replace(" ", "_") + "_projection.png"), img)
+    except AcmError:
+        pass
+    return ConversionMetrics(model, name, final, initial, elapsed, status, val, iterations, quality)
 
 
-def convert_all(input_model: CameraModel, num_points: int, shard=None, log=print):
+def convert_all(input_model: CameraModel, num_points: int, shard=None, log=print, reference_image=None, output_dir=None):
     uv, xyz = sample_points(input_model, num_points, device=True, shard=shard)
     kept = len(uv)
     metrics = []
@@ -132,7 +161,7 @@ def convert_all(input_model: CameraModel, num_points: int, shard=None, log=print
         if cls is type(input_model):
             continue
         try:
-            metrics.append(convert(input_model, name, cls, init, xyz, uv))
+            metrics.append(convert(input_model, name, cls, init, xyz, uv, reference_image, output_dir))
         except AcmError as e:  # the reference skips a target whose conversion returns Err (camera_converter.rs:232-241)
             log(f"  {name}: skipped ({e})")
     return kept, metrics, (uv, xyz)
@@ -171,15 +200,21 @@ def main(argv=None) -> int:
     say(f"Input model: {args.input_model.lower()} -> converting to all supported target models")
     say(f"Input file: {args.input_path}")
     say(f"Sample points: {args.num_points}" + (f" (sharded over {world} GPUs)" if world > 1 else ""))
+    reference_image = None
     if args.image_path:
-        say("Input image: ignored (image-quality diagnostics are outside the GPU path)")
+        reference_image = _load_rgb(args.image_path)
+        say(f"Input image: {args.image_path} ({reference_image.shape[1]}x{reference_image.shape[0]})")
     input_model = load_input_model(args.input_model, args.input_path, ctx)
     say(f"\nInput {input_model.get_model_name()} parameters: {_fmt_params(input_model)}")
     res = input_model.get_resolution()
     say(f"Resolution: {res.width}x{res.height}")
 
     t0 = time.perf_counter()
-    kept, metrics, pts = convert_all(input_model, args.num_points, shard, say)
+    img_dir = args.output_dir if (rank == 0 and args.output_dir) else None
+    if img_dir:
+        os.makedirs(img_dir, exist_ok=True)
+    # every rank takes part in the collectives of the diagnostics; only rank 0 asks for (and saves) the display images
+    kept, metrics, pts = convert_all(input_model, args.num_points, shard, say, reference_image, img_dir)
     total_ms = (time.perf_counter() - t0) * 1e3
     if world > 1:
         import torch
@@ -194,6 +229,10 @@ def main(argv=None) -> int:
         f, i0, v = m.final_reprojection_error, m.initial_reprojection_error, m.validation_results
         say(f"{m.model_name:32s} {i0.mean:12.6f} {f.mean:12.6f} {f.rmse:10.6f} {f.max:10.6f} {f.median:10.6f} {m.iterations:6d} {m.optimization_time_ms:9.3f}  "
             f"{m.convergence_status} / {v.status} (avg {v.average_error:.6f} px)")
+    say("")
+    for m in metrics:   # reporting.rs:198-201
+        if m.image_quality is not None:
+            say(f"{m.model_name}: PSNR {m.image_quality.psnr:.2f} dB, SSIM {m.image_quality.ssim:.4f}")
     say("")
     for m in metrics:
         say(f"{m.model_name}: {_fmt_params(m.model)}")

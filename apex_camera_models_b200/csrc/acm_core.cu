@@ -698,6 +698,15 @@ int32_t acm_allreduce_sum_u64(acm_ctx* ctx, unsigned long long* d_buf, size_t co
     return ACM_OK;
 }
 
+// byte-wise maximum (the OR of 0 / 255 image planes drawn by different ranks)
+int32_t acm_allreduce_max_u8(acm_ctx* ctx, uint8_t* d_buf, size_t count) {
+    if (ctx->n_ranks == 1) return ACM_OK;
+    if (!ctx->comm) return acm_fail(ctx, ACM_ERR_NCCL, "this operation needs an NCCL communicator (acm_comm_init_rank) when ranks > 1");
+    int r = g_nccl.AllReduce(d_buf, d_buf, count, /*ncclUint8*/ 1, /*ncclMax*/ 2, ctx->comm, ctx->stream);
+    if (r != 0) return acm_fail(ctx, ACM_ERR_NCCL, "ncclAllReduce: %s", nccl_err(r));
+    return ACM_OK;
+}
+
 // Bring the first `count` doubles of ctx->d_reduce of every rank to every host: afterwards
 // ctx->h_reduce holds [n_ranks][count] in rank order (stream synchronised).  Every rank writes its
 // vector into its own slot of a zero-padded buffer, so the all-reduce acts as an all-gather and

@@ -128,6 +128,7 @@ int32_t acm_ensure_partials(acm_ctx* ctx, size_t doubles);
 int32_t acm_ensure_scratch(acm_ctx* ctx, size_t bytes);  // ctx->d_scratch holds >= bytes afterwards (256-byte aligned)
 int32_t acm_allreduce_sum_f64(acm_ctx* ctx, double* d_buf, size_t count);
 int32_t acm_allreduce_sum_u64(acm_ctx* ctx, unsigned long long* d_buf, size_t count);
+int32_t acm_allreduce_max_u8(acm_ctx* ctx, uint8_t* d_buf, size_t count);
 int32_t acm_rank_gather_to_host(acm_ctx* ctx, int count);  // d_reduce[0..count) of every rank -> h_reduce[rank][count]
 int32_t acm_points_upload_any(acm_ctx* ctx, acm_points* p, const double* host_aos, size_t n, size_t dst_offset);
 

@@ -233,6 +233,35 @@ int32_t acm_sample_points(acm_ctx* ctx, const acm_camera* cam, size_t n_requeste
 int32_t acm_sample_points_shard(acm_ctx* ctx, const acm_camera* cam, size_t n_requested, int32_t shard, int32_t n_shards,
                                 acm_points** uv_out, acm_points** xyz_out, size_t* n_kept);
 
+/* ---- image-quality diagnostics of the converter (reference src/util/image_quality.rs) ----
+ * Images are RGB8, interleaved, row-major (image::RgbImage), resident in HBM. */
+/* util::calculate_psnr (image_quality.rs:45-89): pixels black in both images are skipped;
+ * +inf for identical (or all-black) images */
+int32_t acm_image_psnr(acm_ctx* ctx, const uint8_t* d_img1, const uint8_t* d_img2, uint32_t width, uint32_t height, double* psnr);
+/* util::calculate_ssim (image_quality.rs:108-210): 3x3 windows over the interior of the
+ * truncated-luma grey images; 1.0 when there is no interior window */
+int32_t acm_image_ssim(acm_ctx* ctx, const uint8_t* d_img1, const uint8_t* d_img2, uint32_t width, uint32_t height, double* ssim);
+/* The radius-2 disc (dx^2 + dy^2 <= 4, clipped) that create_projection_image (:338-373),
+ * create_combined_projection_image[_on_reference] (:389-505) and model_projection_visualization
+ * (:553-616) draw at (round(u), round(v)) of every point, in one colour, onto an existing image.
+ * d_keep (optional) = one byte per point, 0 skips the point. */
+int32_t acm_draw_points_rgb8(acm_ctx* ctx, const acm_points* uv, const uint8_t* d_keep, uint8_t r, uint8_t g, uint8_t b,
+                             uint8_t* d_image, uint32_t width, uint32_t height);
+typedef struct acm_image_quality {
+    double psnr, ssim;
+    uint64_t n_points; /* points kept: both projections Ok and the output projection inside the image */
+} acm_image_quality;
+/* util::compute_image_quality_metrics (image_quality.rs:254-324): project xyz through both models,
+ * keep the points both project and whose OUTPUT projection lies in [0,W) x [0,H), rasterise the
+ * two projection sets (white discs on black), PSNR + SSIM of the two images.  d_combined (optional,
+ * W*H*3 bytes) receives the display image the reference saves: green input discs, then magenta
+ * output discs, over d_reference (optional; NULL = black).  ACM_ERR_ZERO_PROJECTION_POINTS when no
+ * point is kept.  With a communicator attached xyz is this rank's shard and every rank returns the
+ * metrics (and the display image) of the whole set. */
+int32_t acm_image_quality_metrics(acm_ctx* ctx, const acm_camera* input_model, const acm_camera* output_model, const acm_points* xyz,
+                                  uint32_t width, uint32_t height, const uint8_t* d_reference, uint8_t* d_combined,
+                                  acm_image_quality* out);
+
 /* ---- deterministic synthetic inputs, generated in HBM ------------ */
 int32_t acm_synth_points3(acm_ctx* ctx, uint64_t seed, size_t first_index, double cos_theta_max, int32_t adversarial, acm_points* xyz);
 int32_t acm_synth_pixels(acm_ctx* ctx, uint64_t seed, size_t first_index, double width, double height, acm_points* uv);

@@ -98,6 +98,17 @@ int orc_undistort_rgb8(const orc_model* m, const double target[4], const uint8_t
 /* the remap itself: per output pixel source coords (NaN where projection fails) and floor indices */
 void orc_undistort_map(const orc_model* m, const double target[4], double* src_xy /* 2*W*H */);
 
+/* util::image_quality (reference src/util/image_quality.rs; acm_oracle_image.c).  RGB8 interleaved row-major. */
+double orc_image_psnr(const uint8_t* a, const uint8_t* b, uint32_t W, uint32_t H);
+double orc_image_ssim(const uint8_t* a, const uint8_t* b, uint32_t W, uint32_t H);
+void orc_rgb_to_grayscale(const uint8_t* rgb, uint32_t W, uint32_t H, uint8_t* gray);
+void orc_draw_points_rgb8(const double* uv, size_t n, uint8_t r, uint8_t g, uint8_t b, uint8_t* img, uint32_t W, uint32_t H);
+/* compute_image_quality_metrics; combined / reference may be NULL; returns the kept-point count */
+size_t orc_image_quality_metrics(const orc_model* in, const orc_model* out, const double* xyz, size_t n, uint32_t W, uint32_t H,
+                                 const uint8_t* reference, uint8_t* combined, double* psnr, double* ssim);
+/* util::validate_conversion_accuracy (reference src/util/validation.rs:93-213) */
+int orc_validate_conversion(const orc_model* out, const orc_model* in, double errors[5], double* average, double* max_error);
+
 /* deterministic synthetic inputs (transcendental-free so device == host bitwise) */
 uint64_t orc_splitmix64(uint64_t x);
 void orc_synth_points3(uint64_t seed, size_t i0, size_t n, double cos_max, int adversarial, double* xyz);

@@ -84,6 +84,14 @@ def lib():
         L.orc_reprojection_error.restype = C.c_int
         L.orc_undistort_rgb8.argtypes = [mp, dp, u8p, u8p, C.c_int, C.c_int]; L.orc_undistort_rgb8.restype = C.c_int
         L.orc_undistort_map.argtypes = [mp, dp, dp]; L.orc_undistort_map.restype = None
+        L.orc_image_psnr.argtypes = [u8p, u8p, C.c_uint32, C.c_uint32]; L.orc_image_psnr.restype = C.c_double
+        L.orc_image_ssim.argtypes = [u8p, u8p, C.c_uint32, C.c_uint32]; L.orc_image_ssim.restype = C.c_double
+        L.orc_rgb_to_grayscale.argtypes = [u8p, C.c_uint32, C.c_uint32, u8p]; L.orc_rgb_to_grayscale.restype = None
+        L.orc_draw_points_rgb8.argtypes = [dp, C.c_size_t, C.c_uint8, C.c_uint8, C.c_uint8, u8p, C.c_uint32, C.c_uint32]
+        L.orc_draw_points_rgb8.restype = None
+        L.orc_image_quality_metrics.argtypes = [mp, mp, dp, C.c_size_t, C.c_uint32, C.c_uint32, u8p, u8p, dp, dp]
+        L.orc_image_quality_metrics.restype = C.c_size_t
+        L.orc_validate_conversion.argtypes = [mp, mp, dp, dp, dp]; L.orc_validate_conversion.restype = C.c_int
         L.orc_splitmix64.argtypes = [C.c_uint64]; L.orc_splitmix64.restype = C.c_uint64
         L.orc_synth_points3.argtypes = [C.c_uint64, C.c_size_t, C.c_size_t, C.c_double, C.c_int, dp]
         L.orc_synth_points3.restype = None
@@ -222,3 +230,49 @@ def synth_pixels(seed: int, i0: int, n: int, W: float, H: float) -> np.ndarray:
 
 def synth_bytes(seed: int, i0: int, n: int) -> np.ndarray:
     out = np.empty(n, dtype=np.uint8); lib().orc_synth_bytes(seed, i0, n, _u8p(out)); return out
+
+
+# ---- util::image_quality (acm_oracle_image.c) ---------------------------------------------------
+def _img(a):
+    a = np.ascontiguousarray(a, dtype=np.uint8); assert a.ndim == 3 and a.shape[2] == 3
+    return a
+
+
+def image_psnr(a, b) -> float:
+    a, b = _img(a), _img(b); assert a.shape == b.shape
+    return float(lib().orc_image_psnr(_u8p(a), _u8p(b), a.shape[1], a.shape[0]))
+
+
+def image_ssim(a, b) -> float:
+    a, b = _img(a), _img(b); assert a.shape == b.shape
+    return float(lib().orc_image_ssim(_u8p(a), _u8p(b), a.shape[1], a.shape[0]))
+
+
+def rgb_to_grayscale(a) -> np.ndarray:
+    a = _img(a); out = np.empty(a.shape[:2], dtype=np.uint8)
+    lib().orc_rgb_to_grayscale(_u8p(a), a.shape[1], a.shape[0], _u8p(out)); return out
+
+
+def draw_points(img, uv, color) -> np.ndarray:
+    """Draws in place (and returns) radius-2 discs of `color` at the rounded points."""
+    img = _img(img); uv = np.ascontiguousarray(uv, dtype=np.float64).reshape(-1, 2)
+    lib().orc_draw_points_rgb8(_dp(uv), uv.shape[0], color[0], color[1], color[2], _u8p(img), img.shape[1], img.shape[0])
+    return img
+
+
+def image_quality_metrics(m_in: Model, m_out: Model, xyz, W: int, H: int, reference=None, want_image: bool = False):
+    xyz = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)
+    ref = _img(reference) if reference is not None else None
+    comb = np.empty((H, W, 3), dtype=np.uint8) if want_image else None
+    psnr, ssim = C.c_double(), C.c_double()
+    kept = lib().orc_image_quality_metrics(C.byref(m_in), C.byref(m_out), _dp(xyz), xyz.shape[0], W, H,
+                                           _u8p(ref) if ref is not None else None, _u8p(comb) if comb is not None else None,
+                                           C.cast(C.byref(psnr), C.POINTER(C.c_double)), C.cast(C.byref(ssim), C.POINTER(C.c_double)))
+    return kept, psnr.value, ssim.value, comb
+
+
+def validate_conversion(m_out: Model, m_in: Model):
+    err = np.empty(5); avg, mx = C.c_double(), C.c_double()
+    valid = lib().orc_validate_conversion(C.byref(m_out), C.byref(m_in), _dp(err), C.cast(C.byref(avg), C.POINTER(C.c_double)),
+                                          C.cast(C.byref(mx), C.POINTER(C.c_double)))
+    return valid, err, avg.value, mx.value
