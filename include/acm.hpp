@@ -318,4 +318,72 @@ inline std::vector<uint8_t> undistort_image(const std::vector<uint8_t>& image, u
     return out;
 }
 
+// ---- util::image_quality (image_quality.rs) on RGB8 interleaved images (w*h*3 bytes) --------------
+struct ImageQualityMetrics { double psnr, ssim; };   // image_quality.rs:20-26
+
+// RGB8 image staged in HBM for the duration of a call
+class DeviceImage {
+public:
+    DeviceImage(const Context& ctx, size_t bytes, const uint8_t* host = nullptr) : ctx_(ctx), bytes_(bytes) {
+        ctx_.check(acm_device_alloc(ctx_.handle(), bytes ? bytes : 4, &p_));
+        if (bytes && host) ctx_.check(acm_memcpy_h2d(ctx_.handle(), p_, host, bytes));
+        else if (bytes) ctx_.check(acm_memset_d(ctx_.handle(), p_, 0, bytes));
+    }
+    ~DeviceImage() { if (p_) acm_device_free(ctx_.handle(), p_); }
+    DeviceImage(const DeviceImage&) = delete;
+    DeviceImage& operator=(const DeviceImage&) = delete;
+    uint8_t* ptr() const { return static_cast<uint8_t*>(p_); }
+    std::vector<uint8_t> download() const {
+        std::vector<uint8_t> out(bytes_);
+        if (bytes_) { ctx_.check(acm_memcpy_d2h(ctx_.handle(), out.data(), p_, bytes_)); ctx_.check(acm_ctx_sync(ctx_.handle())); }
+        return out;
+    }
+private:
+    const Context& ctx_; size_t bytes_; void* p_ = nullptr;
+};
+
+inline void require_same_size(const std::vector<uint8_t>& a, const std::vector<uint8_t>& b, uint32_t w, uint32_t h) {
+    if (a.size() != b.size() || a.size() != (size_t)w * h * 3)   // image_quality.rs:46-50, :109-113
+        throw CameraModelError(ErrorKind::InvalidParams, "Invalid parameters: Images must have the same dimensions");
+}
+// util::calculate_psnr (image_quality.rs:45-89)
+inline double calculate_psnr(const Context& ctx, const std::vector<uint8_t>& img1, const std::vector<uint8_t>& img2, uint32_t w, uint32_t h) {
+    require_same_size(img1, img2, w, h);
+    DeviceImage a(ctx, img1.size(), img1.data()), b(ctx, img2.size(), img2.data());
+    double out = 0.0;
+    ctx.check(acm_image_psnr(ctx.handle(), a.ptr(), b.ptr(), w, h, &out));
+    return out;
+}
+// util::calculate_ssim (image_quality.rs:108-210)
+inline double calculate_ssim(const Context& ctx, const std::vector<uint8_t>& img1, const std::vector<uint8_t>& img2, uint32_t w, uint32_t h) {
+    require_same_size(img1, img2, w, h);
+    DeviceImage a(ctx, img1.size(), img1.data()), b(ctx, img2.size(), img2.data());
+    double out = 0.0;
+    ctx.check(acm_image_ssim(ctx.handle(), a.ptr(), b.ptr(), w, h, &out));
+    return out;
+}
+// create_projection_image (image_quality.rs:338-373) with one colour: radius-2 discs on black
+inline std::vector<uint8_t> create_projection_image(const Context& ctx, const double* uv_aos, size_t n, uint8_t r, uint8_t g, uint8_t b, uint32_t w, uint32_t h) {
+    DeviceImage img(ctx, (size_t)w * h * 3);
+    Points U(ctx, 2, uv_aos, n);
+    ctx.check(acm_draw_points_rgb8(ctx.handle(), U.handle(), nullptr, r, g, b, img.ptr(), w, h));
+    return img.download();
+}
+// util::compute_image_quality_metrics (image_quality.rs:254-324); `combined` (optional) receives the display image
+inline ImageQualityMetrics compute_image_quality_metrics(const CameraModel& input_model, const CameraModel& output_model, const double* xyz_aos, size_t n,
+                                                         uint32_t w, uint32_t h, const std::vector<uint8_t>* reference = nullptr,
+                                                         std::vector<uint8_t>* combined = nullptr) {
+    const Context& ctx = input_model.ctx();
+    Points X(ctx, 3, xyz_aos, n);
+    const size_t bytes = (size_t)w * h * 3;
+    std::unique_ptr<DeviceImage> ref, comb;
+    if (reference) ref.reset(new DeviceImage(ctx, bytes, reference->data()));
+    if (combined) comb.reset(new DeviceImage(ctx, bytes));
+    acm_camera ci = input_model.block(), co = output_model.block();
+    acm_image_quality out{};
+    ctx.check(acm_image_quality_metrics(ctx.handle(), &ci, &co, X.handle(), w, h, ref ? ref->ptr() : nullptr, comb ? comb->ptr() : nullptr, &out));
+    if (combined) *combined = comb->download();
+    return {out.psnr, out.ssim};
+}
+
 }  // namespace acm

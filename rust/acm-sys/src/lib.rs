@@ -72,6 +72,14 @@ pub struct acm_lm_result {
 
 #[repr(C)]
 #[derive(Clone, Copy, Debug, Default)]
+pub struct acm_image_quality {
+    pub psnr: f64,
+    pub ssim: f64,
+    pub n_points: u64,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
 pub struct acm_projection_error {
     pub rmse: f64,
     pub min: f64,
@@ -138,6 +146,11 @@ extern "C" {
     pub fn acm_reprojection_error(ctx: *mut acm_ctx, cam: *const acm_camera, xyz: *const acm_points, uv: *const acm_points, out: *mut acm_projection_error) -> i32;
     pub fn acm_sample_points(ctx: *mut acm_ctx, cam: *const acm_camera, n_requested: size_t, uv_out: *mut *mut acm_points, xyz_out: *mut *mut acm_points, n_kept: *mut size_t) -> i32;
     pub fn acm_sample_points_shard(ctx: *mut acm_ctx, cam: *const acm_camera, n_requested: size_t, shard: i32, n_shards: i32, uv_out: *mut *mut acm_points, xyz_out: *mut *mut acm_points, n_kept: *mut size_t) -> i32;
+
+    pub fn acm_image_psnr(ctx: *mut acm_ctx, d_img1: *const u8, d_img2: *const u8, width: u32, height: u32, psnr: *mut f64) -> i32;
+    pub fn acm_image_ssim(ctx: *mut acm_ctx, d_img1: *const u8, d_img2: *const u8, width: u32, height: u32, ssim: *mut f64) -> i32;
+    pub fn acm_draw_points_rgb8(ctx: *mut acm_ctx, uv: *const acm_points, d_keep: *const u8, r: u8, g: u8, b: u8, d_image: *mut u8, width: u32, height: u32) -> i32;
+    pub fn acm_image_quality_metrics(ctx: *mut acm_ctx, input_model: *const acm_camera, output_model: *const acm_camera, xyz: *const acm_points, width: u32, height: u32, d_reference: *const u8, d_combined: *mut u8, out: *mut acm_image_quality) -> i32;
 
     pub fn acm_synth_points3(ctx: *mut acm_ctx, seed: u64, first_index: size_t, cos_theta_max: f64, adversarial: i32, xyz: *mut acm_points) -> i32;
     pub fn acm_synth_pixels(ctx: *mut acm_ctx, seed: u64, first_index: size_t, width: f64, height: f64, uv: *mut acm_points) -> i32;

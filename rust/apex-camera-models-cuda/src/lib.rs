@@ -192,3 +192,75 @@ impl<'c> Drop for OptimizationCost<'c> {
         unsafe { sys::acm_points_destroy(self.ctx.0, self.xyz); sys::acm_points_destroy(self.ctx.0, self.uv); }
     }
 }
+
+/// `util::ImageQualityMetrics` (image_quality.rs:20-26).
+#[derive(Debug, Clone)]
+pub struct ImageQualityMetrics { pub psnr: f64, pub ssim: f64 }
+
+/// RGB8 image staged in HBM for the duration of a call.
+struct DeviceImage<'c> { ctx: &'c Context, ptr: *mut std::ffi::c_void, bytes: usize }
+impl<'c> DeviceImage<'c> {
+    fn new(ctx: &'c Context, bytes: usize, host: Option<&[u8]>) -> Result<Self, CameraModelError> {
+        let mut p = ptr::null_mut();
+        let mut rc = unsafe { sys::acm_device_alloc(ctx.0, bytes.max(4), &mut p) };
+        if rc == sys::ACM_OK && bytes > 0 {
+            rc = match host {
+                Some(h) => unsafe { sys::acm_memcpy_h2d(ctx.0, p, h.as_ptr() as *const _, bytes) },
+                None => unsafe { sys::acm_memset_d(ctx.0, p, 0, bytes) },
+            };
+        }
+        if rc != sys::ACM_OK { return Err(ctx.err(rc)); }
+        Ok(DeviceImage { ctx, ptr: p, bytes })
+    }
+    fn download(&self) -> Result<Vec<u8>, CameraModelError> {
+        let mut out = vec![0u8; self.bytes];
+        let mut rc = unsafe { sys::acm_memcpy_d2h(self.ctx.0, out.as_mut_ptr() as *mut _, self.ptr, self.bytes) };
+        if rc == sys::ACM_OK { rc = unsafe { sys::acm_ctx_sync(self.ctx.0) }; }
+        if rc != sys::ACM_OK { Err(self.ctx.err(rc)) } else { Ok(out) }
+    }
+}
+impl<'c> Drop for DeviceImage<'c> { fn drop(&mut self) { unsafe { sys::acm_device_free(self.ctx.0, self.ptr); } } }
+
+/// `util::calculate_psnr(&RgbImage, &RgbImage)` (image_quality.rs:45-89) over raw RGB8 buffers
+/// (`RgbImage::as_raw()`), `width` x `height`.
+pub fn calculate_psnr(ctx: &Context, img1: &[u8], img2: &[u8], width: u32, height: u32) -> Result<f64, CameraModelError> {
+    if img1.len() != img2.len() { return Err(CameraModelError::InvalidParams("Images must have the same dimensions".into())); }
+    let (a, b) = (DeviceImage::new(ctx, img1.len(), Some(img1))?, DeviceImage::new(ctx, img2.len(), Some(img2))?);
+    let mut out = 0.0f64;
+    let rc = unsafe { sys::acm_image_psnr(ctx.0, a.ptr as *const u8, b.ptr as *const u8, width, height, &mut out) };
+    if rc != sys::ACM_OK { Err(ctx.err(rc)) } else { Ok(out) }
+}
+
+/// `util::calculate_ssim` (image_quality.rs:108-210).
+pub fn calculate_ssim(ctx: &Context, img1: &[u8], img2: &[u8], width: u32, height: u32) -> Result<f64, CameraModelError> {
+    if img1.len() != img2.len() { return Err(CameraModelError::InvalidParams("Images must have the same dimensions".into())); }
+    let (a, b) = (DeviceImage::new(ctx, img1.len(), Some(img1))?, DeviceImage::new(ctx, img2.len(), Some(img2))?);
+    let mut out = 0.0f64;
+    let rc = unsafe { sys::acm_image_ssim(ctx.0, a.ptr as *const u8, b.ptr as *const u8, width, height, &mut out) };
+    if rc != sys::ACM_OK { Err(ctx.err(rc)) } else { Ok(out) }
+}
+
+/// `util::compute_image_quality_metrics` (image_quality.rs:254-324) over camera blocks; returns the metrics and,
+/// when `want_image`, the combined display image (green input / magenta output projections over `reference`).
+pub fn compute_image_quality_metrics(ctx: &Context, input_model: &sys::acm_camera, output_model: &sys::acm_camera,
+                                     points_3d: &Matrix3xX<f64>, width: u32, height: u32, reference: Option<&[u8]>, want_image: bool)
+    -> Result<(ImageQualityMetrics, Option<Vec<u8>>), CameraModelError> {
+    let n = points_3d.ncols();
+    let bytes = width as usize * height as usize * 3;
+    let mut xyz = ptr::null_mut();
+    let mut rc = unsafe { sys::acm_points_create(ctx.0, 3, n, sys::ACM_F64, &mut xyz) };
+    if rc == sys::ACM_OK { rc = unsafe { sys::acm_points_upload_aos_f64(ctx.0, xyz, points_3d.as_ptr(), n) }; }
+    if rc != sys::ACM_OK { unsafe { sys::acm_points_destroy(ctx.0, xyz); } return Err(ctx.err(rc)); }
+    let dref = match reference { Some(r) => Some(DeviceImage::new(ctx, bytes, Some(r))?), None => None };
+    let dcomb = if want_image { Some(DeviceImage::new(ctx, bytes, None)?) } else { None };
+    let mut out = sys::acm_image_quality::default();
+    let rc = unsafe {
+        sys::acm_image_quality_metrics(ctx.0, input_model, output_model, xyz, width, height,
+                                       dref.as_ref().map_or(ptr::null(), |d| d.ptr as *const u8),
+                                       dcomb.as_ref().map_or(ptr::null_mut(), |d| d.ptr as *mut u8), &mut out)
+    };
+    unsafe { sys::acm_points_destroy(ctx.0, xyz); }
+    if rc != sys::ACM_OK { return Err(ctx.err(rc)); }   // ACM_ERR_ZERO_PROJECTION_POINTS -> UtilError::ZeroProjectionPoints upstream
+    let img = match dcomb { Some(d) => Some(d.download()?), None => None };
+    Ok((ImageQualityMetrics { psnr: out.psnr, ssim: out.ssim }, img))
+}

@@ -42,8 +42,11 @@ def pipeline(ctx, shard, use_peer):
         lin = [float(v) for v in m.params()]
         res = cost.optimize()
         err = util.compute_reprojection_error(m, xyz, uv)
+        # image-quality diagnostics on the sharded points: every rank gets the metrics of the whole set
+        q, img = acm.compute_image_quality_metrics(kb, m, xyz, return_image=True)
         out[name] = {"linear": lin, "params": [float(v) for v in m.params()], "iterations": int(res.iterations), "final_cost": float(res.final_cost),
-                     "err": [err.rmse, err.min, err.max, err.mean, err.stddev, err.median, err.count]}
+                     "err": [err.rmse, err.min, err.max, err.mean, err.stddev, err.median, err.count],
+                     "psnr": q.psnr, "ssim": q.ssim, "image_crc": int(np.bitwise_xor.reduce(np.frombuffer(img.tobytes(), np.uint32) * np.arange(1, img.size // 4 + 1, dtype=np.uint32)))}
     return out, uv, xyz
 
 
@@ -78,12 +81,16 @@ def main():
                      "iterations": [a["iterations"], b["iterations"]], "err_rel": rel(a["err"][:6], b["err"][:6]),
                      "exact_count_min_max_median": a["err"][6] == b["err"][6] and a["err"][1] == b["err"][1] and a["err"][2] == b["err"][2]
                                                    and a["err"][5] == b["err"][5],
-                     "mean_px": a["err"][3]}
+                     "mean_px": a["err"][3], "psnr": [a["psnr"], b["psnr"]], "ssim": [a["ssim"], b["ssim"]],
+                     "display_image_identical": a["image_crc"] == b["image_crc"]}
                 report[mode]["models"][name] = d
                 # bit-identical parameters must give bit-identical count / min / max / median; parameters that
                 # differ in the last bits (different grouping of the sums) move the errors by as much
                 ok &= d["linear_rel"] < 1e-9 and d["params_rel"] < 1e-9 and d["err_rel"] < 1e-9 and a["err"][6] == b["err"][6]
                 ok &= d["exact_count_min_max_median"] or d["params_rel"] > 0.0
+                # rendered images depend on the parameters only through rounded pixel positions: identical unless a
+                # projection sits on a rounding tie; PSNR is integer arithmetic on the images, SSIM a fixed-order sum
+                ok &= (a["psnr"] == b["psnr"] and abs(a["ssim"] - b["ssim"]) <= 1e-12 and d["display_image_identical"]) or d["params_rel"] > 0.0
         # every rank must hold identical results (rank-ordered sums)
         blob = json.dumps({k: v for k, v in got.items() if k != "kept_local"}, sort_keys=True)
         blobs = [None] * world

@@ -109,6 +109,25 @@ int main(int argc, char** argv) {
     for (int u = 0; u < 16; ++u) CHECK(out[3 * (11 * 16 + u)] == 0);
     CHECK(kind_of([&] { undistort_image(img, 15, 12, small); }) == ErrorKind::InvalidParams);
 
+    // image-quality diagnostics (image_quality.rs): a model against itself is a perfect match; one white pixel
+    // against black is 0 dB; the converted DS model is close to, but not identical with, the KB input
+    {
+        ImageQualityMetrics q = compute_image_quality_metrics(kb, kb, pts3.data(), n, 512, 512);
+        CHECK(std::isinf(q.psnr) && q.psnr > 0 && std::fabs(q.ssim - 1.0) < 1e-12);
+        std::vector<uint8_t> comb;
+        ImageQualityMetrics q2 = compute_image_quality_metrics(kb, target, pts3.data(), n, 512, 512, nullptr, &comb);
+        CHECK(q2.psnr > 0.0 && q2.ssim > 0.9 && q2.ssim <= 1.0 && comb.size() == 512 * 512 * 3);
+        std::vector<uint8_t> z(9 * 7 * 3, 0), one(9 * 7 * 3, 0);
+        one[3 * (3 * 9 + 4)] = one[3 * (3 * 9 + 4) + 1] = one[3 * (3 * 9 + 4) + 2] = 255;
+        CHECK(calculate_psnr(ctx, one, z, 9, 7) == 0.0 && std::isinf(calculate_psnr(ctx, z, z, 9, 7)));
+        CHECK(std::fabs(calculate_ssim(ctx, one, one, 9, 7) - 1.0) < 1e-12);
+        const double c[2] = {4.0, 4.0};
+        auto disc = create_projection_image(ctx, c, 1, 255, 255, 255, 9, 9);
+        int lit = 0; for (size_t i = 0; i < disc.size(); i += 3) lit += disc[i] != 0;
+        CHECK(lit == 13);
+        CHECK(kind_of([&] { calculate_psnr(ctx, one, z, 9, 8); }) == ErrorKind::InvalidParams);
+    }
+
     std::printf("HOST_TEST_OK mean_px=%.7f lm_iters=%d\n", mean, res.iterations);
     return 0;
 }
