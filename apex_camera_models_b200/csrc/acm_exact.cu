@@ -47,20 +47,40 @@ template <> struct StatusVec<4> {
 // ---------------------------------------------------------------------------------------
 // project: xyz -> uv + status
 // ---------------------------------------------------------------------------------------
+// Streaming variant per (kernel, model), chosen by same-box A/B on 100 M f64 points (scripts/ab_pu.sh).
+// PIPE = software-pipelined: the packet of the next iteration is in flight while this one is evaluated, with
+// __launch_bounds__(256, 3) so that the extra registers do not cost a resident block (uncapped, the pipelined
+// kernels grew to 70-100 registers and lost 5-10 %).  ncu had these kernels on long_scoreboard with DRAM at
+// 60-70 % of its peak.  GB/s plain -> pipelined (same box): project RadTan 5808 -> 6165, KB 5308 -> 5760,
+// DS 6000 -> 6130 (Pinhole, UCM, EUCM, FOV are at 5.8-6.5 TB/s plain and lose 2-5 % pipelined); unproject
+// DS 5125 -> 5590, UCM 5680 -> 5930, EUCM 5625 -> 5850, Pinhole 5730 -> 5935, FOV 5280 -> 5470 (KB, RadTan: Newton
+// loops, unchanged); round trip DS 4500 -> 5220, Pinhole 5815 -> 6025 (the others are not faster pipelined).
+// The plain variants keep an unspecified minimum block count: `__launch_bounds__(256, 1)` lets ptxas grow them
+// past 64 registers, which costs a resident block and 10-15 %.
+enum { PU_PROJECT = 0, PU_UNPROJECT = 1, PU_ROUND_TRIP = 2 };
+template <int KERNEL, int M> struct PuStream { static constexpr bool PIPE = false; };
+template <> struct PuStream<PU_PROJECT, ACM_MODEL_RADTAN> { static constexpr bool PIPE = true; };
+template <> struct PuStream<PU_PROJECT, ACM_MODEL_KANNALA_BRANDT> { static constexpr bool PIPE = true; };
+template <> struct PuStream<PU_PROJECT, ACM_MODEL_DOUBLE_SPHERE> { static constexpr bool PIPE = true; };
+template <int M> struct PuStream<PU_UNPROJECT, M> { static constexpr bool PIPE = M != ACM_MODEL_RADTAN; };
+template <> struct PuStream<PU_ROUND_TRIP, ACM_MODEL_PINHOLE> { static constexpr bool PIPE = true; };
+template <> struct PuStream<PU_ROUND_TRIP, ACM_MODEL_DOUBLE_SPHERE> { static constexpr bool PIPE = true; };
 template <int M, typename T, bool BOUNDS>
-__global__ void __launch_bounds__(256) project_kernel(const __grid_constant__ CamParams c, const T* __restrict__ X,
+__global__ void __launch_bounds__(256, (PuStream<PU_PROJECT, M>::PIPE ? 3 : 0)) project_kernel(const __grid_constant__ CamParams c, const T* __restrict__ X,
                                                       const T* __restrict__ Y, const T* __restrict__ Z, T* __restrict__ U,
                                                       T* __restrict__ V, uint8_t* __restrict__ S, size_t n) {
     using VT = typename Vec<T>::type;
     constexpr int NV = Vec<T>::N;
     const size_t npk = n / NV;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npk; p += stride) {
+    constexpr bool PIPE = PuStream<PU_PROJECT, M>::PIPE;
+    const VT* X4 = reinterpret_cast<const VT*>(X); const VT* Y4 = reinterpret_cast<const VT*>(Y); const VT* Z4 = reinterpret_cast<const VT*>(Z);
+    auto packet = [&](size_t p, const VT& vx, const VT& vy, const VT& vz) {
         double x[NV], y[NV], z[NV], u[NV], v[NV];
         int s[NV];
-        Vec<T>::unpack(ld_stream(reinterpret_cast<const VT*>(X) + p), x);
-        Vec<T>::unpack(ld_stream(reinterpret_cast<const VT*>(Y) + p), y);
-        Vec<T>::unpack(ld_stream(reinterpret_cast<const VT*>(Z) + p), z);
+        Vec<T>::unpack(vx, x);
+        Vec<T>::unpack(vy, y);
+        Vec<T>::unpack(vz, z);
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
             u[k] = v[k] = acm_nan();
@@ -71,6 +91,21 @@ __global__ void __launch_bounds__(256) project_kernel(const __grid_constant__ Ca
         st_stream(reinterpret_cast<VT*>(U) + p, Vec<T>::pack(u));
         st_stream(reinterpret_cast<VT*>(V) + p, Vec<T>::pack(v));
         if (S) StatusVec<NV>::store(S + p * NV, s);
+    };
+    if constexpr (PIPE) {
+        size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+        VT px, py, pz;
+        if (p < npk) { px = ld_stream(X4 + p); py = ld_stream(Y4 + p); pz = ld_stream(Z4 + p); }
+        while (p < npk) {
+            const size_t pn = p + stride;
+            VT nx = px, ny = py, nz = pz;
+            if (pn < npk) { nx = ld_stream(X4 + pn); ny = ld_stream(Y4 + pn); nz = ld_stream(Z4 + pn); }
+            packet(p, px, py, pz);
+            px = nx; py = ny; pz = nz; p = pn;
+        }
+    } else {
+        for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npk; p += stride)
+            packet(p, ld_stream(X4 + p), ld_stream(Y4 + p), ld_stream(Z4 + p));
     }
     // ragged tail (n not a multiple of the packet width)
     const size_t t = npk * NV + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -87,18 +122,20 @@ __global__ void __launch_bounds__(256) project_kernel(const __grid_constant__ Ca
 // unproject: uv -> ray + status
 // ---------------------------------------------------------------------------------------
 template <int M, typename T>
-__global__ void __launch_bounds__(256) unproject_kernel(const __grid_constant__ CamParams c, const T* __restrict__ U,
+__global__ void __launch_bounds__(256, (PuStream<PU_UNPROJECT, M>::PIPE ? 3 : 0)) unproject_kernel(const __grid_constant__ CamParams c, const T* __restrict__ U,
                                                         const T* __restrict__ V, T* __restrict__ X, T* __restrict__ Y,
                                                         T* __restrict__ Z, uint8_t* __restrict__ S, size_t n) {
     using VT = typename Vec<T>::type;
     constexpr int NV = Vec<T>::N;
     const size_t npk = n / NV;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npk; p += stride) {
+    constexpr bool PIPE = PuStream<PU_UNPROJECT, M>::PIPE;
+    const VT* U4 = reinterpret_cast<const VT*>(U); const VT* V4 = reinterpret_cast<const VT*>(V);
+    auto packet = [&](size_t p, const VT& vu, const VT& vv) {
         double u[NV], v[NV], x[NV], y[NV], z[NV];
         int s[NV];
-        Vec<T>::unpack(ld_stream(reinterpret_cast<const VT*>(U) + p), u);
-        Vec<T>::unpack(ld_stream(reinterpret_cast<const VT*>(V) + p), v);
+        Vec<T>::unpack(vu, u);
+        Vec<T>::unpack(vv, v);
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
             x[k] = y[k] = z[k] = acm_nan();
@@ -110,6 +147,21 @@ __global__ void __launch_bounds__(256) unproject_kernel(const __grid_constant__ 
         st_stream(reinterpret_cast<VT*>(Y) + p, Vec<T>::pack(y));
         st_stream(reinterpret_cast<VT*>(Z) + p, Vec<T>::pack(z));
         if (S) StatusVec<NV>::store(S + p * NV, s);
+    };
+    if constexpr (PIPE) {
+        size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+        VT pu, pv;
+        if (p < npk) { pu = ld_stream(U4 + p); pv = ld_stream(V4 + p); }
+        while (p < npk) {
+            const size_t pn = p + stride;
+            VT nu = pu, nv = pv;
+            if (pn < npk) { nu = ld_stream(U4 + pn); nv = ld_stream(V4 + pn); }
+            packet(p, pu, pv);
+            pu = nu; pv = nv; p = pn;
+        }
+    } else {
+        for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npk; p += stride)
+            packet(p, ld_stream(U4 + p), ld_stream(V4 + p));
     }
     const size_t t = npk * NV + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n) {
@@ -149,7 +201,7 @@ static int32_t launch_unproject(acm_ctx* ctx, const CamParams& c, const acm_poin
 // fused round trip: xyz -> uv -> ray (BASELINE config 2)
 // ---------------------------------------------------------------------------------------
 template <int M, typename T>
-__global__ void __launch_bounds__(256) round_trip_kernel(const __grid_constant__ CamParams c, const T* __restrict__ X, const T* __restrict__ Y,
+__global__ void __launch_bounds__(256, (PuStream<PU_ROUND_TRIP, M>::PIPE ? 3 : 0)) round_trip_kernel(const __grid_constant__ CamParams c, const T* __restrict__ X, const T* __restrict__ Y,
                                                          const T* __restrict__ Z, T* __restrict__ U, T* __restrict__ V, T* __restrict__ RX,
                                                          T* __restrict__ RY, T* __restrict__ RZ, uint8_t* __restrict__ SP,
                                                          uint8_t* __restrict__ SU, size_t n) {
@@ -170,12 +222,14 @@ __global__ void __launch_bounds__(256) round_trip_kernel(const __grid_constant__
             if (su == ACM_POINT_OK) { rx = ax; ry = ay; rz = az; }
         }
     };
-    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npk; p += stride) {
+    constexpr bool PIPE = PuStream<PU_ROUND_TRIP, M>::PIPE;
+    const VT* X4 = reinterpret_cast<const VT*>(X); const VT* Y4 = reinterpret_cast<const VT*>(Y); const VT* Z4 = reinterpret_cast<const VT*>(Z);
+    auto packet = [&](size_t p, const VT& vx, const VT& vy, const VT& vz) {
         double x[NV], y[NV], z[NV], u[NV], v[NV], rx[NV], ry[NV], rz[NV];
         int sp[NV], su[NV];
-        Vec<T>::unpack(ld_stream(reinterpret_cast<const VT*>(X) + p), x);
-        Vec<T>::unpack(ld_stream(reinterpret_cast<const VT*>(Y) + p), y);
-        Vec<T>::unpack(ld_stream(reinterpret_cast<const VT*>(Z) + p), z);
+        Vec<T>::unpack(vx, x);
+        Vec<T>::unpack(vy, y);
+        Vec<T>::unpack(vz, z);
 #pragma unroll
         for (int k = 0; k < NV; ++k) one(x[k], y[k], z[k], u[k], v[k], rx[k], ry[k], rz[k], sp[k], su[k]);
         st_stream(reinterpret_cast<VT*>(U) + p, Vec<T>::pack(u));
@@ -185,6 +239,21 @@ __global__ void __launch_bounds__(256) round_trip_kernel(const __grid_constant__
         st_stream(reinterpret_cast<VT*>(RZ) + p, Vec<T>::pack(rz));
         if (SP) StatusVec<NV>::store(SP + p * NV, sp);
         if (SU) StatusVec<NV>::store(SU + p * NV, su);
+    };
+    if constexpr (PIPE) {
+        size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+        VT px, py, pz;
+        if (p < npk) { px = ld_stream(X4 + p); py = ld_stream(Y4 + p); pz = ld_stream(Z4 + p); }
+        while (p < npk) {
+            const size_t pn = p + stride;
+            VT nx = px, ny = py, nz = pz;
+            if (pn < npk) { nx = ld_stream(X4 + pn); ny = ld_stream(Y4 + pn); nz = ld_stream(Z4 + pn); }
+            packet(p, px, py, pz);
+            px = nx; py = ny; pz = nz; p = pn;
+        }
+    } else {
+        for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npk; p += stride)
+            packet(p, ld_stream(X4 + p), ld_stream(Y4 + p), ld_stream(Z4 + p));
     }
     const size_t t = npk * NV + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n) {
