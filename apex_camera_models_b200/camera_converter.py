@@ -28,6 +28,7 @@ from .camera import (CameraModel, DoubleSphereModel, EucmModel, FovModel, Intrin
                      UcmModel)
 from .errors import AcmError
 from .image_quality import ImageQualityMetrics, compute_image_quality_metrics
+from .reporting import export_conversion_results
 from .optimization import OptimizationCost
 from .runtime import Context, default_context
 from .util import ProjectionError, compute_reprojection_error, sample_points
@@ -242,6 +243,7 @@ def main(argv=None) -> int:
         for m in metrics:
             m.model.save_to_yaml(os.path.join(args.output_dir, m.model.get_model_name() + ".yaml"))
         say(f"Converted models written to {args.output_dir}/")
+        say(f"Report: {export_conversion_results(metrics, args.input_model, args.output_dir)}")   # reporting.rs:225-413
     for p in pts:
         p.free()
     if world > 1:

@@ -11,6 +11,7 @@
 #include <stdlib.h>
 
 #include "acm_internal.cuh"
+#include "acm_math.cuh"
 #include "acm_reduce.cuh"
 
 // ---------------------------------------------------------------------------------------
@@ -101,7 +102,8 @@ __global__ void __launch_bounds__(256) ssim_kernel(const uint8_t* __restrict__ A
             for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
                 for (int dx = 0; dx < 3; ++dx) { ls1 += (double)t1[ly + dy][lx + dx]; ls2 += (double)t2[ly + dy][lx + dx]; }
-            const double mu1 = ls1 / 9.0, mu2 = ls2 / 9.0;
+            // x / 9.0 through the correctly rounded reciprocal (bit-identical, acm_div_by); x / 8.0 == x * 0.125 exactly
+            const double mu1 = acm_div_by(ls1, 9.0, 1.0 / 9.0), mu2 = acm_div_by(ls2, 9.0, 1.0 / 9.0);
             double s1 = 0.0, s2 = 0.0, s12 = 0.0;
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy)
@@ -112,7 +114,7 @@ __global__ void __launch_bounds__(256) ssim_kernel(const uint8_t* __restrict__ A
                     s2 += (v2 - mu2) * (v2 - mu2);
                     s12 += (v1 - mu1) * (v2 - mu2);
                 }
-            s1 /= 8.0; s2 /= 8.0; s12 /= 8.0;
+            s1 *= 0.125; s2 *= 0.125; s12 *= 0.125;
             const double numerator = (2.0 * mu1 * mu2 + c1) * (2.0 * s12 + c2);
             const double denominator = (mu1 * mu1 + mu2 * mu2 + c1) * (s1 + s2 + c2);
             if (denominator > 0.0) { acc[0] += numerator / denominator; acc[1] += 1.0; }

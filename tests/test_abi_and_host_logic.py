@@ -217,3 +217,41 @@ int main(void){ printf("%zu %zu %zu %zu %zu\n", sizeof(acm_camera), sizeof(acm_n
         subprocess.run(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
         sizes = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
     assert sizes == [C.sizeof(N.Camera), C.sizeof(N.NormalEquations), C.sizeof(N.LMConfig), C.sizeof(N.LMResult), C.sizeof(N.ProjectionError)]
+
+
+# ------------------------------------------------------------------ report text (reporting.rs) ---
+def test_rust_float_formatting_and_report_layout(tmp_path):
+    """reporting.rs:225-413: the exported text file, with Rust's `{}` / `{:?}` / `{:.N}` float formatting."""
+    from types import SimpleNamespace as NS
+    from apex_camera_models_b200.reporting import (export_conversion_results, format_conversion_report, model_debug, rust_debug_f64,
+                                                   rust_display_f64)
+    assert [rust_display_f64(v) for v in (1.0, 0.5, 1e-7, 1e16, -0.28340811, 0.0)] == ["1", "0.5", "0.0000001", "10000000000000000", "-0.28340811", "0"]
+    assert [rust_debug_f64(v) for v in (1.0, 1.76187114e-05, 0.00019359, 1e16, 2.5e-10, 0.0)] == ["1.0", "1.76187114e-5", "0.00019359", "1e16", "2.5e-10", "0.0"]
+    assert rust_display_f64(float("nan")) == "NaN" and rust_debug_f64(float("inf")) == "inf"
+
+    def model(name, intr, dist):
+        return NS(get_model_name=lambda: name, get_intrinsics=lambda: NS(fx=intr[0], fy=intr[1], cx=intr[2], cy=intr[3]),
+                  get_distortion=lambda: dist, get_resolution=lambda: NS(width=752, height=480))
+    ds = model("double_sphere", (158.5, 158.25, 254.0, 256.125), [0.59, -0.17])
+    rt = model("rad_tan", (461.629, 460.152, 362.68, 246.049), [-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05, 0.0])
+    assert model_debug(ds) == "DoubleSphere(DoubleSphere [fx: 158.5 fy: 158.25 cx: 254 cy: 256.125 alpha: 0.59 xi: -0.17])"
+    assert model_debug(rt) == "RadTan(RadTan [fx: 461.629 fy: 460.152 cx: 362.68 cy: 246.049 distortions: [-0.28340811, 0.07395907, 0.00019359, 1.76187114e-5, 0.0]])"
+    assert model_debug(model("pinhole", (500.0, 500.0, 320.0, 240.0), [])) == \
+        "Pinhole(PinholeModel { intrinsics: Intrinsics { fx: 500.0, fy: 500.0, cx: 320.0, cy: 240.0 }, resolution: Resolution { width: 752, height: 480 } })"
+    err = lambda mean: NS(mean=mean, rmse=mean * 1.5, min=0.0, max=mean * 9, stddev=mean, median=mean * 0.8)
+    val = NS(average_error=0.00321, max_error=float("nan"), status="GOOD")
+    metrics = [NS(model=ds, model_name="Double Sphere", final_reprojection_error=err(0.0077324), initial_reprojection_error=err(10.0321),
+                  optimization_time_ms=1.2345, convergence_status="Converged", validation_results=val, image_quality=NS(psnr=float("inf"), ssim=0.99951)),
+               NS(model=rt, model_name="Radial-Tangential", final_reprojection_error=err(184.95), initial_reprojection_error=err(34.5),
+                  optimization_time_ms=0.5, convergence_status="Linear Only", validation_results=val, image_quality=None)]
+    text = format_conversion_report(metrics, "kb")
+    lines = text.split("\n")
+    assert lines[0] == "FISHEYE CAMERA MODEL CONVERSION ANALYSIS REPORT - RUST IMPLEMENTATION" and lines[3] == "INPUT MODEL TYPE: KB"
+    assert "Double Sphere                    |      0.007732   |     10.024368   |        1.23   | Converged      " in lines
+    assert "Radial-Tangential                |    184.950000   |   -150.450000   |        0.50   | Linear Only    " in lines
+    assert "🏆 Best Accuracy: Double Sphere (0.007732 pixels)" in lines and "⚡ Fastest Conversion: Radial-Tangential (0.50 ms)" in lines
+    assert "DOUBLE SPHERE MODEL:" in lines and "-" * (len("Double Sphere") + 7) in lines
+    assert "  Mean: 0.00773240 px" in lines and "  Max Error: NaN px" in lines and "  PSNR: inf dB" in lines and "  SSIM: 0.9995" in lines
+    path = export_conversion_results(metrics, "KB", str(tmp_path))
+    assert path.endswith("camera_conversion_results_kb.txt") and open(path, encoding="utf-8").read() == text
+    assert "No conversions performed" in format_conversion_report([], "pinhole")
