@@ -90,6 +90,7 @@ SIGNATURES = {
     "acm_unproject": (C.c_int32, [_vp, _cam, _vp, _vp, _vp]),
     "acm_project_unproject": (C.c_int32, [_vp, _cam, _vp, _vp, _vp, _vp, _vp]),
     "acm_project_jacobian": (C.c_int32, [_vp, _cam, _vp, _vp, _vp, _vp]),
+    "acm_project_point_jacobian": (C.c_int32, [_vp, _cam, _vp, _vp, _vp, _vp]),
     "acm_project_host": (C.c_int32, [_vp, _cam, _vp, C.c_size_t, _vp, _vp]),
     "acm_unproject_host": (C.c_int32, [_vp, _cam, _vp, C.c_size_t, _vp, _vp]),
     "acm_linearize": (C.c_int32, [_vp, _cam, C.c_int32, _vp, _vp, C.POINTER(NormalEquations)]),

@@ -285,15 +285,38 @@ class CameraModel:
         ctx.device_free(d_j); ctx.device_free(d_s); src.free(); uv.free()
         return out, np.ascontiguousarray(J.reshape(2, P, n).transpose(2, 0, 1)), st
 
+    def project_point_jacobian_batch(self, points_3d):
+        """uv (N,2), J (N,2,3) = d(u,v)/d(x,y,z) -- the trait doc's "Jacobian matrix (2x3)" (mod.rs:246-252) --,
+        status (N,); geometric validity only, J = 0 where the projection fails."""
+        ctx = self.ctx
+        cam = self.camera_block()
+        a = np.ascontiguousarray(points_3d, dtype=np.float64).reshape(-1, 3)
+        n = a.shape[0]
+        src = Points.from_numpy(ctx, a)
+        uv = Points(ctx, 2, n)
+        d_j = ctx.device_alloc(max(n, 1) * 6 * 8)
+        d_s = ctx.device_alloc(max(n, 1))
+        ctx.check(_lib.acm_project_point_jacobian(ctx.handle, C.byref(cam), src.handle, uv.handle, C.c_void_p(d_j), C.c_void_p(d_s)))
+        J = np.empty((6, n)); st = np.empty(n, dtype=np.uint8)
+        if n:
+            ctx.d2h(J, d_j); ctx.d2h(st, d_s)
+        ctx.sync()
+        out = uv.numpy()
+        ctx.device_free(d_j); ctx.device_free(d_s); src.free(); uv.free()
+        return out, np.ascontiguousarray(J.reshape(2, 3, n).transpose(2, 0, 1)), st
+
     # ---- trait: scalar project / unproject ---------------------------------------------------
-    def project(self, point_3d, compute_jacobian: bool = False):
+    def project(self, point_3d, compute_jacobian=False):
         """`project(&Vector3) -> Result<Vector2, CameraModelError>` (mod.rs:256); with
-        `compute_jacobian=True` (README.md:119-126) returns (uv, 2xP Jacobian)."""
+        `compute_jacobian=True` (README.md:119-126) returns (uv, 2xP Jacobian w.r.t. the camera parameters, the
+        shape the per-model docs give: double_sphere.rs:326-332 "2x6"); `compute_jacobian="point"` returns the
+        2x3 Jacobian w.r.t. the 3-D point that the trait doc names (mod.rs:246-252)."""
         p = np.asarray(point_3d, dtype=np.float64).reshape(1, 3)
         uv, st = self.project_batch(p)
         raise_point_status(int(st[0]), self.MODEL_ID)
         if compute_jacobian:
-            _, J, stj = self.project_jacobian_batch(p)
+            fn = self.project_point_jacobian_batch if compute_jacobian == "point" else self.project_jacobian_batch
+            _, J, stj = fn(p)
             raise_point_status(int(stj[0]), self.MODEL_ID)
             return uv[0], J[0]
         return uv[0]

@@ -12,6 +12,7 @@
 #include "acm_linearize.cuh"
 #include "acm_reduce.cuh"
 #include "acm_models.cuh"
+#include "acm_pointjac.cuh"
 
 #include <stdlib.h>
 
@@ -694,6 +695,50 @@ extern "C" int32_t acm_project_jacobian(acm_ctx* ctx, const acm_camera* cam, con
     if (n == 0) return ACM_OK;
     int grid = grid_for(ctx, n, 256, 4);
     ACM_DISPATCH_MODEL(cam->model, (project_jacobian_kernel<M><<<grid, 256, 0, ctx->stream>>>(
+        c, p, comp<double>(xyz, 0), comp<double>(xyz, 1), comp<double>(xyz, 2), comp<double>(uv, 0), comp<double>(uv, 1), d_jac, d_status, n)))
+    ACM_CHECK_LAUNCH(ctx);
+    return ACM_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// project with the 2x3 Jacobian w.r.t. the 3-D point (the other reading of the README-era
+// `compute_jacobian` flag: trait doc reference src/camera/mod.rs:246-252 "Jacobian matrix (2x3)").
+// uv + six rows of n doubles: du/dx, du/dy, du/dz, dv/dx, dv/dy, dv/dz.
+// ---------------------------------------------------------------------------------------
+template <int M>
+__global__ void __launch_bounds__(256) project_point_jacobian_kernel(const __grid_constant__ CamParams c, LinParams p, const double* __restrict__ X,
+                                                                     const double* __restrict__ Y, const double* __restrict__ Z,
+                                                                     double* __restrict__ U, double* __restrict__ V, double* __restrict__ J,
+                                                                     uint8_t* __restrict__ S, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double x = X[i], y = Y[i], z = Z[i];
+        double u, v, ju[3], jv[3];
+        const int st = CamModel<M>::template project<false>(c, x, y, z, u, v);
+        if (st == ACM_POINT_OK) PointJac<M>::eval(p, x, y, z, ju, jv);
+        else { u = v = acm_nan(); ju[0] = ju[1] = ju[2] = jv[0] = jv[1] = jv[2] = 0.0; }
+        U[i] = u; V[i] = v;
+        if (S) S[i] = (uint8_t)st;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { __stcs(J + (size_t)k * n + i, ju[k]); __stcs(J + (size_t)(3 + k) * n + i, jv[k]); }
+    }
+}
+
+extern "C" int32_t acm_project_point_jacobian(acm_ctx* ctx, const acm_camera* cam, const acm_points* xyz, acm_points* uv, double* d_jac,
+                                              uint8_t* d_status) {
+    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_REQUIRE(ctx, cam && xyz && uv && d_jac, "project_point_jacobian: null argument");
+    ACM_REQUIRE(ctx, xyz->dim == 3 && uv->dim == 2 && xyz->n == uv->n, "project_point_jacobian: shape mismatch");
+    ACM_REQUIRE(ctx, xyz->dtype == ACM_F64 && uv->dtype == ACM_F64, "project_point_jacobian: f64 buffers required");
+    CamParams c;
+    int32_t rc = acm_make_cam_params(ctx, cam, &c);
+    if (rc) return rc;
+    LinParams p;
+    make_lin_params(cam, &p);
+    const size_t n = xyz->n;
+    if (n == 0) return ACM_OK;
+    int grid = grid_for(ctx, n, 256, 4);
+    ACM_DISPATCH_MODEL(cam->model, (project_point_jacobian_kernel<M><<<grid, 256, 0, ctx->stream>>>(
         c, p, comp<double>(xyz, 0), comp<double>(xyz, 1), comp<double>(xyz, 2), comp<double>(uv, 0), comp<double>(uv, 1), d_jac, d_status, n)))
     ACM_CHECK_LAUNCH(ctx);
     return ACM_OK;

@@ -145,6 +145,11 @@ int32_t acm_project_unproject(acm_ctx* ctx, const acm_camera* cam, const acm_poi
  * validity is the model's geometric test only (no image-bounds test) */
 int32_t acm_project_jacobian(acm_ctx* ctx, const acm_camera* cam, const acm_points* xyz, acm_points* uv,
                              double* d_jac, uint8_t* d_status);
+/* project with the 2x3 Jacobian w.r.t. the 3-D POINT (the trait doc's "Jacobian matrix (2x3)", reference
+ * src/camera/mod.rs:246-252): d_jac = six rows of n doubles du/dx, du/dy, du/dz, dv/dx, dv/dy, dv/dz (0 where the
+ * projection fails; status = geometric validity, no image-bounds test, like acm_project_jacobian) */
+int32_t acm_project_point_jacobian(acm_ctx* ctx, const acm_camera* cam, const acm_points* xyz, acm_points* uv, double* d_jac,
+                                   uint8_t* d_status);
 /* synchronous host-buffer forms (pageable or pinned AoS f64 in, AoS f64 + status out) */
 int32_t acm_project_host(acm_ctx* ctx, const acm_camera* cam, const double* xyz_aos, size_t n, double* uv_aos, uint8_t* status);
 int32_t acm_unproject_host(acm_ctx* ctx, const acm_camera* cam, const double* uv_aos, size_t n, double* xyz_aos, uint8_t* status);

@@ -288,6 +288,29 @@ private:
     int kind_;
 };
 
+// `project(&p, compute_jacobian = true)` in its 2x3 reading (trait doc mod.rs:246-252): uv (2n, nalgebra order) and the
+// point Jacobians as n row-major 2x3 blocks [du/dx du/dy du/dz dv/dx dv/dy dv/dz]; status = geometric validity
+inline void project_point_jacobian(const CameraModel& m, const double* xyz_aos, size_t n, std::vector<double>& uv_aos,
+                                   std::vector<double>& jac, std::vector<uint8_t>& status) {
+    const Context& ctx = m.ctx();
+    Points X(ctx, 3, xyz_aos, n), U(ctx, 2, n);
+    void *dj = nullptr, *ds = nullptr;
+    ctx.check(acm_device_alloc(ctx.handle(), (n ? n : 1) * 6 * sizeof(double), &dj));
+    ctx.check(acm_device_alloc(ctx.handle(), n ? n : 1, &ds));
+    acm_camera c = m.block();
+    int32_t rc = acm_project_point_jacobian(ctx.handle(), &c, X.handle(), U.handle(), static_cast<double*>(dj), static_cast<uint8_t*>(ds));
+    std::vector<double> rows(6 * n);
+    status.assign(n, 0);
+    if (rc == ACM_OK && n) rc = acm_memcpy_d2h(ctx.handle(), rows.data(), dj, 6 * n * sizeof(double));
+    if (rc == ACM_OK && n) rc = acm_memcpy_d2h(ctx.handle(), status.data(), ds, n);
+    if (rc == ACM_OK) rc = acm_ctx_sync(ctx.handle());
+    acm_device_free(ctx.handle(), dj); acm_device_free(ctx.handle(), ds);
+    ctx.check(rc);
+    uv_aos = U.download();
+    jac.resize(6 * n);
+    for (size_t i = 0; i < n; ++i) for (int k = 0; k < 6; ++k) jac[6 * i + k] = rows[(size_t)k * n + i];
+}
+
 // util::compute_reprojection_error (error_metrics.rs:62-121)
 inline acm_projection_error compute_reprojection_error(const CameraModel& m, const double* xyz_aos, const double* uv_aos, size_t n) {
     Points X(m.ctx(), 3, xyz_aos, n), U(m.ctx(), 2, uv_aos, n);

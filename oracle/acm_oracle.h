@@ -55,6 +55,8 @@ void orc_unproject_batch(const orc_model* m, const double* uv, size_t n, double*
 int orc_project_nobounds(const orc_model* m, const double X[3], double uv[2]);
 /* 2xP Jacobian of (u,v) w.r.t. params, row-major J[2][P]; returns status (nobounds) */
 int orc_project_jacobian(const orc_model* m, const double X[3], double uv[2], double* J);
+/* 2x3 Jacobian of (u,v) w.r.t. the 3-D point, row-major Jx[2][3]; returns status (nobounds) */
+int orc_project_point_jacobian(const orc_model* m, const double X[3], double uv[2], double Jx[6]);
 /* residual (2) and its 2xP Jacobian for either residual kind; returns status (nobounds) */
 int orc_residual_jacobian(const orc_model* m, int kind, const double X[3], const double uv_obs[2], double r[2], double* J);
 

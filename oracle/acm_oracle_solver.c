@@ -467,3 +467,123 @@ int orc_linear_estimation(orc_model* m, const double* xyz, const double* uv, siz
     default: return -1; /* Pinhole has no linear_estimation */
     }
 }
+
+/* 2x3 Jacobian of the projection w.r.t. the 3-D point (the "Jacobian matrix (2x3)" of the README-era
+ * `project(&p, compute_jacobian)`, stale trait doc reference src/camera/mod.rs:246-252).  The reference
+ * tree holds no code for it (derived there, third column of the table); pinned by
+ * mpmath 50-digit differences of the model definitions (tests/golden/mpmath_point_jacobians.json) and by
+ * central differences of orc_project.  Jx row-major: [du/dx du/dy du/dz dv/dx dv/dy dv/dz].
+ * Status = the geometric validity of the projection (no image-bounds test); Jx = 0 when it fails.
+ * KB at r < EPS (the reference returns the principal point there): the analytic limit on the axis, fx/z.
+ * FOV at r^2 < sqrt(EPS): the derivative of the reference's near-axis branch mx = x * (2 tan(w/2) / w). */
+int orc_project_point_jacobian(const orc_model* m, const double X[3], double uv[2], double Jx[6]) {
+    int st = orc_project_nobounds(m, X, uv);
+    memset(Jx, 0, 6 * sizeof(double));
+    if (st != ORC_OK) return st;
+    const double fx = m->p[0], fy = m->p[1];
+    const double x = X[0], y = X[1], z = X[2];
+    double* Ju = Jx;
+    double* Jv = Jx + 3;
+    switch (m->model) {
+    case ORC_PINHOLE: {
+        Ju[0] = fx / z; Ju[2] = -fx * x / (z * z);
+        Jv[1] = fy / z; Jv[2] = -fy * y / (z * z);
+        break;
+    }
+    case ORC_RADTAN: {
+        const double k1 = m->p[4], k2 = m->p[5], p1 = m->p[6], p2 = m->p[7], k3 = m->p[8];
+        double a = x / z, b = y / z;
+        double rho = a * a + b * b;
+        double rad = 1.0 + k1 * rho + k2 * rho * rho + k3 * rho * rho * rho;
+        double drad = k1 + 2.0 * k2 * rho + 3.0 * k3 * rho * rho;  /* d rad / d rho */
+        /* D = d(xd, yd) / d(a, b) */
+        double d00 = rad + a * drad * 2.0 * a + 2.0 * p1 * b + p2 * (2.0 * a + 4.0 * a);
+        double d01 = a * drad * 2.0 * b + 2.0 * p1 * a + p2 * 2.0 * b;
+        double d10 = b * drad * 2.0 * a + p1 * 2.0 * a + 2.0 * p2 * b;
+        double d11 = rad + b * drad * 2.0 * b + p1 * (2.0 * b + 4.0 * b) + 2.0 * p2 * a;
+        /* d(a, b) / dX = [[1/z, 0, -x/z^2], [0, 1/z, -y/z^2]] */
+        double iz = 1.0 / z, ax = -a * iz, bx = -b * iz;
+        Ju[0] = fx * d00 * iz; Ju[1] = fx * d01 * iz; Ju[2] = fx * (d00 * ax + d01 * bx);
+        Jv[0] = fy * d10 * iz; Jv[1] = fy * d11 * iz; Jv[2] = fy * (d10 * ax + d11 * bx);
+        break;
+    }
+    case ORC_KB: {
+        double r2 = x * x + y * y, r = sqrt(r2);
+        double th = atan2(r, z);
+        double t2 = th * th;
+        double thd = th * (1.0 + t2 * (m->p[4] + t2 * (m->p[5] + t2 * (m->p[6] + t2 * m->p[7]))));
+        double dthd = 1.0 + t2 * (3.0 * m->p[4] + t2 * (5.0 * m->p[5] + t2 * (7.0 * m->p[6] + t2 * 9.0 * m->p[7])));
+        if (r < EPS) {  /* on the axis: u - cx -> fx * x / z */
+            Ju[0] = fx / z; Jv[1] = fy / z;
+            break;
+        }
+        double rho2 = r2 + z * z;
+        double thx = x * z / (r * rho2), thy = y * z / (r * rho2), thz = -r / rho2;
+        double xr = x / r, yr = y / r, ir = 1.0 / r;
+        /* u - cx = fx * thd * x / r */
+        Ju[0] = fx * (dthd * thx * xr + thd * (ir - x * x / (r2 * r)));
+        Ju[1] = fx * (dthd * thy * xr - thd * x * y / (r2 * r));
+        Ju[2] = fx * dthd * thz * xr;
+        Jv[0] = fy * (dthd * thx * yr - thd * x * y / (r2 * r));
+        Jv[1] = fy * (dthd * thy * yr + thd * (ir - y * y / (r2 * r)));
+        Jv[2] = fy * dthd * thz * yr;
+        break;
+    }
+    case ORC_UCM: case ORC_EUCM: case ORC_DS: {
+        /* u - cx = fx * x / den:  grad u = fx * (e_x / den - x * grad den / den^2) */
+        const double alpha = m->p[4];
+        double den, gd[3];
+        if (m->model == ORC_UCM) {
+            double d = sqrt(x * x + y * y + z * z);
+            den = alpha * d + (1.0 - alpha) * z;
+            gd[0] = alpha * x / d; gd[1] = alpha * y / d; gd[2] = alpha * z / d + (1.0 - alpha);
+        } else if (m->model == ORC_EUCM) {
+            const double beta = m->p[5];
+            double d = sqrt(beta * (x * x + y * y) + z * z);
+            den = alpha * d + (1.0 - alpha) * z;
+            gd[0] = alpha * beta * x / d; gd[1] = alpha * beta * y / d; gd[2] = alpha * z / d + (1.0 - alpha);
+        } else {
+            const double xi = m->p[5];
+            double rr = x * x + y * y;
+            double d1 = sqrt(rr + z * z);
+            double g = xi * d1 + z;
+            double d2 = sqrt(rr + g * g);
+            den = alpha * d2 + (1.0 - alpha) * g;
+            double gg[3] = {xi * x / d1, xi * y / d1, xi * z / d1 + 1.0};
+            double gd2[3] = {(x + g * gg[0]) / d2, (y + g * gg[1]) / d2, g * gg[2] / d2};
+            for (int k = 0; k < 3; ++k) gd[k] = alpha * gd2[k] + (1.0 - alpha) * gg[k];
+        }
+        double id = 1.0 / den, id2 = id * id;
+        for (int k = 0; k < 3; ++k) {
+            Ju[k] = fx * ((k == 0 ? id : 0.0) - x * gd[k] * id2);
+            Jv[k] = fy * ((k == 1 ? id : 0.0) - y * gd[k] * id2);
+        }
+        break;
+    }
+    case ORC_FOV: {
+        const double w = m->p[4];
+        double t = tan(w / 2.0);
+        double r2 = x * x + y * y;
+        if (r2 < SQRT_EPS) {  /* the reference's near-axis branch (fov.rs:299-301): mx = x * (2t/w), a constant factor, no z */
+            double rd = 2.0 * t / w;
+            Ju[0] = fx * rd; Jv[1] = fy * rd;   /* the derivative of what project() evaluates there */
+            break;
+        }
+        double r = sqrt(r2);
+        double s = 2.0 * t * r;
+        double a = atan2(s, z);
+        double q = s * s + z * z;
+        double rd = a / (r * w);
+        /* grad a = (2t z / q) grad r + (0, 0, -s / q);  grad r = (x/r, y/r, 0) */
+        double ar = 2.0 * t * z / q;              /* da/dr */
+        double rdr = (ar - a / r) / (r * w);      /* d rd / d r */
+        double rdz = (-s / q) / (r * w);          /* d rd / d z */
+        double gx = rdr * x / r, gy = rdr * y / r;
+        Ju[0] = fx * (rd + x * gx); Ju[1] = fx * x * gy; Ju[2] = fx * x * rdz;
+        Jv[0] = fy * y * gx; Jv[1] = fy * (rd + y * gy); Jv[2] = fy * y * rdz;
+        break;
+    }
+    default: return -1;
+    }
+    return ORC_OK;
+}

@@ -70,6 +70,7 @@ def lib():
         L.orc_project_batch.argtypes = [mp, dp, C.c_size_t, dp, u8p, C.c_int]; L.orc_project_batch.restype = None
         L.orc_unproject_batch.argtypes = [mp, dp, C.c_size_t, dp, u8p, C.c_int]; L.orc_unproject_batch.restype = None
         L.orc_project_jacobian.argtypes = [mp, dp, dp, dp]; L.orc_project_jacobian.restype = C.c_int
+        L.orc_project_point_jacobian.argtypes = [mp, dp, dp, dp]; L.orc_project_point_jacobian.restype = C.c_int
         L.orc_residual_jacobian.argtypes = [mp, C.c_int, dp, dp, dp, dp]; L.orc_residual_jacobian.restype = C.c_int
         L.orc_linearize.argtypes = [mp, C.c_int, dp, dp, C.c_size_t, dp, dp, dp, C.POINTER(C.c_uint64), C.c_int]
         L.orc_linearize.restype = C.c_int
@@ -150,6 +151,13 @@ def unproject(m: Model, uv: np.ndarray, nthreads: int = 1):
 def project_jacobian1(m: Model, X):
     X = np.ascontiguousarray(X, dtype=np.float64); uv = np.empty(2); J = np.zeros((2, m.n_params))
     st = lib().orc_project_jacobian(C.byref(m), _dp(X), _dp(uv), _dp(J))
+    return st, uv, J
+
+
+def project_point_jacobian1(m: Model, X):
+    """status, uv, 2x3 Jacobian of (u, v) w.r.t. the 3-D point."""
+    X = np.ascontiguousarray(X, dtype=np.float64); uv = np.empty(2); J = np.zeros((2, 3))
+    st = lib().orc_project_point_jacobian(C.byref(m), _dp(X), _dp(uv), _dp(J))
     return st, uv, J
 
 

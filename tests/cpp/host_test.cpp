@@ -128,6 +128,15 @@ int main(int argc, char** argv) {
         CHECK(kind_of([&] { calculate_psnr(ctx, one, z, 9, 8); }) == ErrorKind::InvalidParams);
     }
 
+    // 2x3 point Jacobian: pinhole closed form, fx * (1/z, 0, -x/z^2)
+    {
+        const double X[3] = {0.2, -0.1, 2.0};
+        std::vector<double> uvj, jac; std::vector<uint8_t> stj;
+        project_point_jacobian(pin, X, 1, uvj, jac, stj);
+        CHECK(stj[0] == 0 && std::fabs(jac[0] - 250.0) < 1e-12 && jac[1] == 0.0 && std::fabs(jac[2] + 500.0 * 0.2 / 4.0) < 1e-12);
+        CHECK(jac[3] == 0.0 && std::fabs(jac[4] - 250.0) < 1e-12 && std::fabs(jac[5] - 500.0 * 0.1 / 4.0) < 1e-12);
+    }
+
     std::printf("HOST_TEST_OK mean_px=%.7f lm_iters=%d\n", mean, res.iterations);
     return 0;
 }

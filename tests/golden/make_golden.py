@@ -111,7 +111,33 @@ def mp_jacobians():
     return out
 
 
+def mp_point_jacobians():
+    """2x3 Jacobians of (u, v) w.r.t. the 3-D point: 50-digit central differences of the same model definitions."""
+    mp.mp.dps = 50
+    out = {"_comment": "mpmath 50-digit central differences (h=1e-20) of the model definitions w.r.t. the 3-D point"}
+    pts = [(0.3, -0.2, 1.5), (-0.7, 0.4, 1.0), (0.05, 0.02, 2.0), (1.2, 0.9, 0.8), (0.0, 0.3, 1.0)]
+    for name in ("pinhole", "rad_tan", "kannala_brandt", "ucm", "eucm", "double_sphere", "fov"):
+        c = cams[name]
+        p0 = [mp.mpf(v) for v in c["params"]]
+        rows = []
+        for X in pts:
+            Xm = [mp.mpf(v) for v in X]
+            J = [[], []]
+            h = mp.mpf(10) ** -20
+            for k in range(3):
+                Xp = list(Xm); Xn = list(Xm)
+                Xp[k] += h; Xn[k] -= h
+                up, vp = project_mp(c["model_id"], p0, Xp)
+                um, vm = project_mp(c["model_id"], p0, Xn)
+                J[0].append(float((up - um) / (2 * h)))
+                J[1].append(float((vp - vm) / (2 * h)))
+            rows.append({"point": list(X), "J": J})
+        out[name] = rows
+    return out
+
+
 if __name__ == "__main__":
     json.dump(opencv_cross(), open(os.path.join(HERE, "opencv_cross.json"), "w"), indent=1)
     json.dump(mp_jacobians(), open(os.path.join(HERE, "mpmath_jacobians.json"), "w"), indent=1)
-    print("wrote opencv_cross.json, mpmath_jacobians.json")
+    json.dump(mp_point_jacobians(), open(os.path.join(HERE, "mpmath_point_jacobians.json"), "w"), indent=1)
+    print("wrote opencv_cross.json, mpmath_jacobians.json, mpmath_point_jacobians.json")

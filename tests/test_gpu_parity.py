@@ -329,6 +329,51 @@ def test_reference_unit_tests_through_the_trait_surface(acm, ctx, cameras):
 
 # ------------------------------------------------------------------ Jacobians / normal equations --
 @pytest.mark.parametrize("name", MODELS)
+def test_point_jacobian_matches_oracle_mpmath_and_differences(acm, ctx, O, cameras, name):
+    """2x3 Jacobian w.r.t. the 3-D point (trait doc mod.rs:246-252): device vs oracle (1e-9), vs the mpmath
+    50-digit differences of the model definitions, and vs central differences of the device's own project."""
+    cam = cameras[name]
+    m, om = gpu_model(acm, ctx, cam), oracle_model(O, cam)
+    n = 2003
+    xyz = O.synth_points3(0xACE50002, 17, n, cone(name), True)
+    xyz[::5, :2] *= 1e-9          # near the axis: KB r < EPS / FOV r^2 < sqrt(EPS) branches
+    xyz[3::11, :2] = 0.0
+    uv, J, st = m.project_point_jacobian_batch(xyz)
+    assert J.shape == (n, 2, 3)
+    checked = 0
+    for i in range(n):
+        so, uvo, Jo = O.project_point_jacobian1(om, xyz[i])
+        assert st[i] == so
+        if so == 0:
+            assert np.allclose(uv[i], uvo, rtol=RTOL, atol=1e-13)
+            assert np.allclose(J[i], Jo, rtol=RTOL, atol=1e-12 * np.abs(Jo).max()), (i, xyz[i], J[i], Jo)
+            checked += 1
+        else:
+            assert np.all(J[i] == 0.0) and np.all(np.isnan(uv[i]))
+    assert checked > n // 4
+    rows = load_golden("mpmath_point_jacobians.json")[name]
+    pts = np.array([r["point"] for r in rows])
+    _, Jg, stg = m.project_point_jacobian_batch(pts)
+    for k, r in enumerate(rows):
+        assert stg[k] == 0
+        assert np.allclose(Jg[k], np.array(r["J"]), rtol=1e-9, atol=1e-12)
+    # central differences of the batch projection itself (smooth region only)
+    good = np.flatnonzero((st == 0) & (np.hypot(xyz[:, 0], xyz[:, 1]) > 1e-2) & (xyz[:, 2] > 0.2))[:200]
+    h = 1e-6
+    for k in range(3):
+        d = np.zeros(3); d[k] = h
+        up, sp = m.project_batch(xyz[good] + d)
+        um, sm = m.project_batch(xyz[good] - d)
+        ok = (sp == 0) & (sm == 0)
+        fd = (up - um) / (2 * h)
+        scale = np.abs(J[good][ok]).max(axis=(1, 2))[:, None]
+        assert np.max(np.abs(J[good][ok][:, :, k] - fd[ok]) / scale) < 1e-5
+    # the trait-level spelling
+    uv1, J1 = m.project(pts[0], compute_jacobian="point")
+    assert J1.shape == (2, 3) and np.array_equal(J1, Jg[0])
+
+
+@pytest.mark.parametrize("name", MODELS)
 def test_project_jacobian_matches_oracle_and_mpmath(acm, ctx, O, cameras, name):
     cam = cameras[name]
     m, om = gpu_model(acm, ctx, cam), oracle_model(O, cam)

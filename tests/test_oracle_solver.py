@@ -228,3 +228,29 @@ def test_synth_generators(O):
     px = O.synth_pixels(9, 0, 100, 752.0, 480.0)
     assert np.all((px[:, 0] >= 0) & (px[:, 0] < 752) & (px[:, 1] >= 0) & (px[:, 1] < 480))
     assert O.lib().orc_splitmix64(0) == 0xE220A8397B1DCDAF  # published splitmix64 first output
+
+
+def test_point_jacobians_match_mpmath_and_differences(O, cameras):
+    """2x3 Jacobian w.r.t. the 3-D point (trait doc mod.rs:246-252; no reference code): oracle vs mpmath
+    50-digit differences of the model definitions, and vs central differences of orc_project."""
+    from conftest import load_golden, oracle_model
+    g = load_golden("mpmath_point_jacobians.json")
+    for name in ("pinhole", "rad_tan", "kannala_brandt", "ucm", "eucm", "double_sphere", "fov"):
+        m = oracle_model(O, cameras[name])
+        for r in g[name]:
+            st, uv, J = O.project_point_jacobian1(m, r["point"])
+            assert st == 0
+            Jm = np.array(r["J"])
+            assert np.max(np.abs(J - Jm)) <= 1e-13 * np.abs(Jm).max(), (name, r["point"])
+            X = np.array(r["point"])
+            for k in range(3):
+                d = np.zeros(3); d[k] = 1e-6
+                _, up, _ = O.project_jacobian1(m, X + d); _, um, _ = O.project_jacobian1(m, X - d)
+                assert np.allclose(J[:, k], (up - um) / 2e-6, rtol=1e-5, atol=1e-6 * np.abs(Jm).max())
+    # invalid projection: status, zero Jacobian
+    kb = oracle_model(O, cameras["kannala_brandt"])
+    st, uv, J = O.project_point_jacobian1(kb, [0.1, 0.2, -1.0])
+    assert st != 0 and np.all(J == 0.0)
+    # on the KB axis: the analytic limit fx / z
+    st, uv, J = O.project_point_jacobian1(kb, [0.0, 0.0, 2.0])
+    assert st == 0 and np.allclose(J, [[kb.p[0] / 2.0, 0, 0], [0, kb.p[1] / 2.0, 0]])
