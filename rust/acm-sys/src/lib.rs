@@ -20,6 +20,8 @@ pub const ACM_F64: i32 = 0;
 pub const ACM_F32: i32 = 1;
 pub const ACM_RESIDUAL_PIXEL: i32 = 0;
 pub const ACM_RESIDUAL_ALGEBRAIC: i32 = 1;
+pub const ACM_INTERP_NEAREST: i32 = 0;
+pub const ACM_INTERP_BILINEAR: i32 = 1;
 
 #[repr(C)]
 pub struct acm_ctx { _private: [u8; 0] }

@@ -132,6 +132,108 @@ impl<'c, M: CameraModel> GpuCamera<'c, M> {
     }
 }
 
+/// Device point buffer owned for the duration of a call.
+struct DevicePoints<'c> { ctx: &'c Context, h: *mut sys::acm_points }
+impl<'c> DevicePoints<'c> {
+    fn upload(ctx: &'c Context, dim: i32, host: *const f64, n: usize) -> Result<Self, CameraModelError> {
+        let mut h = ptr::null_mut();
+        let mut rc = unsafe { sys::acm_points_create(ctx.0, dim, n, sys::ACM_F64, &mut h) };
+        if rc == sys::ACM_OK && n > 0 { rc = unsafe { sys::acm_points_upload_aos_f64(ctx.0, h, host, n) }; }
+        if rc != sys::ACM_OK { unsafe { sys::acm_points_destroy(ctx.0, h); } return Err(ctx.err(rc)); }
+        Ok(DevicePoints { ctx, h })
+    }
+    fn adopt(ctx: &'c Context, h: *mut sys::acm_points) -> Self { DevicePoints { ctx, h } }
+    fn len(&self) -> usize { unsafe { sys::acm_points_len(self.h) } }
+    fn download(&self, out: *mut f64) -> Result<(), CameraModelError> {
+        let rc = unsafe { sys::acm_points_download_aos_f64(self.ctx.0, self.h, out, self.len()) };
+        if rc != sys::ACM_OK { Err(self.ctx.err(rc)) } else { Ok(()) }
+    }
+}
+impl<'c> Drop for DevicePoints<'c> { fn drop(&mut self) { unsafe { sys::acm_points_destroy(self.ctx.0, self.h); } } }
+
+impl<'c, M: CameraModel> GpuCamera<'c, M> {
+    /// `util::sample_points(Some(&model), n) -> (Matrix2xX, Matrix3xX)` (point_sampling.rs:46-120):
+    /// grid of cell centres -> unproject -> keep Ok && z > 0, order preserved.
+    pub fn sample_points(&self, n: usize) -> Result<(Matrix2xX<f64>, Matrix3xX<f64>), CameraModelError> {
+        let cam = self.block();
+        let (mut uv, mut xyz, mut kept) = (ptr::null_mut(), ptr::null_mut(), 0usize);
+        let rc = unsafe { sys::acm_sample_points(self.ctx.0, &cam, n, &mut uv, &mut xyz, &mut kept) };
+        if rc != sys::ACM_OK { return Err(self.ctx.err(rc)); }
+        let (uv, xyz) = (DevicePoints::adopt(self.ctx, uv), DevicePoints::adopt(self.ctx, xyz));
+        let mut p2 = Matrix2xX::<f64>::zeros(kept);
+        let mut p3 = Matrix3xX::<f64>::zeros(kept);
+        uv.download(p2.as_mut_ptr())?;
+        xyz.download(p3.as_mut_ptr())?;
+        Ok((p2, p3))
+    }
+
+    /// `util::compute_reprojection_error(Some(&model), &points3d, &points2d)` (error_metrics.rs:62-121).
+    pub fn compute_reprojection_error(&self, points_3d: &Matrix3xX<f64>, points_2d: &Matrix2xX<f64>)
+        -> Result<sys::acm_projection_error, CameraModelError> {
+        if points_3d.ncols() != points_2d.ncols() {
+            return Err(CameraModelError::InvalidParams("Number of 2D and 3D points must match".into()));
+        }
+        let n = points_3d.ncols();
+        let x = DevicePoints::upload(self.ctx, 3, points_3d.as_ptr(), n)?;
+        let u = DevicePoints::upload(self.ctx, 2, points_2d.as_ptr(), n)?;
+        let cam = self.block();
+        let mut out = sys::acm_projection_error::default();
+        let rc = unsafe { sys::acm_reprojection_error(self.ctx.0, &cam, x.h, u.h, &mut out) };
+        if rc != sys::ACM_OK { return Err(self.ctx.err(rc)); }   // -7 -> UtilError::ZeroProjectionPoints upstream
+        Ok(out)
+    }
+
+    /// `util::undistort_image(&img, &model, target, method)` (undistort.rs:14-49) over the raw RGB8 buffer
+    /// (`RgbImage::as_raw()`); `interpolation` = `sys::ACM_INTERP_NEAREST | ACM_INTERP_BILINEAR`.
+    pub fn undistort_image(&self, image: &[u8], width: u32, height: u32, target: Option<Intrinsics>, interpolation: i32)
+        -> Result<Vec<u8>, CameraModelError> {
+        let r = self.inner.get_resolution();
+        if width != r.width || height != r.height || image.len() != width as usize * height as usize * 3 {   // undistort.rs:23-28
+            return Err(CameraModelError::InvalidParams(format!("Image {}x{} doesn't match model {}x{}", width, height, r.width, r.height)));
+        }
+        let cam = self.block();
+        let t = target.map(|t| [t.fx, t.fy, t.cx, t.cy]);
+        let mut out = vec![0u8; image.len()];
+        let rc = unsafe {
+            sys::acm_undistort_rgb8_host(self.ctx.0, &cam, t.as_ref().map_or(ptr::null(), |a| a.as_ptr()), image.as_ptr(), out.as_mut_ptr(), 1, interpolation)
+        };
+        if rc != sys::ACM_OK { Err(self.ctx.err(rc)) } else { Ok(out) }
+    }
+
+    /// README-era `project(&p, compute_jacobian = true)`: uv plus the 2xP Jacobian w.r.t. `[fx, fy, cx, cy, dist..]`
+    /// (per-model docs, double_sphere.rs:326-332) and the 2x3 Jacobian w.r.t. the 3-D point (trait doc, mod.rs:246-252).
+    pub fn project_with_jacobians(&self, p: &Vector3<f64>)
+        -> Result<(Vector2<f64>, nalgebra::DMatrix<f64>, nalgebra::Matrix2x3<f64>), CameraModelError> {
+        let cam = self.block();
+        let np = cam.n_params as usize;
+        let x = DevicePoints::upload(self.ctx, 3, p.as_ptr(), 1)?;
+        let u = DevicePoints::upload(self.ctx, 2, [0.0f64; 2].as_ptr(), 1)?;
+        let (mut dj, mut ds) = (ptr::null_mut(), ptr::null_mut());
+        let mut rc = unsafe { sys::acm_device_alloc(self.ctx.0, (2 * np + 6) * 8, &mut dj) };
+        if rc == sys::ACM_OK { rc = unsafe { sys::acm_device_alloc(self.ctx.0, 8, &mut ds) }; }
+        let mut jp = vec![0.0f64; 2 * np];
+        let mut jx = [0.0f64; 6];
+        let mut st = [0u8; 1];
+        let mut uv = [0.0f64; 2];
+        unsafe {
+            let djp = dj as *mut f64;
+            let djx = djp.add(2 * np);
+            if rc == sys::ACM_OK { rc = sys::acm_project_jacobian(self.ctx.0, &cam, x.h, u.h, djp, ds as *mut u8); }
+            if rc == sys::ACM_OK { rc = sys::acm_project_point_jacobian(self.ctx.0, &cam, x.h, u.h, djx, ds as *mut u8); }
+            if rc == sys::ACM_OK { rc = sys::acm_memcpy_d2h(self.ctx.0, jp.as_mut_ptr() as *mut _, djp as *const _, 2 * np * 8); }
+            if rc == sys::ACM_OK { rc = sys::acm_memcpy_d2h(self.ctx.0, jx.as_mut_ptr() as *mut _, djx as *const _, 48); }
+            if rc == sys::ACM_OK { rc = sys::acm_memcpy_d2h(self.ctx.0, st.as_mut_ptr() as *mut _, ds as *const _, 1); }
+            if rc == sys::ACM_OK { rc = sys::acm_points_download_aos_f64(self.ctx.0, u.h, uv.as_mut_ptr(), 1); }
+            if rc == sys::ACM_OK { rc = sys::acm_ctx_sync(self.ctx.0); }
+            sys::acm_device_free(self.ctx.0, dj); sys::acm_device_free(self.ctx.0, ds);
+        }
+        if rc != sys::ACM_OK { return Err(self.ctx.err(rc)); }
+        if let Some(e) = status_to_error(st[0], self.model_id) { return Err(e); }
+        // one point: the rows of n doubles are the row-major matrices themselves
+        Ok((Vector2::new(uv[0], uv[1]), nalgebra::DMatrix::from_row_slice(2, np, &jp), nalgebra::Matrix2x3::from_row_slice(&jx)))
+    }
+}
+
 /// Resident correspondences + optimiser: the README-era `*OptimizationCost` and the converter's
 /// `Problem` + `LevenbergMarquardt::with_config(cfg).optimize(..)` (camera_converter.rs:378-420).
 pub struct OptimizationCost<'c> {

@@ -255,3 +255,19 @@ def test_rust_float_formatting_and_report_layout(tmp_path):
     path = export_conversion_results(metrics, "KB", str(tmp_path))
     assert path.endswith("camera_conversion_results_kb.txt") and open(path, encoding="utf-8").read() == text
     assert "No conversions performed" in format_conversion_report([], "pinhole")
+
+
+def test_rust_ffi_crate_declares_every_header_symbol():
+    """rust/acm-sys (uncompiled here: no Rust toolchain) must bind exactly the functions include/acm.h declares,
+    and the wrapper crate may only call functions acm-sys declares."""
+    sys_rs = open(os.path.join(ROOT, "rust", "acm-sys", "src", "lib.rs")).read()
+    declared = set(re.findall(r"pub fn (acm_[a-z0-9_]+)\s*\(", sys_rs))
+    header = set(_declared_functions())
+    assert header - declared == set(), f"in acm.h but not in acm-sys: {sorted(header - declared)}"
+    assert declared - header == set(), f"in acm-sys but not in acm.h: {sorted(declared - header)}"
+    wrapper = open(os.path.join(ROOT, "rust", "apex-camera-models-cuda", "src", "lib.rs")).read()
+    used = set(re.findall(r"sys::(acm_[a-z0-9_]+)\s*\(", wrapper))
+    assert used <= declared, sorted(used - declared)
+    consts = set(re.findall(r"sys::(ACM_[A-Z0-9_]+)", wrapper))
+    have = set(re.findall(r"pub const (ACM_[A-Z0-9_]+)", sys_rs))
+    assert consts <= have, sorted(consts - have)
