@@ -97,23 +97,28 @@ __global__ void __launch_bounds__(256) ssim_kernel(const uint8_t* __restrict__ A
         __syncthreads();
         const uint32_t x = x0 + 1 + lx, y = y0 + 1 + ly;   // window centre
         if (x < W - 1 && y < H - 1) {
-            double ls1 = 0.0, ls2 = 0.0;
-#pragma unroll
-            for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-                for (int dx = 0; dx < 3; ++dx) { ls1 += (double)t1[ly + dy][lx + dx]; ls2 += (double)t2[ly + dy][lx + dx]; }
-            // x / 9.0 through the correctly rounded reciprocal (bit-identical, acm_div_by); x / 8.0 == x * 0.125 exactly
-            const double mu1 = acm_div_by(ls1, 9.0, 1.0 / 9.0), mu2 = acm_div_by(ls2, 9.0, 1.0 / 9.0);
-            double s1 = 0.0, s2 = 0.0, s12 = 0.0;
+            // the window sums run over integers <= 9 * 255: exact in any arithmetic, so they are taken in integer
+            // registers (the reference's sequential f64 sum gives the same value); each grey value is converted once
+            int is1 = 0, is2 = 0;
+            double v1[9], v2[9];
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
                 for (int dx = 0; dx < 3; ++dx) {
-                    const double v1 = (double)t1[ly + dy][lx + dx], v2 = (double)t2[ly + dy][lx + dx];
-                    s1 += (v1 - mu1) * (v1 - mu1);
-                    s2 += (v2 - mu2) * (v2 - mu2);
-                    s12 += (v1 - mu1) * (v2 - mu2);
+                    const int a = t1[ly + dy][lx + dx], b = t2[ly + dy][lx + dx];
+                    is1 += a; is2 += b;
+                    v1[dy * 3 + dx] = (double)a; v2[dy * 3 + dx] = (double)b;
                 }
+            const double ls1 = (double)is1, ls2 = (double)is2;
+            // x / 9.0 through the correctly rounded reciprocal (bit-identical, acm_div_by); x / 8.0 == x * 0.125 exactly
+            const double mu1 = acm_div_by(ls1, 9.0, 1.0 / 9.0), mu2 = acm_div_by(ls2, 9.0, 1.0 / 9.0);
+            double s1 = 0.0, s2 = 0.0, s12 = 0.0;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {   // dy outer, dx inner: the reference's order
+                s1 += (v1[k] - mu1) * (v1[k] - mu1);
+                s2 += (v2[k] - mu2) * (v2[k] - mu2);
+                s12 += (v1[k] - mu1) * (v2[k] - mu2);
+            }
             s1 *= 0.125; s2 *= 0.125; s12 *= 0.125;
             const double numerator = (2.0 * mu1 * mu2 + c1) * (2.0 * s12 + c2);
             const double denominator = (mu1 * mu1 + mu2 * mu2 + c1) * (s1 + s2 + c2);
