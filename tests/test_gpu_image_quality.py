@@ -134,3 +134,27 @@ def test_large_image_many_points(acm, ctx, O, cameras):
     # rounding error itself, the device's tree sum less; the contract's bar (1e-9 relative) applies
     assert kept > 0 and m2.psnr == psnr and same(m2.ssim, ssim, 1e-9)
     uv.free(); xyz.free()
+
+
+@pytest.mark.parametrize("target", ["double_sphere", "ucm", "eucm", "fov", "rad_tan", "pinhole"])
+def test_validate_conversion_accuracy_matches_oracle(acm, ctx, O, cameras, target):
+    """util::validate_conversion_accuracy (validation.rs:93-213): five probe pixels -> unproject(input) ->
+    project(both) -> distance; the host function over the GPU batch entry points vs the oracle's scalar loop."""
+    from apex_camera_models_b200.camera_converter import validate_conversion_accuracy
+    for src in ("kannala_brandt", "double_sphere", "rad_tan"):
+        sc, tc = cameras[src], cameras[target]
+        im, om_in = gpu_model(acm, ctx, sc), oracle_model(O, sc)
+        tm = gpu_model(acm, ctx, tc, sc["width"], sc["height"])
+        om_out = O.make_model(tc["model_id"], tc["params"], sc["width"], sc["height"])
+        got = validate_conversion_accuracy(tm, im)
+        valid, err, avg, mx = O.validate_conversion(om_out, om_in)
+        e = np.array(got.region_errors, dtype=np.float64)
+        assert np.array_equal(np.isnan(e), np.isnan(err)), (src, target, e, err)
+        fin = ~np.isnan(err)
+        assert np.allclose(e[fin], err[fin], rtol=1e-9, atol=1e-12)
+        if valid:
+            assert np.isclose(got.average_error, avg, rtol=1e-9, atol=1e-12) and np.isclose(got.max_error, mx, rtol=1e-9, atol=1e-12)
+            want = "EXCELLENT" if avg < 0.001 else "GOOD" if avg < 0.1 else "NEEDS IMPROVEMENT"
+            assert got.status == want
+        else:
+            assert math.isnan(got.average_error) and got.status == "NEEDS IMPROVEMENT"
