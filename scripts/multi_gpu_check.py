@@ -81,12 +81,15 @@ def main():
                      "iterations": [a["iterations"], b["iterations"]], "err_rel": rel(a["err"][:6], b["err"][:6]),
                      "exact_count_min_max_median": a["err"][6] == b["err"][6] and a["err"][1] == b["err"][1] and a["err"][2] == b["err"][2]
                                                    and a["err"][5] == b["err"][5],
+                     # absolute floor: `min` is a near-zero residual (~1e-6 px), where parameters that differ in the 15th digit
+                     # already move it by 1e-8 relative
+                     "err_close": bool(np.allclose(a["err"][:6], b["err"][:6], rtol=1e-9, atol=1e-11)),
                      "mean_px": a["err"][3], "psnr": [a["psnr"], b["psnr"]], "ssim": [a["ssim"], b["ssim"]],
                      "display_image_identical": a["image_crc"] == b["image_crc"]}
                 report[mode]["models"][name] = d
                 # bit-identical parameters must give bit-identical count / min / max / median; parameters that
                 # differ in the last bits (different grouping of the sums) move the errors by as much
-                ok &= d["linear_rel"] < 1e-9 and d["params_rel"] < 1e-9 and d["err_rel"] < 1e-9 and a["err"][6] == b["err"][6]
+                ok &= d["linear_rel"] < 1e-9 and d["params_rel"] < 1e-9 and d["err_close"] and a["err"][6] == b["err"][6]
                 ok &= d["exact_count_min_max_median"] or d["params_rel"] > 0.0
                 # rendered images depend on the parameters only through rounded pixel positions: identical unless a
                 # projection sits on a rounding tie; PSNR is integer arithmetic on the images, SSIM a fixed-order sum
