@@ -27,8 +27,8 @@ from . import distributed as D
 from .camera import (CameraModel, DoubleSphereModel, EucmModel, FovModel, Intrinsics, KannalaBrandtModel, PinholeModel, RadTanModel,
                      UcmModel)
 from .errors import AcmError
-from .image_quality import ImageQualityMetrics, compute_image_quality_metrics
-from .reporting import export_conversion_results
+from .image_quality import ImageQualityMetrics, compute_image_quality_metrics, model_projection_visualization
+from .reporting import export_conversion_results, export_point_correspondences
 from .optimization import OptimizationCost
 from .runtime import Context, default_context
 from .util import ProjectionError, compute_reprojection_error, sample_points
@@ -49,6 +49,9 @@ TARGETS = [
     ("Extended Unified Camera Model", EucmModel, [0.5, 1.0]),
     ("Field-of-View", FovModel, [1.0]),
 ]
+# `output_model_name` handed to compute_image_quality_metrics -> output/<name>_projection.png (camera_converter.rs:469, :608, :750, :880, :1014, :1144)
+IMAGE_LABELS = {DoubleSphereModel: "double_sphere_apex", KannalaBrandtModel: "kannala_brandt_apex", RadTanModel: "radial_tangential_apex",
+                UcmModel: "unified_camera_model_apex", EucmModel: "extended_unified_camera_model_apex", FovModel: "fov_apex"}
 REGIONS = [("Center", 0.5), ("Near Center", 0.55), ("Mid Region", 0.65), ("Edge Region", 0.8), ("Far Edge", 0.95)]  # validation.rs:106-112
 
 
@@ -148,15 +151,23 @@ def convert(input_model: CameraModel, name: str, cls, init, points_3d, points_2d
         res = compute_image_quality_metrics(input_model, model, points_3d, reference_image, return_image=want)
         quality, img = res if want else (res, None)
         if img is not None:  # save_model_projection_image (image_quality.rs:521-536): output/<model>_projection.png
-            _save_png(os.path.join(output_dir, model.get_model_name().lower().replace(" ", "_") + "_projection.png"), img)
+            _save_png(os.path.join(output_dir, IMAGE_LABELS[cls].lower().replace(" ", "_") + "_projection.png"), img)
     except AcmError:
         pass
     return ConversionMetrics(model, name, final, initial, elapsed, status, val, iterations, quality)
 
 
-def convert_all(input_model: CameraModel, num_points: int, shard=None, log=print, reference_image=None, output_dir=None):
+def convert_all(input_model: CameraModel, num_points: int, shard=None, log=print, reference_image=None, output_dir=None, input_label=None):
     uv, xyz = sample_points(input_model, num_points, device=True, shard=shard)
     kept = len(uv)
+    # camera_converter.rs:203, :213-218: the correspondences as CSV / Rust literals and the input-model projection image
+    # (single-GPU runs of converter size only: these are host files of every point)
+    if output_dir is not None and shard is None and kept <= 200_000:
+        p2, p3 = uv.numpy(), xyz.numpy()
+        export_point_correspondences(p3, p2, "point_correspondences_apex", output_dir)
+        res = input_model.get_resolution()
+        img = model_projection_visualization(p2, reference_image, (res.width, res.height), input_model.ctx)
+        _save_png(os.path.join(output_dir, f"{(input_label or input_model.get_model_name()).lower()}_projection.png"), img)   # image_quality.rs:607
     metrics = []
     for name, cls, init in TARGETS:
         if cls is type(input_model):
@@ -215,7 +226,7 @@ def main(argv=None) -> int:
     if img_dir:
         os.makedirs(img_dir, exist_ok=True)
     # every rank takes part in the collectives of the diagnostics; only rank 0 asks for (and saves) the display images
-    kept, metrics, pts = convert_all(input_model, args.num_points, shard, say, reference_image, img_dir)
+    kept, metrics, pts = convert_all(input_model, args.num_points, shard, say, reference_image, img_dir, args.input_model)
     total_ms = (time.perf_counter() - t0) * 1e3
     if world > 1:
         import torch

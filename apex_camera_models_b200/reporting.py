@@ -156,3 +156,32 @@ def export_conversion_results(metrics, input_model_type: str, output_dir: str = 
     with open(path, "w", encoding="utf-8") as f:
         f.write(format_conversion_report(metrics, input_model_type))
     return path
+
+
+def export_point_correspondences(points_3d, points_2d, filename_prefix: str, output_dir: str = "output"):
+    """`util::export_point_correspondences` (reference src/util/point_sampling.rs:153-237): `<prefix>.csv` and
+    `<prefix>_rust.txt` with `{:.15}` coordinates.  Host-side file output of the converter (camera_converter.rs:203).
+    Returns the two paths."""
+    import numpy as np
+    from .errors import UtilError
+    p3 = np.asarray(points_3d, dtype=np.float64).reshape(-1, 3)
+    p2 = np.asarray(points_2d, dtype=np.float64).reshape(-1, 2)
+    if len(p3) != len(p2):
+        raise UtilError("Invalid parameters: 3D and 2D point counts must match")
+    os.makedirs(output_dir, exist_ok=True)
+    n = len(p3)
+    csv_path = os.path.join(output_dir, f"{filename_prefix}.csv")
+    with open(csv_path, "w", encoding="utf-8") as f:
+        f.write("# 3D-2D Point Correspondences from Rust Implementation\n# Format: x3d,y3d,z3d,x2d,y2d\n")
+        f.write(f"# Total points: {n}\n")
+        for a, b in zip(p3, p2):
+            f.write(f"{a[0]:.15f},{a[1]:.15f},{a[2]:.15f},{b[0]:.15f},{b[1]:.15f}\n")
+    rust_path = os.path.join(output_dir, f"{filename_prefix}_rust.txt")
+    with open(rust_path, "w", encoding="utf-8") as f:
+        f.write("// 3D-2D Point Correspondences for Rust Import\n// Generated from Rust fisheye-tools\n")
+        f.write("let points_3d = Matrix3xX::from_columns(&[\n")
+        f.write(",\n".join(f"    Vector3::new({a[0]:.15f}, {a[1]:.15f}, {a[2]:.15f})" for a in p3) + ("\n" if n else ""))
+        f.write("]);\n\nlet points_2d = Matrix2xX::from_columns(&[\n")
+        f.write(",\n".join(f"    Vector2::new({b[0]:.15f}, {b[1]:.15f})" for b in p2) + ("\n" if n else ""))
+        f.write("]);\n")
+    return csv_path, rust_path

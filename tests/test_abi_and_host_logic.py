@@ -271,3 +271,21 @@ def test_rust_ffi_crate_declares_every_header_symbol():
     consts = set(re.findall(r"sys::(ACM_[A-Z0-9_]+)", wrapper))
     have = set(re.findall(r"pub const (ACM_[A-Z0-9_]+)", sys_rs))
     assert consts <= have, sorted(consts - have)
+
+
+def test_export_point_correspondences_format(tmp_path):
+    """point_sampling.rs:153-237: CSV + Rust-literal dump with `{:.15}` coordinates."""
+    from apex_camera_models_b200.reporting import export_point_correspondences
+    from apex_camera_models_b200.errors import UtilError
+    p3 = np.array([[0.1, -0.2, 1.0], [1.0 / 3.0, 2.0, 3.5]]); p2 = np.array([[10.5, 20.25], [300.0, 400.125]])
+    csv_path, rust_path = export_point_correspondences(p3, p2, "kb_points", str(tmp_path))
+    lines = open(csv_path).read().split("\n")
+    assert lines[:3] == ["# 3D-2D Point Correspondences from Rust Implementation", "# Format: x3d,y3d,z3d,x2d,y2d", "# Total points: 2"]
+    assert lines[3] == "0.100000000000000,-0.200000000000000,1.000000000000000,10.500000000000000,20.250000000000000"
+    assert lines[4].startswith("0.333333333333333,2.000000000000000,3.500000000000000,300.000000000000000,400.125")
+    rust = open(rust_path).read()
+    assert rust.startswith("// 3D-2D Point Correspondences for Rust Import\n// Generated from Rust fisheye-tools\nlet points_3d = Matrix3xX::from_columns(&[\n")
+    assert "    Vector3::new(0.100000000000000, -0.200000000000000, 1.000000000000000),\n    Vector3::new(0.333333333333333, 2.000000000000000, 3.500000000000000)\n]);\n\nlet points_2d" in rust
+    assert rust.endswith("    Vector2::new(300.000000000000000, 400.125000000000000)\n]);\n")
+    with pytest.raises(UtilError):
+        export_point_correspondences(p3, p2[:1], "bad", str(tmp_path))

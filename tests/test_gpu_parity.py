@@ -830,6 +830,17 @@ def test_camera_converter_cli_config1(acm, cameras, tmp_path, capsys):
     assert by["Radial-Tangential"].final_reprojection_error.mean > 50.0                   # README: "EXPECTED" failure on fisheye input
     ds = acm.DoubleSphereModel.load_from_yaml(str(out_dir / "double_sphere.yaml"))
     assert np.allclose(ds.params(), by["Double Sphere"].model.params(), rtol=0, atol=1e-12)
+    # the files the reference writes next to the models: report, correspondences, projection images
+    report = (out_dir / "camera_conversion_results_kb.txt").read_text(encoding="utf-8")
+    assert "INPUT MODEL TYPE: KB" in report and "DOUBLE SPHERE MODEL:" in report and "Image Quality Assessment:" in report
+    assert "Final Parameters: DoubleSphere(DoubleSphere [fx: " in report
+    csv = (out_dir / "point_correspondences_apex.csv").read_text().split("\n")
+    assert csv[2] == "# Total points: 450" and len([l for l in csv if l and not l.startswith("#")]) == 450
+    assert (out_dir / "point_correspondences_apex_rust.txt").exists()
+    from PIL import Image
+    for name in ("kb_projection.png", "double_sphere_apex_projection.png", "radial_tangential_apex_projection.png", "fov_apex_projection.png"):
+        assert Image.open(out_dir / name).size == (512, 512), name
+    assert by["Double Sphere"].image_quality is not None and by["Double Sphere"].image_quality.ssim > 0.99
 
 
 @pytest.mark.gpu
