@@ -88,6 +88,7 @@ SIGNATURES = {
     "acm_points_download_aos_f64": (C.c_int32, [_vp, _vp, _vp, C.c_size_t]),
     "acm_project": (C.c_int32, [_vp, _cam, _vp, _vp, _vp]),
     "acm_unproject": (C.c_int32, [_vp, _cam, _vp, _vp, _vp]),
+    "acm_unproject_ieee": (C.c_int32, [_vp, _cam, _vp, _vp, _vp]),
     "acm_project_unproject": (C.c_int32, [_vp, _cam, _vp, _vp, _vp, _vp, _vp]),
     "acm_project_jacobian": (C.c_int32, [_vp, _cam, _vp, _vp, _vp, _vp]),
     "acm_project_point_jacobian": (C.c_int32, [_vp, _cam, _vp, _vp, _vp, _vp]),

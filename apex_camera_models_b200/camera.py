@@ -229,6 +229,12 @@ class CameraModel:
             return xyz, st
         return self._host_map_via_points(a, 2, 3, _lib.acm_unproject, dtype)
 
+    def unproject_batch_ieee(self, points_2d):
+        """`unproject` with IEEE arithmetic to the end (acm_unproject_ieee): same status bytes as unproject_batch, values
+        bit-identical to the reference's for Pinhole / RadTan / UCM / EUCM / Double Sphere.  (N,2) -> (rays (N,3), status)."""
+        a = np.ascontiguousarray(points_2d, dtype=np.float64).reshape(-1, 2)
+        return self._host_map_via_points(a, 2, 3, _lib.acm_unproject_ieee, N.F64)
+
     def _host_map_via_points(self, a, din, dout, fn, dtype):
         ctx = self.ctx
         cam = self.camera_block()

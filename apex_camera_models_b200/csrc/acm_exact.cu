@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(256, (PuStream<PU_PROJECT, M>::PIPE ? 3 : 0)) 
 // ---------------------------------------------------------------------------------------
 // unproject: uv -> ray + status
 // ---------------------------------------------------------------------------------------
-template <int M, typename T>
+template <int M, typename T, bool IEEE = ACM_TAIL_DEFAULT>
 __global__ void __launch_bounds__(256, (PuStream<PU_UNPROJECT, M>::PIPE ? 3 : 0)) unproject_kernel(const __grid_constant__ CamParams c, const T* __restrict__ U,
                                                         const T* __restrict__ V, T* __restrict__ X, T* __restrict__ Y,
                                                         T* __restrict__ Z, uint8_t* __restrict__ S, size_t n) {
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256, (PuStream<PU_UNPROJECT, M>::PIPE ? 3 : 0)
         for (int k = 0; k < NV; ++k) {
             x[k] = y[k] = z[k] = acm_nan();
             double rx, ry, rz;
-            s[k] = CamModel<M>::unproject(c, u[k], v[k], rx, ry, rz);
+            s[k] = CamModel<M>::template unproject<IEEE>(c, u[k], v[k], rx, ry, rz);
             if (s[k] == ACM_POINT_OK) { x[k] = rx; y[k] = ry; z[k] = rz; }
         }
         st_stream(reinterpret_cast<VT*>(X) + p, Vec<T>::pack(x));
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(256, (PuStream<PU_UNPROJECT, M>::PIPE ? 3 : 0)
     const size_t t = npk * NV + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n) {
         double rx, ry, rz;
-        int st = CamModel<M>::unproject(c, (double)U[t], (double)V[t], rx, ry, rz);
+        int st = CamModel<M>::template unproject<IEEE>(c, (double)U[t], (double)V[t], rx, ry, rz);
         if (st != ACM_POINT_OK) rx = ry = rz = acm_nan();
         X[t] = (T)rx; Y[t] = (T)ry; Z[t] = (T)rz;
         if (S) S[t] = (uint8_t)st;
@@ -185,13 +185,13 @@ static int32_t launch_project(acm_ctx* ctx, const CamParams& c, const acm_points
     return ACM_OK;
 }
 
-template <int M, typename T>
+template <int M, typename T, bool IEEE = ACM_TAIL_DEFAULT>
 static int32_t launch_unproject(acm_ctx* ctx, const CamParams& c, const acm_points* uv, acm_points* xyz, uint8_t* st) {
     const size_t n = uv->n;
     if (n == 0) return ACM_OK;
     constexpr int NV = Vec<T>::N;
     int grid = grid_for(ctx, n / NV + NV, 256, 8);
-    unproject_kernel<M, T><<<grid, 256, 0, ctx->stream>>>(c, comp<T>(uv, 0), comp<T>(uv, 1), comp<T>(xyz, 0),
+    unproject_kernel<M, T, IEEE><<<grid, 256, 0, ctx->stream>>>(c, comp<T>(uv, 0), comp<T>(uv, 1), comp<T>(xyz, 0),
                                                            comp<T>(xyz, 1), comp<T>(xyz, 2), st, n);
     ACM_CHECK_LAUNCH(ctx);
     return ACM_OK;
@@ -317,6 +317,21 @@ extern "C" int32_t acm_unproject(acm_ctx* ctx, const acm_camera* cam, const acm_
     if (rc) return rc;
     if (uv->dtype == ACM_F64) { ACM_DISPATCH_MODEL(cam->model, return (launch_unproject<M, double>(ctx, c, uv, xyz, d_status))) }
     else { ACM_DISPATCH_MODEL(cam->model, return (launch_unproject<M, float>(ctx, c, uv, xyz, d_status))) }
+    return ACM_OK;
+}
+
+// unproject with IEEE arithmetic to the end (what sample_points uses): statuses as acm_unproject, values
+// bit-identical to the reference for the arithmetic-only models (Pinhole, RadTan, UCM, EUCM, Double Sphere)
+extern "C" int32_t acm_unproject_ieee(acm_ctx* ctx, const acm_camera* cam, const acm_points* uv, acm_points* xyz, uint8_t* d_status) {
+    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_REQUIRE(ctx, cam && xyz && uv, "acm_unproject_ieee: null argument");
+    ACM_REQUIRE(ctx, xyz->dim == 3 && uv->dim == 2, "acm_unproject_ieee: xyz must have dim 3 and uv dim 2");
+    ACM_REQUIRE(ctx, xyz->n == uv->n, "acm_unproject_ieee: point counts differ");
+    ACM_REQUIRE(ctx, xyz->dtype == ACM_F64 && uv->dtype == ACM_F64, "acm_unproject_ieee: f64 buffers required");
+    CamParams c;
+    int32_t rc = acm_make_cam_params(ctx, cam, &c);
+    if (rc) return rc;
+    ACM_DISPATCH_MODEL(cam->model, return (launch_unproject<M, double, true>(ctx, c, uv, xyz, d_status)))
     return ACM_OK;
 }
 

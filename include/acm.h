@@ -135,6 +135,11 @@ int32_t acm_points_download_aos_f64(acm_ctx* ctx, const acm_points* p, double* h
 /* xyz (dim 3) -> uv (dim 2) + status; dtypes of in/out must match (f64, or f32 I/O with f64 math) */
 int32_t acm_project(acm_ctx* ctx, const acm_camera* cam, const acm_points* xyz, acm_points* uv, uint8_t* d_status);
 int32_t acm_unproject(acm_ctx* ctx, const acm_camera* cam, const acm_points* uv, acm_points* xyz, uint8_t* d_status);
+/* acm_unproject keeps every validity decision in the reference's IEEE arithmetic (status bytes bit-exact) and
+ * evaluates what follows the last decision with <= 2 ulp reciprocals (values within ~1e-15 relative).  This form
+ * stays IEEE to the end: the values are bit-identical to the reference's for the arithmetic-only models
+ * (Pinhole, RadTan, UCM, EUCM, Double Sphere); f64 buffers only.  util::sample_points uses it. */
+int32_t acm_unproject_ieee(acm_ctx* ctx, const acm_camera* cam, const acm_points* uv, acm_points* xyz, uint8_t* d_status);
 /* BASELINE config 2, fused: project, then unproject the projected pixel, in one pass (66 B/pt f64
  * instead of 82 for the two kernels).  ray/status_unproject of a point whose projection failed are
  * NaN / the projection's status. */

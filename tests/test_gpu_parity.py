@@ -113,6 +113,33 @@ def test_fused_round_trip_matches_oracle(acm, ctx, O, cameras, name):
         assert np.max(np.abs(ray[good] - d)) < 1e-5
 
 
+@pytest.mark.parametrize("name", sorted(EXACT))
+def test_unproject_ieee_is_bit_identical_on_random_cameras(acm, ctx, O, cameras, name):
+    """acm_unproject_ieee: the three rewrites in the decision part of unproject -- (u - cx) / fx through the correctly
+    rounded reciprocal, RadTan's four divisions through one reciprocal, sqrt(s) < t as s < S -- are bit-IDENTICAL to the
+    reference's IEEE operations: with IEEE tails the rays of the arithmetic-only models equal the oracle's bit for bit,
+    on the sample camera and on 24 random cameras (200 k pixels each, in and around the image, incl. the principal point)."""
+    rng = np.random.default_rng(0xB17 + MODELS.index(name))
+    cams = [cameras[name]] + list(_random_cameras(name, rng, 24))
+    for k, cam in enumerate(cams):
+        m, om = gpu_model(acm, ctx, cam), oracle_model(O, cam)
+        Wp, Hp = (cam["width"] or 800), (cam["height"] or 600)
+        n = 200_003
+        px = O.synth_pixels(0xACE50007, 1000 * k, n, Wp * 1.2, Hp * 1.2) - [0.1 * Wp, 0.1 * Hp]
+        px[3::89] = cam["params"][2:4]
+        px[5::97, 0] = cam["params"][2]            # u == cx: zero numerators take the division's slow path
+        ray, st = m.unproject_batch_ieee(px)
+        rayo, sto = O.unproject(om, px, nthreads=8)
+        assert np.array_equal(st, sto), (name, cam["params"])
+        assert np.array_equal(np.isnan(ray), np.isnan(rayo))
+        fin = (sto == 0) & ~np.isnan(rayo).any(axis=1)
+        assert fin.sum() > 1000 or k > 0
+        assert np.array_equal(ray[fin], rayo[fin]), (name, cam["params"], np.abs(ray[fin] - rayo[fin]).max())
+        # and the default (fast-tail) entry point takes the same decisions
+        _, st2 = m.unproject_batch(px)
+        assert np.array_equal(st2, sto)
+
+
 def _random_cameras(name, rng, count):
     """Random parameter sets that exercise every branch of the validity tests (alpha on both sides
     of 0.5, alpha > 1 for UCM/EUCM, negative xi, w near its bounds, KB without a resolution, ...)."""
