@@ -65,14 +65,15 @@ __global__ void __launch_bounds__(256) psnr_kernel(const uint8_t* __restrict__ A
 // A block owns 32 x 8 window centres per tile and stages the (34 x 10) grey values of both images
 // in shared memory (the grey conversion happens once per tile pixel, not nine times).
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ uint8_t luma_u8(const uint8_t* p) {
+__device__ __forceinline__ uint8_t luma_u8(uint32_t rgb) {
     // image_quality.rs:203-204: (0.299 r + 0.587 g + 0.114 b) as u8 -- truncating, saturating
-    const double g = 0.299 * (double)p[0] + 0.587 * (double)p[1] + 0.114 * (double)p[2];
+    const double g = 0.299 * (double)(rgb & 255u) + 0.587 * (double)((rgb >> 8) & 255u) + 0.114 * (double)((rgb >> 16) & 255u);
     return (uint8_t)min(255, max(0, __double2int_rz(g)));
 }
 
 #define SSIM_TX 32
 #define SSIM_TY 8
+#define SSIM_TILE_PX ((SSIM_TY + 2) * (SSIM_TX + 2))
 __global__ void __launch_bounds__(256) ssim_kernel(const uint8_t* __restrict__ A, const uint8_t* __restrict__ B, uint32_t W, uint32_t H,
                                                    double c1, double c2, double* partials, double* out, unsigned int* ticket) {
     __shared__ uint8_t t1[SSIM_TY + 2][SSIM_TX + 2 + 2], t2[SSIM_TY + 2][SSIM_TX + 2 + 2];
@@ -81,20 +82,35 @@ __global__ void __launch_bounds__(256) ssim_kernel(const uint8_t* __restrict__ A
     const uint32_t tiles_x = (iw + SSIM_TX - 1) / SSIM_TX, tiles_y = (ih + SSIM_TY - 1) / SSIM_TY;
     const size_t ntiles = (size_t)tiles_x * tiles_y;
     const int lx = threadIdx.x & (SSIM_TX - 1), ly = threadIdx.x / SSIM_TX;
+    // the RGB bytes of the NEXT tile are fetched into registers while the windows of the current one are evaluated
+    // (ncu: the load and compute phases of a block used to alternate, FP64 pipe 39 % busy); a thread owns tile pixels
+    // k = tid and, for tid < SSIM_TILE_PX - 256, k = tid + 256
+    auto fetch = [&](size_t tile, int k, uint32_t& pa, uint32_t& pb) {
+        pa = pb = 0u;
+        if (tile < ntiles && k < SSIM_TILE_PX) {
+            const int ty = k / (SSIM_TX + 2), tx = k - ty * (SSIM_TX + 2);
+            const uint32_t x = (uint32_t)(tile % tiles_x) * SSIM_TX + tx, y = (uint32_t)(tile / tiles_x) * SSIM_TY + ty;
+            if (x < W && y < H) {
+                const size_t off = 3 * ((size_t)y * W + x);
+                pa = (uint32_t)A[off] | ((uint32_t)A[off + 1] << 8) | ((uint32_t)A[off + 2] << 16);
+                pb = (uint32_t)B[off] | ((uint32_t)B[off + 1] << 8) | ((uint32_t)B[off + 2] << 16);
+            }
+        }
+    };
+    uint32_t pa0, pb0, pa1, pb1;
+    fetch(blockIdx.x, threadIdx.x, pa0, pb0);
+    fetch(blockIdx.x, threadIdx.x + 256, pa1, pb1);
     for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const uint32_t x0 = (uint32_t)(tile % tiles_x) * SSIM_TX, y0 = (uint32_t)(tile / tiles_x) * SSIM_TY;  // tile origin in image coords (halo corner)
         __syncthreads();
-        for (int k = threadIdx.x; k < (SSIM_TY + 2) * (SSIM_TX + 2); k += 256) {
-            const int ty = k / (SSIM_TX + 2), tx = k - ty * (SSIM_TX + 2);
-            const uint32_t x = x0 + tx, y = y0 + ty;
-            uint8_t g1 = 0, g2 = 0;
-            if (x < W && y < H) {
-                const size_t off = 3 * ((size_t)y * W + x);
-                g1 = luma_u8(A + off); g2 = luma_u8(B + off);
-            }
-            t1[ty][tx] = g1; t2[ty][tx] = g2;
+        {   // pixels outside the image were fetched as 0 and are never part of a window
+            const int k0 = threadIdx.x, k1 = threadIdx.x + 256;
+            t1[k0 / (SSIM_TX + 2)][k0 % (SSIM_TX + 2)] = luma_u8(pa0); t2[k0 / (SSIM_TX + 2)][k0 % (SSIM_TX + 2)] = luma_u8(pb0);
+            if (k1 < SSIM_TILE_PX) { t1[k1 / (SSIM_TX + 2)][k1 % (SSIM_TX + 2)] = luma_u8(pa1); t2[k1 / (SSIM_TX + 2)][k1 % (SSIM_TX + 2)] = luma_u8(pb1); }
         }
         __syncthreads();
+        fetch(tile + gridDim.x, threadIdx.x, pa0, pb0);
+        fetch(tile + gridDim.x, threadIdx.x + 256, pa1, pb1);
         const uint32_t x = x0 + 1 + lx, y = y0 + 1 + ly;   // window centre
         if (x < W - 1 && y < H - 1) {
             // the window sums run over integers <= 9 * 255: exact in any arithmetic, so they are taken in integer
