@@ -89,6 +89,7 @@ SIGNATURES = {
     "acm_project": (C.c_int32, [_vp, _cam, _vp, _vp, _vp]),
     "acm_unproject": (C.c_int32, [_vp, _cam, _vp, _vp, _vp]),
     "acm_unproject_ieee": (C.c_int32, [_vp, _cam, _vp, _vp, _vp]),
+    "acm_camera_fast_unproject": (C.c_int32, [_cam]),
     "acm_project_unproject": (C.c_int32, [_vp, _cam, _vp, _vp, _vp, _vp, _vp]),
     "acm_project_jacobian": (C.c_int32, [_vp, _cam, _vp, _vp, _vp, _vp]),
     "acm_project_point_jacobian": (C.c_int32, [_vp, _cam, _vp, _vp, _vp, _vp]),

@@ -276,6 +276,46 @@ int32_t acm_make_cam_params(acm_ctx* ctx, const acm_camera* cam, CamParams* c) {
             c->k1 = 1.0 / t;
             break;
         }
+        case ACM_MODEL_KANNALA_BRANDT: {
+            // unproject solves g(theta) = theta (1 + k1 theta^2 + .. + k4 theta^8) = ru by Newton from theta0 = ru, ru in
+            // (1e-6, pi/2] (kannala_brandt.rs:470-520).  Kantorovich on |theta| <= tb: with m <= g', |g''| <= Mb and the first
+            // step bounded by eta = max|g(ru) - ru| / m, h = Mb eta / m <= 0.4 guarantees quadratic convergence inside a ball of
+            // radius eta (1 - sqrt(1 - 2h)) / h around theta0, for every ru.  The reference's loop (10 iterations, stop at
+            // |delta| < 1e-6, fail on |g'| < EPS) then returns Ok for every pixel and its iterate is within (Mb/2m) 1e-12 of the
+            // root -- which lets the batch kernel run a contracted (FMA + reciprocal) Newton: same status, theta within 1e-11.
+            // Cameras that fail the test keep the IEEE loop.
+            // m, Mb and max|g(ru) - ru| are bounded rigorously from 1024 samples plus a Lipschitz margin taken from
+            // absolute-value bounds of the next derivative (the sample camera has k3 < 0, which makes plain |k| bounds useless).
+            const double tb = 1.75, rmax = 3.14159265358979323846 / 2.0;
+            const double k[4] = {c->d[0], c->d[1], c->d[2], c->d[3]};
+            double L1 = 0.0, L2 = 0.0, L3 = 0.0;   // bounds of |g1 - 1|, |g2|, |g3| (first to third derivative of g) from |k_i|
+            for (int i = 0; i < 4; ++i) {
+                const int p = 2 * (i + 1);   // term k_i theta^(p+1)
+                L1 += (p + 1) * fabs(k[i]) * pow(tb, p);
+                L2 += (p + 1) * p * fabs(k[i]) * pow(tb, p - 1);
+                L3 += (p + 1) * p * (p - 1) * fabs(k[i]) * pow(tb, p - 2);
+            }
+            c->kb_fast = 0;
+            if (std::isfinite(L3) && L3 < 1e6) {
+                const int NS = 1024;
+                const double dt = tb / NS;
+                double gmin = INFINITY, g2max = 0.0, f0max = 0.0;
+                for (int j = 0; j <= NS; ++j) {
+                    const double t = j * dt, t2 = t * t;
+                    const double gp = 1.0 + t2 * (3.0 * k[0] + t2 * (5.0 * k[1] + t2 * (7.0 * k[2] + t2 * 9.0 * k[3])));
+                    const double gpp = t * (6.0 * k[0] + t2 * (20.0 * k[1] + t2 * (42.0 * k[2] + t2 * 72.0 * k[3])));
+                    gmin = fmin(gmin, gp); g2max = fmax(g2max, fabs(gpp));
+                    if (t <= rmax + dt) f0max = fmax(f0max, fabs(t * t2 * (k[0] + t2 * (k[1] + t2 * (k[2] + t2 * k[3])))));
+                }
+                const double m = gmin - L2 * dt, Mb = g2max + L3 * dt, F0 = f0max + L1 * dt;
+                if (m >= 0.5) {
+                    const double eta = F0 / m, h = Mb * eta / m;
+                    const double radius = h > 1e-12 ? eta * (1.0 - sqrt(1.0 - 2.0 * fmin(h, 0.5))) / h : eta;
+                    if (h <= 0.4 && radius <= tb - rmax && Mb / (2.0 * m) <= 4.0) c->kb_fast = 1;
+                }
+            }
+            break;
+        }
         case ACM_MODEL_FOV: {  // fov.rs:296, :340
             c->k0 = tan(c->d[0] / 2.0);
             break;
@@ -283,6 +323,15 @@ int32_t acm_make_cam_params(acm_ctx* ctx, const acm_camera* cam, CamParams* c) {
         default: break;
     }
     return ACM_OK;
+}
+
+// 1 when acm_unproject runs the contracted Newton iteration for this camera (Kannala-Brandt cameras that pass the
+// host-side convergence proof above), 0 when it keeps the IEEE loop; negative on an invalid camera block
+extern "C" int32_t acm_camera_fast_unproject(const acm_camera* cam) {
+    CamParams c;
+    int32_t rc = acm_make_cam_params(nullptr, cam, &c);
+    if (rc) return rc;
+    return (c.model == ACM_MODEL_KANNALA_BRANDT && c.kb_fast) ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -24,7 +24,7 @@ struct CamParams {
     int32_t model;
     int32_t has_resolution;  // width > 0 && height > 0 (kannala_brandt.rs:447-448)
     int32_t fast_div;        // 2^-100 <= |fx|, |fy| <= 2^100: acm_div_by() is bit-identical to the division
-    int32_t pad_;
+    int32_t kb_fast;         // Kannala-Brandt: the host verified that Newton's method converges for every pixel (acm_make_cam_params)
 };
 
 struct acm_points {

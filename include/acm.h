@@ -140,6 +140,11 @@ int32_t acm_unproject(acm_ctx* ctx, const acm_camera* cam, const acm_points* uv,
  * stays IEEE to the end: the values are bit-identical to the reference's for the arithmetic-only models
  * (Pinhole, RadTan, UCM, EUCM, Double Sphere); f64 buffers only.  util::sample_points uses it. */
 int32_t acm_unproject_ieee(acm_ctx* ctx, const acm_camera* cam, const acm_points* uv, acm_points* xyz, uint8_t* d_status);
+/* Kannala-Brandt: acm_unproject replaces the reference's Newton loop (kannala_brandt.rs:470-520) by a contracted one
+ * (FMA + reciprocal) for cameras whose coefficients pass a host-side convergence proof (Kantorovich bound over every
+ * ru in (1e-6, pi/2]: the reference's loop provably returns Ok and its iterate lies within ~1e-12 of the root); other
+ * cameras keep the IEEE loop.  Returns 1 / 0 for "contracted" / "IEEE", negative for an invalid camera block. */
+int32_t acm_camera_fast_unproject(const acm_camera* cam);
 /* BASELINE config 2, fused: project, then unproject the projected pixel, in one pass (66 B/pt f64
  * instead of 82 for the two kernels).  ray/status_unproject of a point whose projection failed are
  * NaN / the projection's status. */

@@ -128,6 +128,7 @@ extern "C" {
     pub fn acm_project(ctx: *mut acm_ctx, cam: *const acm_camera, xyz: *const acm_points, uv: *mut acm_points, d_status: *mut u8) -> i32;
     pub fn acm_unproject(ctx: *mut acm_ctx, cam: *const acm_camera, uv: *const acm_points, xyz: *mut acm_points, d_status: *mut u8) -> i32;
     pub fn acm_unproject_ieee(ctx: *mut acm_ctx, cam: *const acm_camera, uv: *const acm_points, xyz: *mut acm_points, d_status: *mut u8) -> i32;
+    pub fn acm_camera_fast_unproject(cam: *const acm_camera) -> i32;
     pub fn acm_project_unproject(ctx: *mut acm_ctx, cam: *const acm_camera, xyz: *const acm_points, uv: *mut acm_points, ray: *mut acm_points, d_status_project: *mut u8, d_status_unproject: *mut u8) -> i32;
     pub fn acm_project_jacobian(ctx: *mut acm_ctx, cam: *const acm_camera, xyz: *const acm_points, uv: *mut acm_points, d_jac: *mut f64, d_status: *mut u8) -> i32;
     pub fn acm_project_point_jacobian(ctx: *mut acm_ctx, cam: *const acm_camera, xyz: *const acm_points, uv: *mut acm_points, d_jac: *mut f64, d_status: *mut u8) -> i32;

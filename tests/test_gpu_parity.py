@@ -140,6 +140,46 @@ def test_unproject_ieee_is_bit_identical_on_random_cameras(acm, ctx, O, cameras,
         assert np.array_equal(st2, sto)
 
 
+def test_kb_contracted_newton_matches_reference_loop(acm, ctx, O, cameras):
+    """Kannala-Brandt unproject: cameras that pass the host-side convergence proof run a contracted Newton iteration,
+    the others the IEEE loop (acm_camera_fast_unproject tells which).  Both must give the oracle's status bytes bit for bit
+    and its rays within 1e-9 -- on the sample camera at two scales, mild random cameras (fast path) and wild ones (IEEE)."""
+    import ctypes as C
+    from apex_camera_models_b200 import _native as N
+    rng = np.random.default_rng(0xCB)
+    base = cameras["kannala_brandt"]
+    cams = [base, dict(base, params=[8 * v for v in base["params"][:4]] + base["params"][4:], width=4096, height=4096)]
+    for _ in range(10):   # mild distortion: must take the contracted path
+        cams.append(dict(base, params=base["params"][:4] + list(rng.uniform(-4e-3, 4e-3, 4) * [1, 0.5, 0.5, 0.1]), width=640, height=480))
+    for _ in range(6):    # wild distortion (incl. non-monotone theta_d): IEEE loop, NumericalError pixels
+        cams.append(dict(base, params=base["params"][:4] + list(rng.uniform(-0.6, 0.6, 4)), width=640, height=480))
+    cams.append(dict(cameras["kannala_brandt_inline"]))
+    fast = 0
+    for k, cam in enumerate(cams):
+        m, om = gpu_model(acm, ctx, cam), oracle_model(O, cam)
+        blk = m.camera_block()
+        flag = N.lib.acm_camera_fast_unproject(C.byref(blk))
+        assert flag in (0, 1)
+        fast += flag
+        if k < 2:
+            assert flag == 1, cam["params"]   # the reference's sample camera, at both scales
+        W, H = cam["width"], cam["height"]
+        n = 300_001
+        px = O.synth_pixels(0xACE5000B, 977 * k, n, W * 1.1, H * 1.1) - [0.05 * W, 0.05 * H]
+        cx, cy, fx = cam["params"][2], cam["params"][3], cam["params"][0]
+        px[1::53] = [cx, cy]                                    # ru == 0
+        px[2::59] = [cx + 0.5e-6 * fx, cy]                      # 0 < ru <= 1e-6: NumericalError
+        px[3::61] = [cx + 1.000001e-6 * fx, cy]                 # just above the hole
+        ray, st = m.unproject_batch(px)
+        rayo, sto = O.unproject(om, px, nthreads=8)
+        assert np.array_equal(st, sto), (k, cam["params"], np.flatnonzero(st != sto)[:5])
+        ok = sto == 0
+        assert np.array_equal(np.isnan(ray), np.isnan(rayo))
+        fin = ok & ~np.isnan(rayo).any(axis=1)
+        assert np.allclose(ray[fin], rayo[fin], rtol=RTOL, atol=1e-12), (k, np.abs(ray[fin] - rayo[fin]).max())
+    assert 9 <= fast < len(cams)   # both loops are exercised
+
+
 def _random_cameras(name, rng, count):
     """Random parameter sets that exercise every branch of the validity tests (alpha on both sides
     of 0.5, alpha > 1 for UCM/EUCM, negative xi, w near its bounds, KB without a resolution, ...)."""
