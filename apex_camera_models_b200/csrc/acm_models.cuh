@@ -396,7 +396,8 @@ template <> struct CamModel<ACM_MODEL_FOV> {
             double ird;
             const double rd = acm_sqrt_inv(r2, ird);
             double s, co;
-            sincos(rd * w, &s, &co);
+            const double arg = rd * w;
+            if (arg >= 0.0 && arg <= 1.8) acm_sincos_small(arg, s, co); else sincos(arg, &s, &co);
             const double k = s * ird * acm_rcp(mul2 * co);   // (sin / (rd mul2)) / cos
             x = mx * k; y = my * k;
         } else { x = mx; y = my; }
