@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(256, (PuStream<PU_PROJECT, M>::PIPE ? 3 : 0)) 
         for (int k = 0; k < NV; ++k) {
             u[k] = v[k] = acm_nan();
             double uu, vv;
-            s[k] = CamModel<M>::template project<BOUNDS>(c, x[k], y[k], z[k], uu, vv);
+            s[k] = CamModel<M>::template project<BOUNDS, true>(c, x[k], y[k], z[k], uu, vv);
             if (s[k] == ACM_POINT_OK) { u[k] = uu; v[k] = vv; }
         }
         st_stream(reinterpret_cast<VT*>(U) + p, Vec<T>::pack(u));
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256, (PuStream<PU_PROJECT, M>::PIPE ? 3 : 0)) 
     const size_t t = npk * NV + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n) {
         double uu, vv;
-        int st = CamModel<M>::template project<BOUNDS>(c, (double)X[t], (double)Y[t], (double)Z[t], uu, vv);
+        int st = CamModel<M>::template project<BOUNDS, true>(c, (double)X[t], (double)Y[t], (double)Z[t], uu, vv);
         if (st != ACM_POINT_OK) uu = vv = acm_nan();
         U[t] = (T)uu; V[t] = (T)vv;
         if (S) S[t] = (uint8_t)st;
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(256, (PuStream<PU_ROUND_TRIP, M>::PIPE ? 3 : 0
     auto one = [&](double x, double y, double z, double& u, double& v, double& rx, double& ry, double& rz, int& sp, int& su) {
         u = v = rx = ry = rz = acm_nan();
         double uu, vv;
-        sp = CamModel<M>::template project<true>(c, x, y, z, uu, vv);
+        sp = CamModel<M>::template project<true, true>(c, x, y, z, uu, vv);
         su = sp;
         if (sp == ACM_POINT_OK) {
             u = uu; v = vv;

@@ -71,7 +71,7 @@ template <int M> struct CamModel;
 
 // ---- Pinhole (pinhole.rs:165-182, :228-246) ----------------------------------------------
 template <> struct CamModel<ACM_MODEL_PINHOLE> {
-    template <bool BOUNDS>
+    template <bool BOUNDS, bool FAST = false>
     static __device__ __forceinline__ int project(const CamParams& c, double x, double y, double z, double& u, double& v) {
         if (z < ACM_SQRT_EPS) return ACM_POINT_AT_CAMERA_CENTER;
         u = c.fx * x / z + c.cx;
@@ -92,7 +92,7 @@ template <> struct CamModel<ACM_MODEL_PINHOLE> {
 
 // ---- RadTan (rad_tan.rs:302-348, :401-524), d = [k1,k2,p1,p2,k3] ---------------------------
 template <> struct CamModel<ACM_MODEL_RADTAN> {
-    template <bool BOUNDS>
+    template <bool BOUNDS, bool FAST = false>
     static __device__ __forceinline__ int project(const CamParams& c, double x, double y, double z, double& u, double& v) {
         if (z < ACM_SQRT_EPS) return ACM_POINT_AT_CAMERA_CENTER;
         const double k1 = c.d[0], k2 = c.d[1], p1 = c.d[2], p2 = c.d[3], k3 = c.d[4];
@@ -152,11 +152,16 @@ template <> struct CamModel<ACM_MODEL_RADTAN> {
 
 // ---- Kannala-Brandt (kannala_brandt.rs:340-394, :445-562), d = [k1..k4] ---------------------
 template <> struct CamModel<ACM_MODEL_KANNALA_BRANDT> {
-    template <bool BOUNDS>
+    template <bool BOUNDS, bool FAST = false>
     static __device__ __forceinline__ int project(const CamParams& c, double x, double y, double z, double& u, double& v) {
         if (z < 0.0) return ACM_POINT_IS_OUTSIDE_IMAGE;
         else if (z < ACM_EPS) return ACM_POINT_AT_CAMERA_CENTER;
-        double r = sqrt(x * x + y * y);
+        // FAST (batch project / round trip only; undistort and the statistics keep the IEEE form): nothing after the two
+        // z tests is a status decision, so sqrt + the two divisions by r become one coupled sqrt / rsqrt (<= 2 ulp);
+        // the r < EPS branch is taken exactly on r2 (sqrt(s) < 2^-52  <=>  s < 2^-104 for the correctly rounded root)
+        const double r2 = x * x + y * y;
+        double ir = 0.0;
+        const double r = FAST ? acm_sqrt_inv(r2, ir) : sqrt(r2);
         double th = acm_atan2_q1(r, z);  // r >= 0, z >= EPS: first quadrant (<= 1.5 ulp, see acm_math.cuh)
         double t2 = th * th;
         double t3 = t2 * th;
@@ -165,7 +170,8 @@ template <> struct CamModel<ACM_MODEL_KANNALA_BRANDT> {
         double t9 = t7 * t2;
         double thd = th + c.d[0] * t3 + c.d[1] * t5 + c.d[2] * t7 + c.d[3] * t9;
         double xr, yr;
-        if (r < ACM_EPS) { xr = 0.0; yr = 0.0; } else { xr = x / r; yr = y / r; }
+        if (FAST) { const bool axis = r2 < 0x1.0p-104; xr = axis ? 0.0 : x * ir; yr = axis ? 0.0 : y * ir; }
+        else if (r < ACM_EPS) { xr = 0.0; yr = 0.0; } else { xr = x / r; yr = y / r; }
         u = c.fx * thd * xr + c.cx;
         v = c.fy * thd * yr + c.cy;
         return ACM_POINT_OK;  // no image-bounds test in the reference
@@ -251,7 +257,7 @@ template <> struct CamModel<ACM_MODEL_KANNALA_BRANDT> {
 // ---- UCM (ucm.rs:297-316, :337-367, :154-161, :177-184), d = [alpha] -------------------------
 // k0 = w of check_proj_condition, k1 = gamma*gamma/(2*alpha-1), k2 = xi = alpha/gamma
 template <> struct CamModel<ACM_MODEL_UCM> {
-    template <bool BOUNDS>
+    template <bool BOUNDS, bool FAST = false>
     static __device__ __forceinline__ int project(const CamParams& c, double x, double y, double z, double& u, double& v) {
         const double alpha = c.d[0];
         double d = sqrt(x * x + y * y + z * z);
@@ -282,7 +288,7 @@ template <> struct CamModel<ACM_MODEL_UCM> {
 // ---- EUCM (eucm.rs:328-347, :368-398, :167-177, :194-200), d = [alpha,beta] -------------------
 // k0 = (alpha-1)/(2*alpha-1), k1 = 1/beta*(2*alpha-1)  (the reference's precedence, kept)
 template <> struct CamModel<ACM_MODEL_EUCM> {
-    template <bool BOUNDS>
+    template <bool BOUNDS, bool FAST = false>
     static __device__ __forceinline__ int project(const CamParams& c, double x, double y, double z, double& u, double& v) {
         const double alpha = c.d[0], beta = c.d[1];
         double d = sqrt(beta * (x * x + y * y) + z * z);
@@ -314,7 +320,7 @@ template <> struct CamModel<ACM_MODEL_EUCM> {
 // ---- Double Sphere (double_sphere.rs:361-390, :436-476, :177-184, :200-209), d = [alpha,xi] ---
 // k0 = w2, k1 = 1/(2*alpha-1)
 template <> struct CamModel<ACM_MODEL_DOUBLE_SPHERE> {
-    template <bool BOUNDS>
+    template <bool BOUNDS, bool FAST = false>
     static __device__ __forceinline__ int project(const CamParams& c, double x, double y, double z, double& u, double& v) {
         const double alpha = c.d[0], xi = c.d[1];
         double r2 = (x * x) + (y * y);
@@ -359,16 +365,19 @@ template <> struct CamModel<ACM_MODEL_DOUBLE_SPHERE> {
 
 // ---- FOV (fov.rs:284-316, :336-363), d = [w]; k0 = tan(w/2) from the host's libm -------------
 template <> struct CamModel<ACM_MODEL_FOV> {
-    template <bool BOUNDS>
+    template <bool BOUNDS, bool FAST = false>
     static __device__ __forceinline__ int project(const CamParams& c, double x, double y, double z, double& u, double& v) {
         const double w = c.d[0];
         if (z < ACM_SQRT_EPS) return ACM_POINT_AT_CAMERA_CENTER;
         double r2 = x * x + y * y;
-        double r = sqrt(r2);
         double t = c.k0;
         double rd;
         if (r2 < ACM_SQRT_EPS) rd = 2.0 * t / w;
-        else rd = acm_atan2_q1(2.0 * t * r, z) / (r * w);  // 2*t*r >= 0, z >= sqrt(EPS)
+        else if (FAST) {   // values only behind the branch: coupled sqrt / rsqrt and a reciprocal of w instead of sqrt + division
+            double ir;
+            const double r = acm_sqrt_inv(r2, ir);
+            rd = acm_atan2_q1(2.0 * t * r, z) * (ir * acm_rcp(w));
+        } else { const double r = sqrt(r2); rd = acm_atan2_q1(2.0 * t * r, z) / (r * w); }  // 2*t*r >= 0, z >= sqrt(EPS)
         double mx = x * rd, my = y * rd;
         u = c.fx * mx + c.cx;
         v = c.fy * my + c.cy;
