@@ -22,6 +22,6 @@ from .util import (InterpolationMethod, ProjectionError, compute_reprojection_er
 from .image_quality import (ImageQualityMetrics, calculate_psnr, calculate_ssim, compute_image_quality_metrics,
                             create_combined_projection_image, create_combined_projection_image_on_reference,
                             create_projection_image, model_projection_visualization)
-from .distributed import attach_communicator, attach_peers, shard_range
+from .distributed import ContextGroup, attach_communicator, attach_peers, shard_range
 
 __all__ = [n for n in dir() if not n.startswith("_")]

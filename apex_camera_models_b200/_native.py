@@ -18,7 +18,7 @@ INTERP_NEAREST, INTERP_BILINEAR = 0, 1
 
 OK = 0
 ERR_INVALID_ARG, ERR_CUDA, ERR_NCCL, ERR_INVALID_PARAMS, ERR_NUMERICAL = -1, -2, -3, -4, -5
-ERR_NO_DEVICE, ERR_ZERO_PROJECTION_POINTS, ERR_FOCAL_LENGTH, ERR_PRINCIPAL_POINT = -6, -7, -8, -9
+ERR_NO_DEVICE, ERR_ZERO_PROJECTION_POINTS, ERR_FOCAL_LENGTH, ERR_PRINCIPAL_POINT, ERR_PEER = -6, -7, -8, -9, -10
 
 
 class Camera(C.Structure):
@@ -40,7 +40,7 @@ class LMConfig(C.Structure):
 class LMResult(C.Structure):
     _fields_ = [("status", C.c_int32), ("iterations", C.c_int32), ("passes", C.c_int32),
                 ("initial_cost", C.c_double), ("final_cost", C.c_double), ("n_valid", C.c_uint64),
-                ("elapsed_ms", C.c_double)]
+                ("elapsed_ms", C.c_double), ("device_ms", C.c_double)]
 
 
 class ImageQuality(C.Structure):
@@ -53,6 +53,7 @@ class ProjectionError(C.Structure):
 
 
 _vp, _dp, _u8p = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint8)
+_vpp = C.POINTER(C.c_void_p)
 _cam = C.POINTER(Camera)
 
 # name -> (restype, argtypes).  Must list every symbol include/acm.h declares
@@ -121,6 +122,13 @@ SIGNATURES = {
     "acm_peer_export": (C.c_int32, [_vp, _u8p]),
     "acm_peer_attach": (C.c_int32, [_vp, C.c_int32, C.c_int32, _u8p]),
     "acm_peer_detach": (C.c_int32, [_vp]),
+    "acm_comm_init_all": (C.c_int32, [_vpp, C.c_int32]),
+    "acm_comm_destroy_all": (C.c_int32, [_vpp, C.c_int32]),
+    "acm_linearize_multi": (C.c_int32, [_vpp, C.c_int32, _cam, C.c_int32, _vpp, _vpp, C.POINTER(NormalEquations)]),
+    "acm_lm_solve_multi": (C.c_int32, [_vpp, C.c_int32, _cam, C.c_int32, _vpp, _vpp, _dp, _dp, C.POINTER(LMConfig), _dp, C.POINTER(LMResult)]),
+    "acm_linear_estimation_multi": (C.c_int32, [_vpp, C.c_int32, _cam, _vpp, _vpp]),
+    "acm_reprojection_error_multi": (C.c_int32, [_vpp, C.c_int32, _cam, _vpp, _vpp, C.POINTER(ProjectionError)]),
+    "acm_sample_points_multi": (C.c_int32, [_vpp, C.c_int32, _cam, C.c_size_t, _vpp, _vpp, C.POINTER(C.c_size_t)]),
 }
 
 

@@ -55,7 +55,9 @@ extern "C" int32_t acm_ctx_create(int32_t device, void* cuda_stream, acm_ctx** o
     ctx->cache3 = nullptr; ctx->cache2 = nullptr; ctx->cache_cap = 0;
     ctx->d_scratch = nullptr; ctx->scratch_cap = 0;
     for (int i = 0; i < ACM_FREE_LIST; ++i) { ctx->free_ptr[i] = nullptr; ctx->free_bytes[i] = 0; }
-    ctx->peer_local = nullptr; ctx->d_peer_ptrs = nullptr; ctx->peer_n = 0; ctx->peer_rank = 0; ctx->peer_seq = 0;
+    ctx->peer_local = nullptr; ctx->d_peer_ptrs = nullptr; ctx->peer_n = 0; ctx->peer_rank = 0; ctx->peer_seq = 0; ctx->peer_failed = false;
+    ctx->group = nullptr; ctx->lm_tag = 0; ctx->d_lm_ll = nullptr; ctx->lm_ll_cap = 0; ctx->coop_launch = 0;
+    ctx->h_small = nullptr; ctx->d_small_alias = nullptr; ctx->small_cap = 0;
     for (int i = 0; i < ACM_MAX_PEERS; ++i) ctx->peer_mapped[i] = nullptr;
 #define CREATE_CUDA(call)                                                                                     \
     do { cudaError_t _e = (call); if (_e != cudaSuccess) { int32_t rc = acm_fail(nullptr, ACM_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(_e)); delete ctx; return rc; } } while (0)
@@ -65,6 +67,7 @@ extern "C" int32_t acm_ctx_create(int32_t device, void* cuda_stream, acm_ctx** o
     ctx->sm_count = prop.multiProcessorCount;
     ctx->l2_bytes = (size_t)prop.l2CacheSize;
     ctx->cc = prop.major * 10 + prop.minor;
+    CREATE_CUDA(cudaDeviceGetAttribute(&ctx->coop_launch, cudaDevAttrCooperativeLaunch, device));
     if (cuda_stream) { ctx->stream = (cudaStream_t)cuda_stream; ctx->owns_stream = false; }
     else { CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->owns_stream = true; }
     CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
@@ -107,6 +110,7 @@ int32_t acm_device_malloc(acm_ctx* ctx, void** out, size_t bytes) {
 
 extern "C" int32_t acm_ctx_destroy(acm_ctx* ctx) {
     if (!ctx) return ACM_OK;
+    if (ctx->group) acm_group_dissolve(ctx);  // stops the group's workers and detaches every member (acm_multi.cu)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     acm_comm_destroy(ctx);
@@ -114,6 +118,8 @@ extern "C" int32_t acm_ctx_destroy(acm_ctx* ctx) {
     acm_points_destroy(ctx, ctx->cache3); acm_points_destroy(ctx, ctx->cache2);
     acm_free_list_release(ctx);
     cudaFree(ctx->peer_local);
+    cudaFree(ctx->d_lm_ll);
+    cudaFreeHost(ctx->h_small);
     cudaFree(ctx->d_scratch);
     cudaFree(ctx->d_partials); cudaFree(ctx->d_reduce); cudaFree(ctx->d_ticket); cudaFreeHost(ctx->h_reduce);
     cudaFree(ctx->d_lm); cudaFreeHost(ctx->h_lm);
@@ -127,13 +133,14 @@ extern "C" int32_t acm_ctx_destroy(acm_ctx* ctx) {
 }
 
 extern "C" int32_t acm_ctx_sync(acm_ctx* ctx) {
-    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_ENTER(ctx);
     ACM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return ACM_OK;
 }
 
 extern "C" int32_t acm_ctx_device_info(const acm_ctx* ctx, int64_t info[4]) {
     if (!ctx || !info) return ACM_ERR_INVALID_ARG;
+    acm_bind(ctx);
     info[0] = ctx->sm_count; info[1] = (int64_t)ctx->l2_bytes; info[2] = 0; info[3] = ctx->cc;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess) info[2] = (int64_t)prop.sharedMemPerBlockOptin;
@@ -141,12 +148,13 @@ extern "C" int32_t acm_ctx_device_info(const acm_ctx* ctx, int64_t info[4]) {
 }
 
 extern "C" int32_t acm_timer_start(acm_ctx* ctx) {
-    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_ENTER(ctx);
     ACM_CUDA(ctx, cudaEventRecord(ctx->t0, ctx->stream));
     return ACM_OK;
 }
 extern "C" int32_t acm_timer_stop(acm_ctx* ctx, float* elapsed_ms) {
     if (!ctx || !elapsed_ms) return ACM_ERR_INVALID_ARG;
+    acm_bind(ctx);
     ACM_CUDA(ctx, cudaEventRecord(ctx->t1, ctx->stream));
     ACM_CUDA(ctx, cudaEventSynchronize(ctx->t1));
     ACM_CUDA(ctx, cudaEventElapsedTime(elapsed_ms, ctx->t0, ctx->t1));
@@ -339,43 +347,45 @@ extern "C" int32_t acm_camera_fast_unproject(const acm_camera* cam) {
 // ---------------------------------------------------------------------------------------
 extern "C" int32_t acm_device_alloc(acm_ctx* ctx, size_t bytes, void** out) {
     if (!ctx || !out) return ACM_ERR_INVALID_ARG;
+    acm_bind(ctx);
     ACM_CUDA(ctx, cudaSetDevice(ctx->device));
     { int32_t rc = acm_device_malloc(ctx, out, bytes); if (rc) return rc; }
     return ACM_OK;
 }
 extern "C" int32_t acm_device_free(acm_ctx* ctx, void* p) {
-    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_ENTER(ctx);
     ACM_CUDA(ctx, cudaFree(p));
     return ACM_OK;
 }
 extern "C" int32_t acm_host_alloc_pinned(acm_ctx* ctx, size_t bytes, void** out) {
     if (!ctx || !out) return ACM_ERR_INVALID_ARG;
+    acm_bind(ctx);
     ACM_CUDA(ctx, cudaSetDevice(ctx->device));
     ACM_CUDA(ctx, cudaMallocHost(out, bytes ? bytes : 1));
     return ACM_OK;
 }
 extern "C" int32_t acm_host_free_pinned(acm_ctx* ctx, void* p) {
-    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_ENTER(ctx);
     ACM_CUDA(ctx, cudaFreeHost(p));
     return ACM_OK;
 }
 extern "C" int32_t acm_memcpy_h2d(acm_ctx* ctx, void* dst, const void* src, size_t bytes) {
-    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_ENTER(ctx);
     ACM_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     return ACM_OK;
 }
 extern "C" int32_t acm_memcpy_d2h(acm_ctx* ctx, void* dst, const void* src, size_t bytes) {
-    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_ENTER(ctx);
     ACM_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     return ACM_OK;
 }
 extern "C" int32_t acm_memcpy_d2d(acm_ctx* ctx, void* dst, const void* src, size_t bytes) {
-    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_ENTER(ctx);
     ACM_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     return ACM_OK;
 }
 extern "C" int32_t acm_memset_d(acm_ctx* ctx, void* dst, int value, size_t bytes) {
-    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_ENTER(ctx);
     ACM_CUDA(ctx, cudaMemsetAsync(dst, value, bytes, ctx->stream));
     return ACM_OK;
 }
@@ -410,6 +420,19 @@ int32_t acm_ensure_scratch(acm_ctx* ctx, size_t bytes) {
     return ACM_OK;
 }
 
+int32_t acm_kernel_blocks_per_sm(acm_ctx* ctx, const void* fn, int block, size_t smem, int* out) {
+    auto it = ctx->blocks_per_sm.find(fn);
+    if (it != ctx->blocks_per_sm.end()) { *out = it->second; return ACM_OK; }
+    // both the opt-in and the occupancy are properties of (kernel, device): cached per context, not per process
+    if (smem > 48 * 1024) ACM_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int b = 0;
+    ACM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, fn, block, smem));
+    if (b < 1) b = 1;
+    ctx->blocks_per_sm[fn] = b;
+    *out = b;
+    return ACM_OK;
+}
+
 int32_t acm_ensure_partials(acm_ctx* ctx, size_t doubles) {
     if (ctx->partials_cap >= doubles) return ACM_OK;
     ACM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -424,6 +447,7 @@ int32_t acm_ensure_partials(acm_ctx* ctx, size_t doubles) {
 // ---------------------------------------------------------------------------------------
 extern "C" int32_t acm_points_create(acm_ctx* ctx, int32_t dim, size_t n, int32_t dtype, acm_points** out) {
     if (!ctx || !out) return ACM_ERR_INVALID_ARG;
+    acm_bind(ctx);
     *out = nullptr;
     ACM_REQUIRE(ctx, dim == 2 || dim == 3, "points: dim must be 2 or 3");
     ACM_REQUIRE(ctx, dtype == ACM_F64 || dtype == ACM_F32, "points: dtype must be ACM_F64 or ACM_F32");
@@ -577,12 +601,12 @@ int32_t acm_points_upload_any(acm_ctx* ctx, acm_points* p, const double* host_ao
 }
 
 extern "C" int32_t acm_points_upload_aos_f64(acm_ctx* ctx, acm_points* p, const double* host_aos, size_t n) {
-    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_ENTER(ctx);
     return acm_points_upload_any(ctx, p, host_aos, n, 0);
 }
 
 extern "C" int32_t acm_points_download_aos_f64(acm_ctx* ctx, const acm_points* p, double* host_aos, size_t n) {
-    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_ENTER(ctx);
     ACM_REQUIRE(ctx, p && (host_aos || n == 0), "download: null argument");
     ACM_REQUIRE(ctx, n <= p->n, "download: more points than the buffer holds");
     if (n == 0) return ACM_OK;
@@ -609,11 +633,33 @@ extern "C" int32_t acm_points_download_aos_f64(acm_ctx* ctx, const acm_points* p
 static int32_t host_map(acm_ctx* ctx, const acm_camera* cam, const double* in_aos, size_t n, double* out_aos, uint8_t* status, bool is_project) {
     ACM_REQUIRE(ctx, cam && (n == 0 || (in_aos && out_aos)), "host map: null argument");
     if (n == 0) return ACM_OK;
+    if (n <= ACM_SMALL_BATCH) {
+        // scalar / small-batch calls (the trait's project(&p)): mapped pinned staging owned by the context, one kernel, one sync
+        const size_t in_dim = is_project ? 3 : 2, out_dim = is_project ? 2 : 3;
+        if (!ctx->h_small) {
+            const size_t bytes = (size_t)ACM_SMALL_BATCH * (5 * sizeof(double) + 8);
+            ACM_CUDA(ctx, cudaHostAlloc(&ctx->h_small, bytes, cudaHostAllocMapped));
+            ACM_CUDA(ctx, cudaHostGetDevicePointer(&ctx->d_small_alias, ctx->h_small, 0));
+            ctx->small_cap = ACM_SMALL_BATCH;
+        }
+        double* h_in = static_cast<double*>(ctx->h_small);
+        double* h_out = h_in + 3 * (size_t)ACM_SMALL_BATCH;
+        uint8_t* h_st = reinterpret_cast<uint8_t*>(h_in + 5 * (size_t)ACM_SMALL_BATCH);
+        double* d_in = static_cast<double*>(ctx->d_small_alias);
+        memcpy(h_in, in_aos, n * in_dim * sizeof(double));
+        int32_t rcs = acm_small_map(ctx, cam, d_in, d_in + 3 * (size_t)ACM_SMALL_BATCH,
+                                    reinterpret_cast<uint8_t*>(d_in + 5 * (size_t)ACM_SMALL_BATCH), (int)n, is_project);
+        if (rcs) return rcs;
+        ACM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        memcpy(out_aos, h_out, n * out_dim * sizeof(double));
+        if (status) memcpy(status, h_st, n);
+        return ACM_OK;
+    }
     acm_points *in = nullptr, *out = nullptr;
     uint8_t* d_st = nullptr;
     int32_t rc = acm_points_create(ctx, is_project ? 3 : 2, n, ACM_F64, &in);
     if (!rc) rc = acm_points_create(ctx, is_project ? 2 : 3, n, ACM_F64, &out);
-    if (!rc && cudaMalloc(&d_st, n) != cudaSuccess) rc = acm_fail(ctx, ACM_ERR_CUDA, "cudaMalloc status failed");
+    if (!rc) { rc = acm_ensure_scratch(ctx, n); d_st = static_cast<uint8_t*>(ctx->d_scratch); }
     if (!rc) rc = acm_points_upload_aos_f64(ctx, in, in_aos, n);
     if (!rc) rc = is_project ? acm_project(ctx, cam, in, out, d_st) : acm_unproject(ctx, cam, in, out, d_st);
     if (!rc) rc = acm_points_download_aos_f64(ctx, out, out_aos, n);
@@ -623,24 +669,23 @@ static int32_t host_map(acm_ctx* ctx, const acm_camera* cam, const double* in_ao
         if (e != cudaSuccess) rc = acm_fail(ctx, ACM_ERR_CUDA, "status download failed: %s", cudaGetErrorString(e));
     }
     cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_st);
     acm_points_destroy(ctx, in);
     acm_points_destroy(ctx, out);
     return rc;
 }
 
 extern "C" int32_t acm_project_host(acm_ctx* ctx, const acm_camera* cam, const double* xyz_aos, size_t n, double* uv_aos, uint8_t* status) {
-    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_ENTER(ctx);
     return host_map(ctx, cam, xyz_aos, n, uv_aos, status, true);
 }
 extern "C" int32_t acm_unproject_host(acm_ctx* ctx, const acm_camera* cam, const double* uv_aos, size_t n, double* xyz_aos, uint8_t* status) {
-    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_ENTER(ctx);
     return host_map(ctx, cam, uv_aos, n, xyz_aos, status, false);
 }
 
 extern "C" int32_t acm_undistort_rgb8_host(acm_ctx* ctx, const acm_camera* cam, const double* target_intrinsics, const uint8_t* frames_in,
                                            uint8_t* frames_out, size_t n_frames, int32_t interpolation) {
-    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_ENTER(ctx);
     ACM_REQUIRE(ctx, cam && (n_frames == 0 || (frames_in && frames_out)), "undistort_host: null argument");
     if (n_frames == 0) return ACM_OK;
     size_t fb = (size_t)cam->width * cam->height * 3;
@@ -670,10 +715,11 @@ struct NcclApi {
     int (*GetUniqueId)(void*);
     int (*CommInitRank)(void**, int, /*ncclUniqueId by value*/ NcclId, int);
     int (*CommDestroy)(void*);
+    int (*CommInitAll)(void**, int, const int*);
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
     const char* (*GetErrorString)(int);
 };
-static NcclApi g_nccl = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+static NcclApi g_nccl = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
 static int32_t load_nccl(acm_ctx* ctx) {
     if (g_nccl.handle) return ACM_OK;
@@ -686,6 +732,7 @@ static int32_t load_nccl(acm_ctx* ctx) {
     g_nccl.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
     g_nccl.CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(h, "ncclCommInitRank");
     g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+    g_nccl.CommInitAll = (int (*)(void**, int, const int*))dlsym(h, "ncclCommInitAll");
     g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
     g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
     if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce)
@@ -707,6 +754,7 @@ extern "C" int32_t acm_comm_get_unique_id(uint8_t id[128]) {
 
 extern "C" int32_t acm_comm_init_rank(acm_ctx* ctx, int32_t n_ranks, int32_t rank, const uint8_t id[128]) {
     if (!ctx || !id) return ACM_ERR_INVALID_ARG;
+    acm_bind(ctx);
     ACM_REQUIRE(ctx, n_ranks >= 1 && rank >= 0 && rank < n_ranks, "comm_init_rank: bad rank / size");
     ACM_REQUIRE(ctx, ctx->comm == nullptr, "comm_init_rank: communicator already attached");
     int32_t rc = load_nccl(ctx);
@@ -721,8 +769,21 @@ extern "C" int32_t acm_comm_init_rank(acm_ctx* ctx, int32_t n_ranks, int32_t ran
     return ACM_OK;
 }
 
+// One communicator per context of a single-process group (acm_comm_init_all).  libnccl missing is not an error here:
+// the fused NVLink exchange does not need it; the entry points that do (linear estimation, statistics) say so.
+int32_t acm_nccl_init_all(acm_ctx** ctxs, int32_t n) {
+    if (load_nccl(nullptr) != ACM_OK || !g_nccl.CommInitAll) return ACM_OK;
+    void* comms[ACM_MAX_PEERS];
+    int devs[ACM_MAX_PEERS];
+    for (int i = 0; i < n; ++i) devs[i] = ctxs[i]->device;
+    int r = g_nccl.CommInitAll(comms, n, devs);
+    if (r != 0) return acm_fail(ctxs[0], ACM_ERR_NCCL, "ncclCommInitAll: %s", nccl_err(r));
+    for (int i = 0; i < n; ++i) { ctxs[i]->comm = comms[i]; ctxs[i]->n_ranks = n; ctxs[i]->rank = i; }
+    return ACM_OK;
+}
+
 extern "C" int32_t acm_comm_destroy(acm_ctx* ctx) {
-    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_ENTER(ctx);
     if (ctx->comm && g_nccl.CommDestroy) { cudaStreamSynchronize(ctx->stream); g_nccl.CommDestroy(ctx->comm); }
     ctx->comm = nullptr; ctx->n_ranks = 1; ctx->rank = 0;
     return ACM_OK;
@@ -776,30 +837,46 @@ int32_t acm_rank_gather_to_host(acm_ctx* ctx, int count) {
 }
 
 // ---------------------------------------------------------------------------------------
-// NVLink peer exchange buffers (CUDA IPC; one process per GPU)
+// NVLink peer exchange buffers (CUDA IPC for one process per GPU; direct peer mappings in-process)
 // ---------------------------------------------------------------------------------------
+static int32_t peer_alloc_local(acm_ctx* ctx) {
+    if (ctx->peer_local) return ACM_OK;
+    ACM_CUDA(ctx, cudaMalloc(&ctx->peer_local, ACM_PEER_BUFFER_BYTES));
+    ACM_CUDA(ctx, cudaMemset(ctx->peer_local, 0, ACM_PEER_BUFFER_BYTES));
+    ACM_CUDA(ctx, cudaDeviceSynchronize());
+    return ACM_OK;
+}
+
 extern "C" int32_t acm_peer_export(acm_ctx* ctx, uint8_t handle[64]) {
     if (!ctx || !handle) return ACM_ERR_INVALID_ARG;
+    acm_bind(ctx);
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle is 64 bytes");
-    ACM_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (!ctx->peer_local) {
-        ACM_CUDA(ctx, cudaMalloc(&ctx->peer_local, ACM_PEER_BUFFER_DOUBLES * sizeof(double)));
-        ACM_CUDA(ctx, cudaMemset(ctx->peer_local, 0, ACM_PEER_BUFFER_DOUBLES * sizeof(double)));
-        ACM_CUDA(ctx, cudaDeviceSynchronize());
-    }
+    int32_t rc = peer_alloc_local(ctx);
+    if (rc) return rc;
     cudaIpcMemHandle_t h;
     ACM_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->peer_local));
     memcpy(handle, &h, 64);
     return ACM_OK;
 }
 
+// Shared by the IPC form and the in-process form: ptrs[r] = rank r's exchange buffer as seen from this device.
+// Every (re-)attach starts from a clean slate: zeroed cells, exchange counter 0, abort flag down.  All ranks must
+// have finished their previous exchanges (the caller's barrier) before any of them attaches again.
+int32_t acm_peer_setup_pointers(acm_ctx* ctx, int32_t n_ranks, int32_t rank, unsigned char* const* ptrs) {
+    ACM_CUDA(ctx, cudaMalloc(&ctx->d_peer_ptrs, ACM_MAX_PEERS * sizeof(unsigned char*)));
+    ACM_CUDA(ctx, cudaMemcpy(ctx->d_peer_ptrs, ptrs, n_ranks * sizeof(unsigned char*), cudaMemcpyHostToDevice));
+    ctx->peer_n = n_ranks; ctx->peer_rank = rank; ctx->peer_seq = 0; ctx->peer_failed = false;
+    if (ctx->n_ranks == 1) { ctx->n_ranks = n_ranks; ctx->rank = rank; }
+    return ACM_OK;
+}
+
 extern "C" int32_t acm_peer_attach(acm_ctx* ctx, int32_t n_ranks, int32_t rank, const uint8_t* handles) {
     if (!ctx || !handles) return ACM_ERR_INVALID_ARG;
+    acm_bind(ctx);
     ACM_REQUIRE(ctx, n_ranks >= 1 && n_ranks <= ACM_MAX_PEERS && rank >= 0 && rank < n_ranks, "peer_attach: bad rank / size (at most 8 ranks)");
     ACM_REQUIRE(ctx, ctx->peer_local != nullptr, "peer_attach: call acm_peer_export first");
     ACM_REQUIRE(ctx, ctx->peer_n == 0, "peer_attach: peers already attached");
-    ACM_CUDA(ctx, cudaSetDevice(ctx->device));
-    double* ptrs[ACM_MAX_PEERS];
+    unsigned char* ptrs[ACM_MAX_PEERS];
     for (int r = 0; r < n_ranks; ++r) {
         if (r == rank) { ptrs[r] = ctx->peer_local; continue; }
         cudaIpcMemHandle_t h;
@@ -811,22 +888,20 @@ extern "C" int32_t acm_peer_attach(acm_ctx* ctx, int32_t n_ranks, int32_t rank, 
             return acm_fail(ctx, ACM_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
         }
         ctx->peer_mapped[r] = p;
-        ptrs[r] = static_cast<double*>(p);
+        ptrs[r] = static_cast<unsigned char*>(p);
     }
-    ACM_CUDA(ctx, cudaMalloc(&ctx->d_peer_ptrs, ACM_MAX_PEERS * sizeof(double*)));
-    ACM_CUDA(ctx, cudaMemcpy(ctx->d_peer_ptrs, ptrs, n_ranks * sizeof(double*), cudaMemcpyHostToDevice));
-    ctx->peer_n = n_ranks; ctx->peer_rank = rank; ctx->peer_seq = 0;
-    if (ctx->n_ranks == 1) { ctx->n_ranks = n_ranks; ctx->rank = rank; }
-    return ACM_OK;
+    return acm_peer_setup_pointers(ctx, n_ranks, rank, ptrs);
 }
 
 extern "C" int32_t acm_peer_detach(acm_ctx* ctx) {
-    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_ENTER(ctx);
     if (ctx->peer_n == 0) return ACM_OK;
     cudaStreamSynchronize(ctx->stream);
     for (int r = 0; r < ACM_MAX_PEERS; ++r) if (ctx->peer_mapped[r]) { cudaIpcCloseMemHandle(ctx->peer_mapped[r]); ctx->peer_mapped[r] = nullptr; }
     cudaFree(ctx->d_peer_ptrs); ctx->d_peer_ptrs = nullptr;
-    ctx->peer_n = 0;
+    // the buffer itself stays (its IPC handle may be exported again); wipe it so that a re-attach starts clean
+    if (ctx->peer_local) { cudaMemset(ctx->peer_local, 0, ACM_PEER_BUFFER_BYTES); cudaDeviceSynchronize(); }
+    ctx->peer_n = 0; ctx->peer_seq = 0; ctx->peer_failed = false;
     if (!ctx->comm) { ctx->n_ranks = 1; ctx->rank = 0; }
     return ACM_OK;
 }

@@ -279,7 +279,7 @@ static int32_t launch_round_trip(acm_ctx* ctx, const CamParams& c, const acm_poi
 
 extern "C" int32_t acm_project_unproject(acm_ctx* ctx, const acm_camera* cam, const acm_points* xyz, acm_points* uv, acm_points* ray,
                                          uint8_t* d_status_project, uint8_t* d_status_unproject) {
-    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_ENTER(ctx);
     ACM_REQUIRE(ctx, cam && xyz && uv && ray, "acm_project_unproject: null argument");
     ACM_REQUIRE(ctx, xyz->dim == 3 && uv->dim == 2 && ray->dim == 3, "acm_project_unproject: xyz / ray must have dim 3 and uv dim 2");
     ACM_REQUIRE(ctx, xyz->n == uv->n && xyz->n == ray->n, "acm_project_unproject: point counts differ");
@@ -293,7 +293,7 @@ extern "C" int32_t acm_project_unproject(acm_ctx* ctx, const acm_camera* cam, co
 }
 
 extern "C" int32_t acm_project(acm_ctx* ctx, const acm_camera* cam, const acm_points* xyz, acm_points* uv, uint8_t* d_status) {
-    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_ENTER(ctx);
     ACM_REQUIRE(ctx, cam && xyz && uv, "acm_project: null argument");
     ACM_REQUIRE(ctx, xyz->dim == 3 && uv->dim == 2, "acm_project: xyz must have dim 3 and uv dim 2");
     ACM_REQUIRE(ctx, xyz->n == uv->n, "acm_project: point counts differ");
@@ -307,7 +307,7 @@ extern "C" int32_t acm_project(acm_ctx* ctx, const acm_camera* cam, const acm_po
 }
 
 extern "C" int32_t acm_unproject(acm_ctx* ctx, const acm_camera* cam, const acm_points* uv, acm_points* xyz, uint8_t* d_status) {
-    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_ENTER(ctx);
     ACM_REQUIRE(ctx, cam && xyz && uv, "acm_unproject: null argument");
     ACM_REQUIRE(ctx, xyz->dim == 3 && uv->dim == 2, "acm_unproject: xyz must have dim 3 and uv dim 2");
     ACM_REQUIRE(ctx, xyz->n == uv->n, "acm_unproject: point counts differ");
@@ -323,7 +323,7 @@ extern "C" int32_t acm_unproject(acm_ctx* ctx, const acm_camera* cam, const acm_
 // unproject with IEEE arithmetic to the end (what sample_points uses): statuses as acm_unproject, values
 // bit-identical to the reference for the arithmetic-only models (Pinhole, RadTan, UCM, EUCM, Double Sphere)
 extern "C" int32_t acm_unproject_ieee(acm_ctx* ctx, const acm_camera* cam, const acm_points* uv, acm_points* xyz, uint8_t* d_status) {
-    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_ENTER(ctx);
     ACM_REQUIRE(ctx, cam && xyz && uv, "acm_unproject_ieee: null argument");
     ACM_REQUIRE(ctx, xyz->dim == 3 && uv->dim == 2, "acm_unproject_ieee: xyz must have dim 3 and uv dim 2");
     ACM_REQUIRE(ctx, xyz->n == uv->n, "acm_unproject_ieee: point counts differ");
@@ -332,6 +332,43 @@ extern "C" int32_t acm_unproject_ieee(acm_ctx* ctx, const acm_camera* cam, const
     int32_t rc = acm_make_cam_params(ctx, cam, &c);
     if (rc) return rc;
     ACM_DISPATCH_MODEL(cam->model, return (launch_unproject<M, double, true>(ctx, c, uv, xyz, d_status)))
+    return ACM_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Small-batch host form (what a scalar `CameraModel::project(&p)` / `unproject(&uv)` of the trait binds): the points
+// sit in mapped pinned host memory in nalgebra's AoS order, one kernel reads them over PCIe and writes the results
+// (AoS) and the status bytes straight back -- one launch and one stream synchronisation per call, no allocation, no
+// staging copy on the device.  Same device functions as the batch kernels, hence the same bits.
+// ---------------------------------------------------------------------------------------
+template <int M, bool PROJECT>
+__global__ void __launch_bounds__(128) small_map_kernel(const __grid_constant__ CamParams c, const double* __restrict__ in, double* __restrict__ out,
+                                                        uint8_t* __restrict__ S, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int st;
+    if (PROJECT) {
+        double u, v;
+        st = CamModel<M>::template project<true, true>(c, in[3 * i], in[3 * i + 1], in[3 * i + 2], u, v);
+        if (st != ACM_POINT_OK) u = v = acm_nan();
+        out[2 * i] = u; out[2 * i + 1] = v;
+    } else {
+        double x, y, z;
+        st = CamModel<M>::template unproject<ACM_TAIL_DEFAULT>(c, in[2 * i], in[2 * i + 1], x, y, z);
+        if (st != ACM_POINT_OK) x = y = z = acm_nan();
+        out[3 * i] = x; out[3 * i + 1] = y; out[3 * i + 2] = z;
+    }
+    S[i] = (uint8_t)st;
+}
+
+int32_t acm_small_map(acm_ctx* ctx, const acm_camera* cam, const double* d_in, double* d_out, uint8_t* d_status, int n, bool is_project) {
+    CamParams c;
+    int32_t rc = acm_make_cam_params(ctx, cam, &c);
+    if (rc) return rc;
+    const int grid = (n + 127) / 128;
+    if (is_project) { ACM_DISPATCH_MODEL(cam->model, (small_map_kernel<M, true><<<grid, 128, 0, ctx->stream>>>(c, d_in, d_out, d_status, n))) }
+    else { ACM_DISPATCH_MODEL(cam->model, (small_map_kernel<M, false><<<grid, 128, 0, ctx->stream>>>(c, d_in, d_out, d_status, n))) }
+    ACM_CHECK_LAUNCH(ctx);
     return ACM_OK;
 }
 
@@ -885,7 +922,7 @@ static int32_t check_undistort_args(acm_ctx* ctx, const acm_camera* cam, const d
 
 extern "C" int32_t acm_undistort_rgb8(acm_ctx* ctx, const acm_camera* cam, const double* target_intrinsics, const uint8_t* d_in,
                                       uint8_t* d_out, size_t n_frames, int32_t interpolation) {
-    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_ENTER(ctx);
     double t[4];
     int32_t rc = check_undistort_args(ctx, cam, target_intrinsics, t);
     if (rc) return rc;
@@ -935,7 +972,7 @@ extern "C" int32_t acm_undistort_rgb8(acm_ctx* ctx, const acm_camera* cam, const
 }
 
 extern "C" int32_t acm_undistort_map(acm_ctx* ctx, const acm_camera* cam, const double* target_intrinsics, double* d_src_xy) {
-    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_ENTER(ctx);
     double t[4];
     int32_t rc = check_undistort_args(ctx, cam, target_intrinsics, t);
     if (rc) return rc;
@@ -1026,7 +1063,7 @@ __global__ void __launch_bounds__(256) synth_bytes_kernel(uint64_t seed, uint64_
 }
 
 extern "C" int32_t acm_synth_points3(acm_ctx* ctx, uint64_t seed, size_t first_index, double cos_theta_max, int32_t adversarial, acm_points* xyz) {
-    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_ENTER(ctx);
     ACM_REQUIRE(ctx, xyz && xyz->dim == 3, "synth_points3: need a dim-3 buffer");
     if (xyz->n == 0) return ACM_OK;
     int grid = grid_for(ctx, xyz->n, 256, 8);
@@ -1039,7 +1076,7 @@ extern "C" int32_t acm_synth_points3(acm_ctx* ctx, uint64_t seed, size_t first_i
 }
 
 extern "C" int32_t acm_synth_pixels(acm_ctx* ctx, uint64_t seed, size_t first_index, double width, double height, acm_points* uv) {
-    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_ENTER(ctx);
     ACM_REQUIRE(ctx, uv && uv->dim == 2, "synth_pixels: need a dim-2 buffer");
     if (uv->n == 0) return ACM_OK;
     int grid = grid_for(ctx, uv->n, 256, 8);
@@ -1052,7 +1089,7 @@ extern "C" int32_t acm_synth_pixels(acm_ctx* ctx, uint64_t seed, size_t first_in
 }
 
 extern "C" int32_t acm_synth_bytes(acm_ctx* ctx, uint64_t seed, size_t first_index, uint8_t* d_out, size_t n) {
-    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_ENTER(ctx);
     ACM_REQUIRE(ctx, d_out || n == 0, "synth_bytes: null output");
     if (n == 0) return ACM_OK;
     ACM_REQUIRE(ctx, ((uintptr_t)d_out & 3) == 0, "synth_bytes: output must be 4-byte aligned");

@@ -233,6 +233,7 @@ static double psnr_from_sums(unsigned long long sse, unsigned long long valid) {
 
 extern "C" int32_t acm_image_psnr(acm_ctx* ctx, const uint8_t* d_img1, const uint8_t* d_img2, uint32_t width, uint32_t height, double* psnr) {
     if (!ctx || !psnr) return ACM_ERR_INVALID_ARG;
+    acm_bind(ctx);
     const size_t npix = (size_t)width * height;
     ACM_REQUIRE(ctx, npix == 0 || (d_img1 && d_img2), "image_psnr: null image");
     int32_t rc = acm_ensure_scratch(ctx, 256);
@@ -246,6 +247,7 @@ extern "C" int32_t acm_image_psnr(acm_ctx* ctx, const uint8_t* d_img1, const uin
 
 extern "C" int32_t acm_image_ssim(acm_ctx* ctx, const uint8_t* d_img1, const uint8_t* d_img2, uint32_t width, uint32_t height, double* ssim) {
     if (!ctx || !ssim) return ACM_ERR_INVALID_ARG;
+    acm_bind(ctx);
     if (width < 3 || height < 3) { *ssim = 1.0; return ACM_OK; }   // no interior window: count == 0 (image_quality.rs:184-188)
     ACM_REQUIRE(ctx, d_img1 && d_img2, "image_ssim: null image");
     int32_t rc = acm_ensure_partials(ctx, (size_t)ctx->sm_count * 32 * 64);
@@ -265,7 +267,7 @@ extern "C" int32_t acm_image_ssim(acm_ctx* ctx, const uint8_t* d_img1, const uin
 
 extern "C" int32_t acm_draw_points_rgb8(acm_ctx* ctx, const acm_points* uv, const uint8_t* d_keep, uint8_t r, uint8_t g, uint8_t b,
                                         uint8_t* d_image, uint32_t width, uint32_t height) {
-    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_ENTER(ctx);
     ACM_REQUIRE(ctx, uv && d_image, "draw_points: null argument");
     ACM_REQUIRE(ctx, uv->dim == 2 && uv->dtype == ACM_F64, "draw_points: uv must be an f64 buffer of dim 2");
     if (uv->n == 0 || width == 0 || height == 0) return ACM_OK;
@@ -279,6 +281,7 @@ extern "C" int32_t acm_image_quality_metrics(acm_ctx* ctx, const acm_camera* inp
                                              uint32_t width, uint32_t height, const uint8_t* d_reference, uint8_t* d_combined,
                                              acm_image_quality* out) {
     if (!ctx || !out) return ACM_ERR_INVALID_ARG;
+    acm_bind(ctx);
     ACM_REQUIRE(ctx, input_model && output_model && xyz, "image_quality_metrics: null argument");
     ACM_REQUIRE(ctx, xyz->dim == 3 && xyz->dtype == ACM_F64, "image_quality_metrics: xyz must be an f64 buffer of dim 3");
     memset(out, 0, sizeof(*out));

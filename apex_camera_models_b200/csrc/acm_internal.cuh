@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <string>
+#include <unordered_map>
 
 #include "../../include/acm.h"
 
@@ -37,6 +38,9 @@ struct acm_points {
 };
 
 #define ACM_FREE_LIST 8
+
+// "flag-in-data" cell: a double split over two 8-byte words that each carry half of a 64-bit tag (acm_solver.cu)
+struct __align__(16) LLCell { unsigned long long w0, w1; };
 
 #define ACM_MAX_PEERS 8
 
@@ -79,21 +83,44 @@ struct acm_ctx {
     void* comm;
     int n_ranks, rank;
     // NVLink peer exchange (acm_peer_*)
-    double* peer_local;          // this rank's exchange buffer (exported through CUDA IPC)
-    void* peer_mapped[ACM_MAX_PEERS];  // peers' buffers opened in this process (nullptr for self)
-    double** d_peer_ptrs;        // device array [n_peers] of every rank's buffer, indexed by rank
+    unsigned char* peer_local;   // this rank's exchange buffer (exported through CUDA IPC, or peer-mapped in-process)
+    void* peer_mapped[ACM_MAX_PEERS];  // peers' buffers opened in this process through CUDA IPC (nullptr for self / in-process peers)
+    unsigned char** d_peer_ptrs; // device array [n_peers] of every rank's buffer, indexed by rank
     int peer_n, peer_rank;
-    unsigned long long peer_seq; // exchange counter, advances identically on every rank
+    unsigned long long peer_seq; // exchanges executed so far; advances by the executed count only, identically on every rank
+    bool peer_failed;            // an exchange timed out: the ranks are out of step until the peers are re-attached
+    struct acm_group* group;     // single-process multi-GPU group this context belongs to (acm_comm_init_all), or nullptr
+    unsigned long long lm_tag;   // hand-off tags already handed to lin_kernel launches (never reused)
+    LLCell* d_lm_ll;             // flag-in-data hand-off buffers of lin_kernel (block partials + broadcast)
+    size_t lm_ll_cap;            // in cells
+    int coop_launch;             // cudaDevAttrCooperativeLaunch
+    // per-device launch configuration of kernels that need an opt-in (dynamic shared memory above 48 KB) or an occupancy
+    // query: attributes and occupancy are per device, so they are cached per context, keyed by the kernel's address
+    std::unordered_map<const void*, int> blocks_per_sm;
+    // small-batch host path (acm_project_host / acm_unproject_host with few points): mapped pinned staging, no allocation per call
+    void* h_small; void* d_small_alias; size_t small_cap;
 };
 
-// exchange buffer: 2 alternating sets x ACM_MAX_PEERS rank slots x (64 values + flag + padding)
-#define ACM_PEER_SLOT_DOUBLES 72
-#define ACM_PEER_BUFFER_DOUBLES (2 * ACM_MAX_PEERS * ACM_PEER_SLOT_DOUBLES)
+// Make the context's device current on the calling thread (contexts of several GPUs may be driven by one thread).
+static inline void acm_bind(const acm_ctx* ctx) {
+    int d = -1;
+    if (cudaGetDevice(&d) != cudaSuccess || d != ctx->device) cudaSetDevice(ctx->device);
+}
+#define ACM_ENTER(ctx)                                  \
+    do {                                                \
+        if (!(ctx)) return ACM_ERR_INVALID_ARG;         \
+        acm_bind(ctx);                                  \
+    } while (0)
+
+// exchange buffer: 256-byte header (word 0 = sticky abort flag) + 2 alternating sets x ACM_MAX_PEERS rank slots x 64 cells
+#define ACM_PEER_HEADER_BYTES 256
+#define ACM_PEER_SLOT_CELLS 64
+#define ACM_PEER_BUFFER_BYTES (ACM_PEER_HEADER_BYTES + 2 * ACM_MAX_PEERS * ACM_PEER_SLOT_CELLS * sizeof(LLCell))
 
 struct PeerArgs {
-    double* const* bufs;         // nullptr: exchange disabled
+    unsigned char* const* bufs;  // nullptr: exchange disabled
     int n_ranks, rank;
-    unsigned long long seq;
+    unsigned long long seq;      // number of the (first) exchange this launch executes
 };
 
 int32_t acm_fail(acm_ctx* ctx, int32_t code, const char* fmt, ...);
@@ -125,11 +152,18 @@ int32_t acm_device_malloc(acm_ctx* ctx, void** out, size_t bytes);  // cudaMallo
 int32_t acm_ensure_stage(acm_ctx* ctx, size_t bytes);
 int32_t acm_ensure_host_stage(acm_ctx* ctx, size_t bytes);
 int32_t acm_ensure_partials(acm_ctx* ctx, size_t doubles);
-int32_t acm_ensure_scratch(acm_ctx* ctx, size_t bytes);  // ctx->d_scratch holds >= bytes afterwards (256-byte aligned)
+int32_t acm_ensure_scratch(acm_ctx* ctx, size_t bytes);
+// resident blocks per SM of a kernel on this context's device (cached); opts in to `smem` bytes of dynamic shared memory above 48 KB
+int32_t acm_kernel_blocks_per_sm(acm_ctx* ctx, const void* fn, int block, size_t smem, int* out);
+void acm_group_dissolve(acm_ctx* member);
+int32_t acm_peer_setup_pointers(acm_ctx* ctx, int32_t n_ranks, int32_t rank, unsigned char* const* ptrs);  // ctx->d_scratch holds >= bytes afterwards (256-byte aligned)
 int32_t acm_allreduce_sum_f64(acm_ctx* ctx, double* d_buf, size_t count);
 int32_t acm_allreduce_sum_u64(acm_ctx* ctx, unsigned long long* d_buf, size_t count);
 int32_t acm_allreduce_max_u8(acm_ctx* ctx, uint8_t* d_buf, size_t count);
 int32_t acm_rank_gather_to_host(acm_ctx* ctx, int count);  // d_reduce[0..count) of every rank -> h_reduce[rank][count]
+// project / unproject of n <= ACM_SMALL_BATCH AoS points that sit in device-visible (mapped pinned) memory (acm_exact.cu)
+#define ACM_SMALL_BATCH 2048
+int32_t acm_small_map(acm_ctx* ctx, const acm_camera* cam, const double* d_in, double* d_out, uint8_t* d_status, int n, bool is_project);
 int32_t acm_points_upload_any(acm_ctx* ctx, acm_points* p, const double* host_aos, size_t n, size_t dst_offset);
 
 template <typename T>

@@ -1,14 +1,23 @@
 // Fused linearisation kernel, deterministic reduction, device-resident Levenberg-Marquardt.
 //
-// One LM iteration = one streaming pass (linearize_kernel at the trial point: cost, H and g
-// together, "speculative linearisation") + an all-reduce of <= 54 doubles when a communicator
-// is attached + one single-thread step kernel (accept / reject, damping update, P x P
-// Cholesky with Jacobi scaling, next trial point).  The host only polls a done flag every
-// `check_every` iterations; kernels launched after convergence exit on their first load.
+// ONE kernel (`lin_kernel`, launched cooperatively so that every block is resident) serves
+//   * acm_linearize: one streaming pass over the resident correspondences -> <= 54 sums, and
+//   * acm_lm_solve:  the WHOLE solve -- pass, reduction, cross-GPU sum, LM step, next pass ... --
+//     without returning to the host (one launch, one read-back per solve).
 //
-// Determinism: fixed grid, per-thread sequential accumulation over a grid-stride range,
-// fixed shuffle tree, per-block partials, the last block to finish sums the partials in
-// block order.  No floating-point atomics.  The result depends on the grid size only.
+// Per pass: every thread accumulates the normal equations of its grid-stride share in registers
+// (cp.async ring), the block combines them (fixed shuffle tree + fixed warp order) and hands its
+// partial to the *reducer warp* of each sum: sum j is owned by warp 0 of block j (sums wrap around
+// when the grid is smaller), which adds the partials in a fixed order, exchanges the total with the
+// same warp on the other GPUs over NVLink peer memory, and broadcasts the result to every block.
+// All three hand-offs travel as "flag-in-data" cells (a double split over two 8-byte words, each
+// carrying half of a 64-bit tag -- 8-byte accesses are single-copy atomic, so a reader that sees
+// the tag sees the data): no fence, no atomic, no barrier, one L2 (or NVLink) trip per hand-off.
+// Every block then takes the LM step redundantly out of its own shared memory -- same arithmetic,
+// same inputs, hence identical decisions everywhere, on every block and on every GPU.
+//
+// Determinism: fixed grid, per-thread sequential accumulation, fixed combine order at every level,
+// rank-ordered cross-GPU sum.  No floating-point atomics.  Results depend on the grid size only.
 #include "acm_linearize.cuh"
 #include "acm_reduce.cuh"
 #include "acm_models.cuh"
@@ -26,14 +35,16 @@ struct LmState {
     double pred, dnorm, xnorm;
     double cost_tol, param_tol, grad_tol;
     double initial_cost, n_valid;
+    long long t_begin_ns, t_end_ns;  // %globaltimer at the first and after the last pass of a persistent solve
     int32_t max_iter, iterations, passes, status, done, first, P, pad;
 };
 static_assert(sizeof(LmState) <= 4096, "LmState must fit the context's 4 KiB slot");
+static_assert(sizeof(LmState) % sizeof(double) == 0, "LmState is copied as doubles");
+
+#define LM_STATUS_PEER_FAILURE 5
 
 // ---------------------------------------------------------------------------------------
-// LM step: serial algebra on P <= 9 unknowns, run by one thread out of shared memory.
-// Written for a small register footprint (arrays in the shared LmWork, rolled loops, not
-// inlined) because it is also called from the tail of the streaming kernel.
+// LM step: serial algebra on P <= 9 unknowns out of shared memory.
 // Divisions are hoisted into reciprocals (1/D_i, 1/L_ii): a serial f64 division costs ~250
 // cycles and the first version spent most of its 12 us on ~50 of them.
 // ---------------------------------------------------------------------------------------
@@ -49,7 +60,7 @@ struct LmWork {
 // the result goes back to w->st.  Reciprocals of the diagonal replace the divisions of the
 // substitutions (a dependent f64 division costs ~150 cycles).
 template <int P>
-__device__ __noinline__ bool chol_solve_work(LmWork* w) {
+__device__ __forceinline__ bool chol_solve_work(LmWork* w) {
     double L[P * (P + 1) / 2], inv[P], yv[P], x[P];
 #pragma unroll
     for (int i = 0; i < P; ++i)
@@ -95,9 +106,9 @@ __device__ inline double clampd(double v, double lo, double hi) { return v < lo 
 
 // Decision part of the step (thread 0): accept / reject the trial point, update the damping,
 // test convergence.  Returns true when the trial point was accepted.
-__device__ __noinline__ bool lm_decide(int P, LmState* s, const LmWork* w, double cost_t) {
+__device__ __forceinline__ bool lm_decide(int P, LmState* s, const LmWork* w, double cost_t) {
     s->passes++;
-    if (!(cost_t == cost_t)) { s->status = 4; s->done = 1; return false; }  // NaN sums (poisoned exchange or NaN observations): stop
+    if (!(cost_t == cost_t)) { s->status = 4; s->done = 1; return false; }  // NaN sums (NaN observations): stop
     if (s->first) {
         s->first = 0;
         s->initial_cost = cost_t;
@@ -127,28 +138,22 @@ __device__ __noinline__ bool lm_decide(int P, LmState* s, const LmWork* w, doubl
     return false;
 }
 
-// Cooperative step: `nthreads` (>= 81) threads copy the 1.1 KB state and the reduced accumulators
-// into shared memory; thread 0 decides and factors, the element-wise parts (copies, scaled matrix,
-// trial point, quadratic-model rows) are spread over the threads; the state is copied back.
-// The arithmetic of every scalar is the same as in the serial reference (oracle/acm_oracle_solver.c),
-// including the order of the few sums, so both walk the same trajectory.
+// Cooperative step on a state that already sits in shared memory (`sh`), with the reduced sums of
+// the pass in w->red (the pass ran at the trial point sh->xt).  Thread 0 decides and factors, the
+// element-wise parts (copies, scaled matrix, trial point, quadratic-model rows) are spread over the
+// first 81 threads.  The arithmetic of every scalar is the same as in the serial reference
+// (oracle/acm_oracle_solver.c), including the order of the few sums, so both walk the same
+// trajectory.  Every thread of the block must call it (barriers inside); on return the state is
+// consistent and visible to the whole block.
 template <int M, int KIND>
-__device__ __forceinline__ void lm_step_block(LmState* __restrict__ s, const double* __restrict__ red, LmState* sh, LmWork* w,
-                                              int tid, int nthreads) {
-    static_assert(sizeof(LmState) % sizeof(double) == 0, "LmState is copied as doubles");
-    constexpr int NW = sizeof(LmState) / sizeof(double);
+__device__ __forceinline__ void lm_step_smem(LmState* sh, LmWork* w, int tid) {
     constexpr int P = LinOps<M, KIND>::P;
     __shared__ int flag_accept, flag_ok;
     __shared__ double s_cost_t, s_cnt;
-    double* shw = reinterpret_cast<double*>(sh);
-    const double* gw = reinterpret_cast<const double*>(s);
-    for (int i = tid; i < NW; i += nthreads) shw[i] = __ldcg(gw + i);
-    for (int i = tid; i < LinOps<M, KIND>::NACC; i += nthreads) w->red[i] = __ldcg(red + i);
-    __syncthreads();
-    if (sh->done) return;
+    if (sh->done) return;  // uniform: shared state, read after the caller's barrier
     if (tid == 0) {
         double cost_t, cnt;
-        LinOps<M, KIND>::unpack(w->red, sh->xt, w->Ht, w->gt, &cost_t, &cnt);  // the pass ran at the trial point xt
+        LinOps<M, KIND>::unpack(w->red, sh->xt, w->Ht, w->gt, &cost_t, &cnt);
         s_cost_t = cost_t; s_cnt = cnt;
         flag_accept = lm_decide(P, sh, w, cost_t) ? 1 : 0;
     }
@@ -161,6 +166,7 @@ __device__ __forceinline__ void lm_step_block(LmState* __restrict__ s, const dou
     __syncthreads();
     if (!sh->done) {
         // next trial point from (H, g, lambda) at the accepted x
+        int ok;
         for (;;) {
             if (tid == 0) {
                 flag_ok = 1;
@@ -169,7 +175,8 @@ __device__ __forceinline__ void lm_step_block(LmState* __restrict__ s, const dou
             }
             if (tid < P) { const double d = sqrt(sh->H[tid * P + tid]); w->invD[tid] = (d > 1e-300) ? 1.0 / d : 1.0; }
             __syncthreads();
-            if (flag_ok < 0) break;
+            ok = flag_ok;
+            if (ok < 0) break;  // uniform; thread 0 does not touch the flag again on this path
             if (tid < P * P) {
                 const int i = tid / P, j = tid - i * P;
                 double a = sh->H[tid] * w->invD[i] * w->invD[j];
@@ -186,9 +193,11 @@ __device__ __forceinline__ void lm_step_block(LmState* __restrict__ s, const dou
                 }
             }
             __syncthreads();
-            if (flag_ok != 0) break;
+            ok = flag_ok;      // register copy taken between two barriers ...
+            __syncthreads();   // ... so nobody re-arms the flag at the loop top before everybody has read it
+            if (ok != 0) break;
         }
-        if (flag_ok > 0) {
+        if (ok > 0) {
             if (tid < P) {
                 sh->xt[tid] = clampd(sh->x[tid] + w->st[tid] * w->invD[tid], sh->lower[tid], sh->upper[tid]);
                 w->dx[tid] = sh->xt[tid] - sh->x[tid];
@@ -210,81 +219,142 @@ __device__ __forceinline__ void lm_step_block(LmState* __restrict__ s, const dou
         }
     }
     __syncthreads();
-    double* gout = reinterpret_cast<double*>(s);
-    for (int i = tid; i < NW; i += nthreads) gout[i] = shw[i];
 }
 
-// Stand-alone step kernel: used when an all-reduce sits between the pass and the step (N > 1).
+// Stand-alone step kernel: used when an NCCL all-reduce sits between the pass and the step (ranks
+// without NVLink peer buffers).
 template <int M, int KIND>
 __global__ void __launch_bounds__(128) lm_step_kernel(LmState* __restrict__ s, const double* __restrict__ red) {
     __shared__ LmState sh;
     __shared__ LmWork work;
-    lm_step_block<M, KIND>(s, red, &sh, &work, threadIdx.x, blockDim.x);
+    constexpr int NW = sizeof(LmState) / sizeof(double);
+    double* shw = reinterpret_cast<double*>(&sh);
+    const double* gw = reinterpret_cast<const double*>(s);
+    for (int i = threadIdx.x; i < NW; i += blockDim.x) shw[i] = __ldcg(gw + i);
+    for (int i = threadIdx.x; i < LinOps<M, KIND>::NACC; i += blockDim.x) work.red[i] = __ldcg(red + i);
+    __syncthreads();
+    if (sh.done) return;
+    lm_step_smem<M, KIND>(&sh, &work, threadIdx.x);
+    double* gout = reinterpret_cast<double*>(s);
+    for (int i = threadIdx.x; i < NW; i += blockDim.x) gout[i] = shw[i];
 }
 
 // ---------------------------------------------------------------------------------------
-// All-reduce over NVLink peer memory, fused into the tail of the streaming kernel.
-// Executed by the last block of every rank's kernel (the ranks run on different GPUs, so they are
-// all resident).  Rank r stores its NACC sums into slot [set][r] of EVERY rank's exchange buffer
-// (plain stores to peer-mapped addresses travel over NVLink), publishes them with a release store
-// of the exchange counter, waits (acquire loads of its own buffer) until all slots carry that
-// counter and adds the slots in rank order: the totals are bit-identical on every rank, which
-// keeps the ranks' LM decisions -- and therefore their kernel sequences -- in lock step.
-// Two slot sets alternate so that a rank that runs ahead by one exchange cannot overwrite data a
-// slower rank still has to read.  The spin is bounded: on time-out the sums are poisoned with NaN
-// (the solve then stops with status 4) instead of hanging the GPU.
+// Flag-in-data cells.  A double travels as two 8-byte words {data_lo32 | tag_lo32 << 32},
+// {data_hi32 | tag_hi32 << 32}; a reader accepts the cell once both halves carry the expected
+// 64-bit tag.  Tags are never reused (64-bit counters starting at 1; buffers start zeroed).
+// The accesses are volatile = relaxed at system scope: they bypass L1 and are coherent across
+// NVLink peers.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void ll_store(LLCell* p, double v, unsigned long long tag) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    const unsigned long long w0 = (b & 0xffffffffULL) | (tag << 32);
+    const unsigned long long w1 = (b >> 32) | (tag & 0xffffffff00000000ULL);
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(w0), "l"(w1) : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+__device__ __forceinline__ ulonglong2 ll_load(const LLCell* p) {
+    ulonglong2 r;
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ bool ll_ready(const ulonglong2 c, unsigned long long tag) {
+    return ((c.x >> 32) == (tag & 0xffffffffULL)) && ((c.y >> 32) == (tag >> 32));
+}
+__device__ __forceinline__ double ll_value(const ulonglong2 c) {
+    return __longlong_as_double((long long)((c.x & 0xffffffffULL) | (c.y << 32)));
+}
+__device__ __forceinline__ double acm_qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
+
+__device__ __forceinline__ unsigned long long acm_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+#define ACM_SPIN_LIMIT_CYCLES 4000000000LL  // ~2 s: a lost peer (or a bug) ends the solve instead of hanging the GPU
+
+// Warp-collective: total of col[0..nb) -- lane-strided sequential sums, then the fixed shuffle tree --
+// where the cells are filled by the other blocks of this grid.  Up to 8 cells per lane are polled
+// per trip (one L2 round trip per 256 blocks).
+__device__ __forceinline__ double warp_sum_cells(const LLCell* __restrict__ col, int nb, int lane, unsigned long long tag, bool& bad) {
+    double a = 0.0;
+    for (int b0 = lane; b0 < nb; b0 += 32 * 8) {
+        ulonglong2 c[8];
+        unsigned pending = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (b0 + 32 * j < nb) pending |= 1u << j;
+        const long long t0 = clock64();
+        while (pending) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (pending & (1u << j)) c[j] = ll_load(col + b0 + 32 * j);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if ((pending & (1u << j)) && ll_ready(c[j], tag)) pending &= ~(1u << j);
+            if (pending && clock64() - t0 > ACM_SPIN_LIMIT_CYCLES) { bad = true; break; }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (b0 + 32 * j < nb) a += ll_value(c[j]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+    bad = __any_sync(0xffffffffu, bad);
+    return __shfl_sync(0xffffffffu, a, 0);
+}
+
+// ---------------------------------------------------------------------------------------
+// All-reduce over NVLink peer memory, one sum per warp.  Lane r < n_ranks stores this rank's
+// value into cell [set][my rank][slot] of rank r's exchange buffer (a plain store to a peer-mapped
+// address travels over NVLink) and polls cell [set][r][slot] of its own buffer; the values are then
+// added in rank order, so the totals are bit-identical on every rank, which keeps the ranks' LM
+// decisions in lock step.  Two cell sets alternate (seq & 1): a rank can run at most one exchange
+// ahead of the slowest one, so it never overwrites a cell that is still being read.
+// A time-out (or a peer's abort flag) raises the sticky abort flag in EVERY rank's buffer: all ranks
+// leave with an error instead of drifting apart; the host must re-attach the peers afterwards.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ LLCell* peer_cell(unsigned char* buf, int set, int src_rank, int slot) {
+    return reinterpret_cast<LLCell*>(buf + ACM_PEER_HEADER_BYTES) + ((size_t)(set * ACM_MAX_PEERS + src_rank) * ACM_PEER_SLOT_CELLS + slot);
+}
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
     unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 
-template <int NACC>
-__device__ __forceinline__ void peer_exchange(const PeerArgs& peer, double* __restrict__ out) {
-    const int t = threadIdx.x;
-    const size_t set_off = (size_t)(peer.seq & 1ULL) * ACM_MAX_PEERS * ACM_PEER_SLOT_DOUBLES;
-    const size_t my_slot = set_off + (size_t)peer.rank * ACM_PEER_SLOT_DOUBLES;
-    __shared__ int timed_out;
-    if (t == 0) timed_out = 0;
-    // 1. my sums -> my slot in every rank's buffer
-    for (int i = t; i < NACC * peer.n_ranks; i += blockDim.x) {
-        const int r = i / NACC, k = i - r * NACC;
-        peer.bufs[r][my_slot + k] = __ldcg(out + k);
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (t < peer.n_ranks) st_release_sys(reinterpret_cast<unsigned long long*>(peer.bufs[t] + my_slot + 64), peer.seq);
-    // 2. wait for every rank's slot in my own buffer
-    if (t < peer.n_ranks) {
-        const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(peer.bufs[peer.rank] + set_off + (size_t)t * ACM_PEER_SLOT_DOUBLES + 64);
+__device__ __forceinline__ double warp_peer_exchange(const PeerArgs& peer, unsigned long long seq, int slot, double v, int lane, bool& bad) {
+    const int set = (int)(seq & 1ULL);
+    double mine = 0.0;
+    bool fail = false;
+    if (lane < peer.n_ranks) {
+        ll_store(peer_cell(peer.bufs[lane], set, peer.rank, slot), v, seq);
+        const LLCell* src = peer_cell(peer.bufs[peer.rank], set, lane, slot);
+        const unsigned long long* abort_word = reinterpret_cast<const unsigned long long*>(peer.bufs[peer.rank]);
         const long long t0 = clock64();
-        while (ld_acquire_sys(flag) != peer.seq) {
-            if (clock64() - t0 > 4000000000LL) { timed_out = 1; break; }  // ~2 s
-            __nanosleep(64);
+        unsigned polls = 0;
+        for (;;) {
+            const ulonglong2 c = ll_load(src);
+            if (ll_ready(c, seq)) { mine = ll_value(c); break; }
+            if ((++polls & 255u) == 0 && (ld_volatile_u64(abort_word) != 0ULL || clock64() - t0 > ACM_SPIN_LIMIT_CYCLES)) { fail = true; break; }
         }
     }
-    __syncthreads();
-    // 3. add the slots in rank order
-    if (t < NACC) {
-        const double* mine = peer.bufs[peer.rank] + set_off;
-        double tot = 0.0;
-        for (int r = 0; r < peer.n_ranks; ++r) tot += __ldcv(mine + (size_t)r * ACM_PEER_SLOT_DOUBLES + t);
-        out[t] = timed_out ? __longlong_as_double(0x7ff8000000000000LL) : tot;
+    fail = __any_sync(0xffffffffu, fail);
+    if (fail) {
+        if (lane < peer.n_ranks) st_volatile_u64(reinterpret_cast<unsigned long long*>(peer.bufs[lane]), 1ULL);  // sticky, every rank sees it
+        bad = true;
+        return acm_qnan();
     }
-    __threadfence();
-    __syncthreads();
+    double tot = 0.0;
+    for (int r = 0; r < peer.n_ranks; ++r) tot += __shfl_sync(0xffffffffu, mine, r);
+    return tot;
 }
 
 // ---------------------------------------------------------------------------------------
-// linearize kernel
+// Streaming part: per-model configuration
 // ---------------------------------------------------------------------------------------
-// Per-model streaming configuration, measured on 100 M points (scripts/lin_bench.py; GB/s register
-// prefetch -> cp.async ring): DEPTH > 0 = every thread keeps that many packets in flight in a
-// shared-memory ring fed by cp.async; 0 = the next packet is prefetched into registers.
+// Measured on 100 M points (scripts/lin_bench.py; GB/s register prefetch -> cp.async ring):
+// DEPTH > 0 = every thread keeps that many packets in flight in a shared-memory ring fed by cp.async;
+// 0 = the next packet is prefetched into registers.
 //   DS 5.88 -> 6.24 TB/s (3 deep), EUCM 5.63 -> 5.79, UCM 5.83 -> 6.47 (2 deep), FOV 4.50 -> 4.97
 //   (3 deep, 128 threads), RadTan 4.09 -> 4.25 (2 deep; 5.1 with the structured accumulation; 128-thread blocks capped at 168
 //   registers for 12 warps/SM measured 4.2-4.8); Pinhole (already at 7.1 TB/s) is faster without the ring.
@@ -306,134 +376,282 @@ template <int M> struct LinStream : LinStreamDefault<M> {};
 template <> struct LinStream<ACM_EXP_MODEL> { static constexpr int DEPTH = ACM_EXP_DEPTH, BLOCK = ACM_EXP_BLOCK, MIN_BLOCKS = ACM_EXP_MINB; };
 #endif
 
+struct LinKernelArgs {
+    LinParams hp;                 // parameters of a single evaluation (mode 0)
+    LmState* lm;                  // device-resident LM state (modes 1, 2)
+    int mode;                     // 0: one pass at hp -> out; 1: one pass at lm->xt (skipped when lm->done) -> out; 2: the whole LM solve
+    int max_passes;               // mode 2
+    PeerArgs peer;                // NVLink exchange (bufs == nullptr: single GPU, or the caller all-reduces `out` itself)
+    const double2 *X, *Y, *Z, *U, *V;
+    size_t n;
+    double pen2x2;                // 2 * invalid_penalty^2: cost of one invalid point
+    LLCell* partials;             // [NACC][gridDim.x] block partials
+    LLCell* bcast;                // [64] totals, reducer warps -> every block (mode 2)
+    unsigned long long tag0;      // first hand-off tag of this launch (mode 2 uses tag0 + pass)
+    double* out;                  // [NACC] totals (modes 0, 1)
+};
+
+// One streaming pass of this block over its grid-stride share + the block partial (fixed shuffle tree, then the
+// warps in order) handed to the reducer warps as tagged cells.
+// PRIMED: the first DEPTH packets of this pass are already in flight (issued while the previous pass's sums travelled).
 template <int M, int KIND, int BS>
-__global__ void __launch_bounds__(BS, (BS == LinStream<M>::BLOCK ? LinStream<M>::MIN_BLOCKS : 0)) linearize_kernel(LinParams hp, LmState* __restrict__ lm, int fuse_step, PeerArgs peer,
-                                                       const double2* __restrict__ X,
-                                                        const double2* __restrict__ Y, const double2* __restrict__ Z,
-                                                        const double2* __restrict__ U, const double2* __restrict__ V, size_t n,
-                                                        double pen2x2, double* __restrict__ partials, double* __restrict__ out,
-                                                        unsigned int* __restrict__ ticket) {
+__device__ __forceinline__ void lin_stream_pass(const LinKernelArgs& a, const LinParams& p_in, unsigned long long tag, bool primed, bool prime_next) {
     using LM_ = LinOps<M, KIND>;
-    constexpr int ND = LM_::ND;
     constexpr int NACC = LM_::NACC;
-    static_assert(NACC <= 64, "final-pass layout assumes <= 64 accumulators");
-
-    LinParams p = hp;
-    if (lm) {
-        // one round trip: the done flag and the trial parameters are fetched together
-        const int done = lm->done;
-        p.fx = lm->xt[0]; p.fy = lm->xt[1]; p.cx = lm->xt[2]; p.cy = lm->xt[3];
-#pragma unroll
-        for (int k = 0; k < ND; ++k) p.d[k] = lm->xt[4 + k];
-        if (done) return;  // converged earlier in this enqueue batch
-        lin_derive(M, p);
-    }
-
-    double acc[NACC];
-#pragma unroll
-    for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
-
-    const size_t npairs = n >> 1;
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr int NWARP = BS / 32;
     constexpr int DEPTH = LinStream<M>::DEPTH;
-    if constexpr (DEPTH > 0) {
+    __shared__ double wsum[NWARP][NACC];
+    extern __shared__ double2 lin_ring[];
+    const LinParams p = p_in;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nb = (int)gridDim.x;
+    const size_t npairs = a.n >> 1;
+    const size_t stride = (size_t)nb * BS;
+    const size_t i0 = (size_t)blockIdx.x * BS + tid;
+
     // cp.async ring: every thread keeps DEPTH packets (5 x 16 B each) in flight in its own
     // shared-memory slots -- deeper than a register prefetch could afford -- and reads them back with
     // five conflict-free LDS.128.  Only the owning thread touches a slot, so wait_group is all the
     // synchronisation needed.  ring[stage][array][thread].
-    extern __shared__ double2 lin_ring[];
-    const double2* const src[5] = {X, Y, Z, U, V};
+    const double2* const src[5] = {a.X, a.Y, a.Z, a.U, a.V};
     auto issue = [&](int stage, size_t idx) {
         if (idx < npairs) {
 #pragma unroll
-            for (int a = 0; a < 5; ++a) {
-                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&lin_ring[(stage * 5 + a) * BS + threadIdx.x]);
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src[a] + idx) : "memory");
+            for (int q = 0; q < 5; ++q) {
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&lin_ring[(stage * 5 + q) * BS + tid]);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src[q] + idx) : "memory");
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    auto prime = [&]() {
+        if constexpr (DEPTH > 0) {
 #pragma unroll
-    for (int s = 0; s < DEPTH; ++s) issue(s, i + (size_t)s * stride);
-    int stage = 0;
-#pragma unroll 1
-    while (i < npairs) {
-        asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH > 0 ? DEPTH - 1 : 0) : "memory");
-        const double2 x = lin_ring[(stage * 5 + 0) * BS + threadIdx.x], y = lin_ring[(stage * 5 + 1) * BS + threadIdx.x],
-                      z = lin_ring[(stage * 5 + 2) * BS + threadIdx.x], u = lin_ring[(stage * 5 + 3) * BS + threadIdx.x],
-                      v = lin_ring[(stage * 5 + 4) * BS + threadIdx.x];
-        LM_::point(acc, p, x.x, y.x, z.x, u.x, v.x);
-        LM_::point(acc, p, x.y, y.y, z.y, u.y, v.y);
-        issue(stage, i + (size_t)DEPTH * stride);  // after the packet has been consumed
-        stage = (stage + 1 == DEPTH) ? 0 : stage + 1;
-        i += stride;
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    } else {
-    // Software-pipelined stream: the five 16-byte loads of the next pair of points are in flight
-    // while the current pair is evaluated, so that the few resident warps (accumulators cost
-    // registers) still keep enough bytes in flight to cover the HBM latency.
-    double2 x, y, z, u, v;
-    if (i < npairs) { x = __ldcs(X + i); y = __ldcs(Y + i); z = __ldcs(Z + i); u = __ldcs(U + i); v = __ldcs(V + i); }
-#pragma unroll 1
-    while (i < npairs) {
-        const size_t nx = i + stride;
-        const size_t j = nx < npairs ? nx : i;  // clamp: the tail re-reads its own (cached) packet
-        const double2 x2 = __ldcs(X + j), y2 = __ldcs(Y + j), z2 = __ldcs(Z + j), u2 = __ldcs(U + j), v2 = __ldcs(V + j);
-        LM_::point(acc, p, x.x, y.x, z.x, u.x, v.x);
-        LM_::point(acc, p, x.y, y.y, z.y, u.y, v.y);
-        x = x2; y = y2; z = z2; u = u2; v = v2;
-        i = nx;
-    }
-    }
-    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
-        const size_t t = n - 1;
-        const double* Xs = reinterpret_cast<const double*>(X); const double* Ys = reinterpret_cast<const double*>(Y);
-        const double* Zs = reinterpret_cast<const double*>(Z); const double* Us = reinterpret_cast<const double*>(U);
-        const double* Vs = reinterpret_cast<const double*>(V);
-        LM_::point(acc, p, Xs[t], Ys[t], Zs[t], Us[t], Vs[t]);
-    }
+            for (int s = 0; s < DEPTH; ++s) issue(s, i0 + (size_t)s * stride);
+        }
+    };
+    if (!primed) prime();
 
-    if (GridReduce<NACC, 0, 0, BS>::run(acc, partials, out, ticket)) {
-        // invalid points carry the residual (pen, pen): cost += pen^2 per invalid point
-        if (threadIdx.x == 0 && pen2x2 != 0.0) out[LM_::COST] += pen2x2 * ((double)n - out[LM_::COUNT]);
-        if (peer.bufs) {
-            __threadfence();
-            __syncthreads();
-            peer_exchange<NACC>(peer, out);
+    double acc[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
+    size_t i = i0;
+    if constexpr (DEPTH > 0) {
+        int stage = 0;
+#pragma unroll 1
+        while (i < npairs) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH > 0 ? DEPTH - 1 : 0) : "memory");
+            const double2 x = lin_ring[(stage * 5 + 0) * BS + tid], y = lin_ring[(stage * 5 + 1) * BS + tid],
+                          z = lin_ring[(stage * 5 + 2) * BS + tid], u = lin_ring[(stage * 5 + 3) * BS + tid],
+                          v = lin_ring[(stage * 5 + 4) * BS + tid];
+            LM_::point(acc, p, x.x, y.x, z.x, u.x, v.x);
+            LM_::point(acc, p, x.y, y.y, z.y, u.y, v.y);
+            issue(stage, i + (size_t)DEPTH * stride);  // after the packet has been consumed
+            stage = (stage + 1 == DEPTH) ? 0 : stage + 1;
+            i += stride;
         }
-        if (lm && fuse_step) {
-            // single GPU: no all-reduce between the pass and the step, so the last block takes the
-            // LM step right here (saves a launch and the global round trip of the sums)
-            __shared__ LmState sh;
-            __shared__ LmWork work;
-            __threadfence();
-            __syncthreads();
-            lm_step_block<M, KIND>(lm, out, &sh, &work, threadIdx.x, BS);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else {
+        // Software-pipelined stream: the five 16-byte loads of the next pair of points are in flight
+        // while the current pair is evaluated.
+        double2 x, y, z, u, v;
+        if (i < npairs) { x = __ldcs(a.X + i); y = __ldcs(a.Y + i); z = __ldcs(a.Z + i); u = __ldcs(a.U + i); v = __ldcs(a.V + i); }
+#pragma unroll 1
+        while (i < npairs) {
+            const size_t nx = i + stride;
+            const size_t j = nx < npairs ? nx : i;  // clamp: the tail re-reads its own (cached) packet
+            const double2 x2 = __ldcs(a.X + j), y2 = __ldcs(a.Y + j), z2 = __ldcs(a.Z + j), u2 = __ldcs(a.U + j), v2 = __ldcs(a.V + j);
+            LM_::point(acc, p, x.x, y.x, z.x, u.x, v.x);
+            LM_::point(acc, p, x.y, y.y, z.y, u.y, v.y);
+            x = x2; y = y2; z = z2; u = u2; v = v2;
+            i = nx;
         }
+    }
+    unsigned long long npts = (i0 < npairs) ? 2ULL * (unsigned long long)((npairs - i0 + stride - 1) / stride) : 0ULL;
+    if ((a.n & 1) && blockIdx.x == 0 && tid == 0) {
+        const size_t t = a.n - 1;
+        const double* Xs = reinterpret_cast<const double*>(a.X); const double* Ys = reinterpret_cast<const double*>(a.Y);
+        const double* Zs = reinterpret_cast<const double*>(a.Z); const double* Us = reinterpret_cast<const double*>(a.U);
+        const double* Vs = reinterpret_cast<const double*>(a.V);
+        LM_::point(acc, p, Xs[t], Ys[t], Zs[t], Us[t], Vs[t]);
+        npts += 1;
+    }
+    // invalid points carry the residual (pen, pen): cost += pen^2 per invalid point
+    if (a.pen2x2 != 0.0) acc[LM_::COST] += a.pen2x2 * ((double)npts - acc[LM_::COUNT]);
+
+    // ---- block partial: fixed shuffle tree, then the warps in order
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) {
+        double v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) wsum[warp][k] = v;
+    }
+    __syncthreads();
+    if (tid < NACC) {
+        double v = wsum[0][tid];
+#pragma unroll
+        for (int k = 1; k < NWARP; ++k) v += wsum[k][tid];
+        ll_store(a.partials + (size_t)tid * nb + blockIdx.x, v, tag);
+    }
+    // the first packets of the next pass do not depend on its parameters: fetch them while the sums travel
+    if (prime_next) prime();
+    __syncthreads();  // wsum may be rewritten by the next pass
+}
+
+// One pass of the solve on this block: stream, reduce, (exchange,) collect the totals, LM step.
+// Everything below the kernel is force-inlined on purpose: a real (ABI) call inside the pass loop stacks the callee's
+// register frame on top of the caller's (measured with ptxas -v: +38 registers for a thin loop around a non-inlined pass
+// body, +70 for non-inlined reducers under an inlined streaming loop), which costs the streaming loop a resident block.
+// Returns false when the solve is over (uniform over the block -- and over the grid: every block holds the same state).
+template <int M, int KIND, int BS, bool SOLVE>
+__device__ __forceinline__ bool lin_pass(const LinKernelArgs& a, LmState* sh, LmWork* work, int pass) {
+    using LM_ = LinOps<M, KIND>;
+    constexpr int ND = LM_::ND;
+    constexpr int NACC = LM_::NACC;
+    constexpr int NWARP = BS / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nb = (int)gridDim.x;
+    const unsigned long long tag = a.tag0 + (unsigned long long)pass, seq = a.peer.seq + (unsigned long long)pass;
+
+    LinParams p = a.hp;
+    if (SOLVE) {
+        if (sh->done || pass >= a.max_passes) return false;
+        p.fx = sh->xt[0]; p.fy = sh->xt[1]; p.cx = sh->xt[2]; p.cy = sh->xt[3];
+#pragma unroll
+        for (int k = 0; k < ND; ++k) p.d[k] = sh->xt[4 + k];
+        lin_derive(M, p);
+    } else if (a.mode != 0) {
+        // one round trip: the done flag and the trial parameters are fetched together
+        const int done = a.lm->done;
+        p.fx = a.lm->xt[0]; p.fy = a.lm->xt[1]; p.cx = a.lm->xt[2]; p.cy = a.lm->xt[3];
+#pragma unroll
+        for (int k = 0; k < ND; ++k) p.d[k] = a.lm->xt[4 + k];
+        if (done) return false;  // converged earlier in this enqueue batch (uniform over the grid)
+        lin_derive(M, p);
+    }
+    lin_stream_pass<M, KIND, BS>(a, p, tag, SOLVE && pass > 0, SOLVE);
+
+    // ---- reducer warps: sum j belongs to warp (j / nb) % NWARP of block j % nb
+    bool bad = false;
+#pragma unroll 1
+    for (int slot = (int)blockIdx.x + nb * warp; slot < NACC; slot += nb * NWARP) {
+        double tot = warp_sum_cells(a.partials + (size_t)slot * nb, nb, lane, tag, bad);
+        if (a.peer.bufs && !bad) tot = warp_peer_exchange(a.peer, seq, slot, tot, lane, bad);
+        if (bad) tot = acm_qnan();
+        if (lane == 0) {
+            if (SOLVE) ll_store(a.bcast + slot, tot, tag);
+            else a.out[slot] = tot;
+        }
+    }
+    if (!SOLVE) return false;
+
+    // ---- every block: collect the totals, take the LM step out of shared memory
+    int nan_seen = 0;
+    if (tid < NACC) {
+        const long long t0 = clock64();
+        for (;;) {
+            const ulonglong2 c = ll_load(a.bcast + tid);
+            if (ll_ready(c, tag)) { const double v = ll_value(c); work->red[tid] = v; nan_seen = !(v == v); break; }
+            if (clock64() - t0 > ACM_SPIN_LIMIT_CYCLES) { nan_seen = 1; break; }
+        }
+    }
+    nan_seen = __syncthreads_or(nan_seen);
+    if (nan_seen) {
+        // a hand-off timed out or a sum is NaN: stop here (every block takes the same decision)
+        if (tid == 0) { sh->passes++; sh->status = 4; sh->done = 1; }
+        __syncthreads();
+    } else {
+        lm_step_smem<M, KIND>(sh, work, tid);
+    }
+    return true;
+}
+
+// Launch bounds: the one-pass form keeps the per-model tuning of LinStream.  The solve form carries the trial
+// parameters in registers (the one-pass form reads them from the constant bank) and peaks at 152-168 registers
+// outside the streaming loop; it runs in 128-thread blocks, three per SM (<= 170 registers, no spill), except for the
+// wide models (KB, RadTan), which are left uncapped.
+template <int M> struct SolveBounds { static constexpr int MIN_BLOCKS = (M == ACM_MODEL_KANNALA_BRANDT || M == ACM_MODEL_RADTAN) ? 0 : 3; };
+template <int M, int KIND, int BS, bool SOLVE>
+__global__ void __launch_bounds__(BS, (SOLVE ? (BS == 128 ? SolveBounds<M>::MIN_BLOCKS : 0) : (BS == LinStream<M>::BLOCK ? LinStream<M>::MIN_BLOCKS : 0))) lin_kernel(const __grid_constant__ LinKernelArgs a) {
+    static_assert(LinOps<M, KIND>::NACC <= 64, "hand-off layout assumes <= 64 accumulators");
+    constexpr int NSTATE = sizeof(LmState) / sizeof(double);
+    __shared__ LmState sh;
+    __shared__ LmWork work;
+    const int tid = threadIdx.x;
+    if (!SOLVE) {
+        lin_pass<M, KIND, BS, false>(a, &sh, &work, 0);
+        return;
+    }
+    double* shw = reinterpret_cast<double*>(&sh);
+    const double* gw = reinterpret_cast<const double*>(a.lm);
+    for (int i = tid; i < NSTATE; i += BS) shw[i] = __ldcg(gw + i);
+    __syncthreads();
+    if (blockIdx.x == 0 && tid == 0) sh.t_begin_ns = (long long)acm_globaltimer();
+#pragma unroll 1
+    for (int pass = 0; lin_pass<M, KIND, BS, SOLVE>(a, &sh, &work, pass); ++pass) {}
+    if constexpr (LinStream<M>::DEPTH > 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (blockIdx.x == 0) {
+        __syncthreads();
+        if (tid == 0) {
+            sh.t_end_ns = (long long)acm_globaltimer();
+            if (a.peer.bufs && ld_volatile_u64(reinterpret_cast<const unsigned long long*>(a.peer.bufs[a.peer.rank])) != 0ULL) sh.status = LM_STATUS_PEER_FAILURE;
+        }
+        __syncthreads();
+        double* gout = reinterpret_cast<double*>(a.lm);
+        for (int i = tid; i < NSTATE; i += BS) gout[i] = shw[i];
     }
 }
 
-template <int M, int KIND, int BS>
-static int32_t launch_linearize_bs(acm_ctx* ctx, const LinParams& hp, LmState* d_lm, int fuse_step, const PeerArgs& peer,
-                                   const acm_points* xyz, const acm_points* uv, double invalid_penalty) {
-    static int blocks_per_sm = 0;
-    constexpr size_t ring_bytes = (size_t)LinStream<M>::DEPTH * 5 * BS * sizeof(double2);
-    if (!blocks_per_sm) {
-        int b = 0;
-        if (ring_bytes > 0) ACM_CUDA(ctx, cudaFuncSetAttribute(linearize_kernel<M, KIND, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes));
-        ACM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, linearize_kernel<M, KIND, BS>, BS, ring_bytes));
-        blocks_per_sm = b > 0 ? b : 1;
-    }
-    const size_t n = xyz->n;
-    int grid = grid_for(ctx, (n >> 1) + 1, BS, blocks_per_sm);
-    int32_t rc = acm_ensure_partials(ctx, (size_t)ctx->sm_count * 32 * 64);
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+// Hand-off buffers of the kernel: [64 sums][blocks] partial cells + 64 broadcast cells, zeroed once
+// (tags start at 1 and never repeat).
+static int32_t ensure_ll(acm_ctx* ctx, size_t blocks) {
+    const size_t cells = 64 * blocks + 64;
+    if (ctx->lm_ll_cap >= cells) return ACM_OK;
+    ACM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->d_lm_ll); ctx->d_lm_ll = nullptr; ctx->lm_ll_cap = 0;
+    void* p = nullptr;
+    int32_t rc = acm_device_malloc(ctx, &p, cells * sizeof(LLCell));
     if (rc) return rc;
-    linearize_kernel<M, KIND, BS><<<grid, BS, ring_bytes, ctx->stream>>>(
-        hp, d_lm, fuse_step, peer, comp<double2>(xyz, 0), comp<double2>(xyz, 1), comp<double2>(xyz, 2), comp<double2>(uv, 0), comp<double2>(uv, 1), n,
-        2.0 * invalid_penalty * invalid_penalty, ctx->d_partials, ctx->d_reduce, ctx->d_ticket);
-    ACM_CHECK_LAUNCH(ctx);
+    ACM_CUDA(ctx, cudaMemsetAsync(p, 0, cells * sizeof(LLCell), ctx->stream));
+    ctx->d_lm_ll = static_cast<LLCell*>(p); ctx->lm_ll_cap = cells;
+    return ACM_OK;
+}
+
+template <int M, int KIND, int BS>
+static int32_t launch_lin_bs(acm_ctx* ctx, LinKernelArgs& a, const acm_points* xyz, const acm_points* uv) {
+    constexpr size_t ring_bytes = (size_t)LinStream<M>::DEPTH * 5 * BS * sizeof(double2);
+    const void* fn = a.mode == 2 ? reinterpret_cast<const void*>(&lin_kernel<M, KIND, BS, true>) : reinterpret_cast<const void*>(&lin_kernel<M, KIND, BS, false>);
+    int bps = 0;
+    int32_t rc = acm_kernel_blocks_per_sm(ctx, fn, BS, ring_bytes, &bps);
+    if (rc) return rc;
+    const size_t n = xyz->n;
+    const int grid = grid_for(ctx, (n >> 1) + 1, BS, bps);
+    rc = ensure_ll(ctx, (size_t)ctx->sm_count * 16);
+    if (rc) return rc;
+    ACM_REQUIRE(ctx, (size_t)grid <= (size_t)ctx->sm_count * 16, "linearize: grid larger than the hand-off buffer");
+    a.X = comp<double2>(xyz, 0); a.Y = comp<double2>(xyz, 1); a.Z = comp<double2>(xyz, 2);
+    a.U = comp<double2>(uv, 0); a.V = comp<double2>(uv, 1);
+    a.n = n;
+    a.partials = ctx->d_lm_ll;
+    a.bcast = ctx->d_lm_ll + (ctx->lm_ll_cap - 64);
+    a.out = ctx->d_reduce;
+    // tags: one per pass, never reused
+    a.tag0 = ctx->lm_tag + 1;
+    ctx->lm_tag += (a.mode == 2 ? (unsigned long long)a.max_passes : 1ULL) + 1ULL;
+    void* args[] = {&a};
+    if (ctx->coop_launch) {
+        ACM_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(BS), args, ring_bytes, ctx->stream));
+        ctx->launches++;
+    } else {
+        // no cooperative launch on this device / configuration: the grid never exceeds the resident capacity computed above
+        if (a.mode == 2) lin_kernel<M, KIND, BS, true><<<grid, BS, ring_bytes, ctx->stream>>>(a);
+        else lin_kernel<M, KIND, BS, false><<<grid, BS, ring_bytes, ctx->stream>>>(a);
+        ACM_CHECK_LAUNCH(ctx);
+    }
     return ACM_OK;
 }
 
@@ -441,16 +659,12 @@ static int32_t launch_linearize_bs(acm_ctx* ctx, const LinParams& hp, LmState* d
 // kernel past 128 registers/thread; 128-thread blocks then pack one more block per SM.
 // ACM_LIN_BLOCK=128|256 overrides (tuning aid).
 template <int M, int KIND>
-static int32_t launch_linearize(acm_ctx* ctx, const LinParams& hp, LmState* d_lm, int fuse_step, const PeerArgs& peer,
-                                const acm_points* xyz, const acm_points* uv, double invalid_penalty) {
-    static int bs = 0;
-    if (!bs) {
-        bs = LinStream<M>::BLOCK;
-        const char* e = getenv("ACM_LIN_BLOCK");
-        if (e && (atoi(e) == 128 || atoi(e) == 256)) bs = atoi(e);
-    }
-    if (bs == 128) return launch_linearize_bs<M, KIND, 128>(ctx, hp, d_lm, fuse_step, peer, xyz, uv, invalid_penalty);
-    return launch_linearize_bs<M, KIND, 256>(ctx, hp, d_lm, fuse_step, peer, xyz, uv, invalid_penalty);
+static int32_t launch_lin(acm_ctx* ctx, LinKernelArgs& a, const acm_points* xyz, const acm_points* uv) {
+    int bs = a.mode == 2 ? 128 : LinStream<M>::BLOCK;
+    const char* e = getenv("ACM_LIN_BLOCK");
+    if (e && (atoi(e) == 128 || atoi(e) == 256)) bs = atoi(e);
+    if (bs == 128) return launch_lin_bs<M, KIND, 128>(ctx, a, xyz, uv);
+    return launch_lin_bs<M, KIND, 256>(ctx, a, xyz, uv);
 }
 
 #define ACM_DISPATCH_LIN(model, kind, ...)                                                                       \
@@ -494,28 +708,44 @@ static void make_lin_params(const acm_camera* cam, LinParams* p) {
     lin_derive(cam->model, *p);
 }
 
-// Enqueue one pass (+ the cross-rank sum).  With peers attached the sum happens inside the kernel
-// (and so can the LM step); otherwise an NCCL all-reduce follows when a communicator is attached.
-// *fused_step tells the caller whether the kernel also takes the LM step.
+static bool peers_usable(const acm_ctx* ctx) { return ctx->peer_n > 1 && !getenv("ACM_NO_PEER_EXCHANGE"); }
+
+// A peer exchange that timed out leaves the ranks' exchange counters out of step: refuse to go on
+// until the host has re-attached the peers (acm_peer_detach + acm_peer_attach / acm_comm_init_all).
+static int32_t check_peer_state(acm_ctx* ctx) {
+    if (ctx->peer_failed)
+        return acm_fail(ctx, ACM_ERR_PEER, "the NVLink peer exchange failed earlier (time-out or a peer's abort); detach and re-attach the peers");
+    return ACM_OK;
+}
+static int32_t peer_failure(acm_ctx* ctx) {
+    ctx->peer_failed = true;
+    return acm_fail(ctx, ACM_ERR_PEER, "NVLink peer exchange timed out: a peer rank did not deliver its normal equations within ~2 s; "
+                                       "every rank was aborted, detach and re-attach the peers before the next call");
+}
+
+// Enqueue one pass (+ the cross-rank sum).  With peers attached the sum happens inside the kernel;
+// otherwise an NCCL all-reduce follows when a communicator is attached.  d_lm != nullptr: evaluate at
+// the trial point of the device-resident LM state (NCCL path of acm_lm_solve).
 static int32_t enqueue_linearize(acm_ctx* ctx, const acm_camera* cam, int32_t kind, LmState* d_lm, const acm_points* xyz,
-                                 const acm_points* uv, double invalid_penalty, int* nacc, int* fused_step) {
-    LinParams hp;
-    make_lin_params(cam, &hp);
-    PeerArgs peer{nullptr, 1, 0, 0ULL};
-    const bool use_peer = ctx->peer_n > 1 && !getenv("ACM_NO_PEER_EXCHANGE");
+                                 const acm_points* uv, double invalid_penalty, int* nacc) {
+    LinKernelArgs a;
+    memset(&a, 0, sizeof(a));
+    make_lin_params(cam, &a.hp);
+    a.lm = d_lm; a.mode = d_lm ? 1 : 0; a.max_passes = 1;
+    a.pen2x2 = 2.0 * invalid_penalty * invalid_penalty;
+    const bool use_peer = peers_usable(ctx) && !d_lm;
     if (use_peer) {
-        peer.bufs = ctx->d_peer_ptrs; peer.n_ranks = ctx->peer_n; peer.rank = ctx->peer_rank;
-        peer.seq = ++ctx->peer_seq;
+        int32_t rc = check_peer_state(ctx);
+        if (rc) return rc;
+        a.peer.bufs = ctx->d_peer_ptrs; a.peer.n_ranks = ctx->peer_n; a.peer.rank = ctx->peer_rank;
+        a.peer.seq = ++ctx->peer_seq;   // this launch executes exactly one exchange
     }
-    const bool need_nccl = !use_peer && ctx->comm && ctx->n_ranks > 1;
-    const int fuse = (d_lm && !need_nccl && !getenv("ACM_LM_NO_FUSE")) ? 1 : 0;
-    if (fused_step) *fused_step = fuse;
     ACM_DISPATCH_LIN(cam->model, kind, {
-        int32_t rc = launch_linearize<M, KIND>(ctx, hp, d_lm, fuse, peer, xyz, uv, invalid_penalty);
+        int32_t rc = launch_lin<M, KIND>(ctx, a, xyz, uv);
         if (rc) return rc;
         *nacc = LinOps<M, KIND>::NACC;
     });
-    if (need_nccl) return acm_allreduce_sum_f64(ctx, ctx->d_reduce, (size_t)*nacc);
+    if (!use_peer && ctx->comm && ctx->n_ranks > 1) return acm_allreduce_sum_f64(ctx, ctx->d_reduce, (size_t)*nacc);
     return ACM_OK;
 }
 
@@ -528,30 +758,46 @@ static int32_t unpack_host(acm_ctx* ctx, const acm_camera* cam, int32_t kind, co
     return ACM_OK;
 }
 
+// host copy of the abort word of this rank's exchange buffer (only consulted when a result came back NaN)
+static bool peer_abort_raised(acm_ctx* ctx) {
+    unsigned long long w = 0;
+    if (!ctx->peer_local) return false;
+    if (cudaMemcpyAsync(&w, ctx->peer_local, sizeof(w), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return false;
+    cudaStreamSynchronize(ctx->stream);
+    return w != 0ULL;
+}
+
 extern "C" int32_t acm_linearize_async(acm_ctx* ctx, const acm_camera* cam, int32_t residual_kind, const acm_points* xyz, const acm_points* uv) {
-    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_ENTER(ctx);
     int32_t rc = check_lin_args(ctx, cam, xyz, uv);
     if (rc) return rc;
     int nacc = 0;
-    return enqueue_linearize(ctx, cam, residual_kind, nullptr, xyz, uv, 0.0, &nacc, nullptr);
+    return enqueue_linearize(ctx, cam, residual_kind, nullptr, xyz, uv, 0.0, &nacc);
 }
 
 extern "C" int32_t acm_linearize(acm_ctx* ctx, const acm_camera* cam, int32_t residual_kind, const acm_points* xyz, const acm_points* uv,
                                  acm_normal_equations* out) {
     if (!ctx || !out) return ACM_ERR_INVALID_ARG;
+    acm_bind(ctx);
     int32_t rc = check_lin_args(ctx, cam, xyz, uv);
     if (rc) return rc;
     int nacc = 0;
-    rc = enqueue_linearize(ctx, cam, residual_kind, nullptr, xyz, uv, 0.0, &nacc, nullptr);
+    rc = enqueue_linearize(ctx, cam, residual_kind, nullptr, xyz, uv, 0.0, &nacc);
     if (rc) return rc;
     ACM_CUDA(ctx, cudaMemcpyAsync(ctx->h_reduce, ctx->d_reduce, nacc * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     ACM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (peers_usable(ctx)) {
+        bool any_nan = false;
+        for (int i = 0; i < nacc; ++i) any_nan = any_nan || !(ctx->h_reduce[i] == ctx->h_reduce[i]);
+        if (any_nan && peer_abort_raised(ctx)) return peer_failure(ctx);
+    }
     return unpack_host(ctx, cam, residual_kind, ctx->h_reduce, out);
 }
 
 extern "C" int32_t acm_linearize_host(acm_ctx* ctx, const acm_camera* cam, int32_t residual_kind, const double* xyz_aos, const double* uv_aos,
                                       size_t n, acm_normal_equations* out) {
     if (!ctx || !out) return ACM_ERR_INVALID_ARG;
+    acm_bind(ctx);
     ACM_REQUIRE(ctx, cam && (n == 0 || (xyz_aos && uv_aos)), "linearize_host: null argument");
     // device buffers are kept between calls (grow-only): a 4 GB cudaMalloc/cudaFree pair per call
     // would cost more than the kernel
@@ -590,6 +836,7 @@ extern "C" int32_t acm_lm_solve(acm_ctx* ctx, const acm_camera* init, int32_t re
                                 const double* lower, const double* upper, const acm_lm_config* cfg_in, double* out_params,
                                 acm_lm_result* result) {
     if (!ctx || !out_params || !result) return ACM_ERR_INVALID_ARG;
+    acm_bind(ctx);
     int32_t rc = check_lin_args(ctx, init, xyz, uv);
     if (rc) return rc;
     acm_lm_config cfg;
@@ -610,37 +857,63 @@ extern "C" int32_t acm_lm_solve(acm_ctx* ctx, const acm_camera* init, int32_t re
     h->lambda = cfg.lambda0; h->nu = 2.0;
     h->cost_tol = cfg.cost_tolerance; h->param_tol = cfg.parameter_tolerance; h->grad_tol = cfg.gradient_tolerance;
     h->max_iter = cfg.max_iterations; h->first = 1; h->P = P; h->status = 3;
+    const int max_passes = cfg.max_iterations + 2;
+    const bool use_peer = peers_usable(ctx);
+    const bool nccl_path = !use_peer && ctx->comm && ctx->n_ranks > 1;
+    if (use_peer) { rc = check_peer_state(ctx); if (rc) return rc; }
     ACM_CUDA(ctx, cudaMemcpyAsync(d, h, sizeof(LmState), cudaMemcpyHostToDevice, ctx->stream));
     // the host copy doubles as the read-back buffer: wait until the upload has consumed it
     ACM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 
-    int nacc = 0;
-    auto one_iteration = [&]() -> int32_t {
-        int fuse = 0;
-        int32_t r = enqueue_linearize(ctx, init, residual_kind, d, xyz, uv, cfg.invalid_penalty, &nacc, &fuse);
-        if (r) return r;
-        if (!fuse) {
-            ACM_DISPATCH_LIN(init->model, residual_kind, (lm_step_kernel<M, KIND><<<1, 128, 0, ctx->stream>>>(d, ctx->d_reduce)));
-            ACM_CHECK_LAUNCH(ctx);
+    double device_ms = 0.0;
+    if (!nccl_path) {
+        // the whole solve is ONE cooperative kernel: pass, reduction, NVLink exchange and LM step loop on the device
+        LinKernelArgs a;
+        memset(&a, 0, sizeof(a));
+        make_lin_params(init, &a.hp);
+        a.lm = d; a.mode = 2; a.max_passes = max_passes;
+        a.pen2x2 = 2.0 * cfg.invalid_penalty * cfg.invalid_penalty;
+        if (use_peer) {
+            a.peer.bufs = ctx->d_peer_ptrs; a.peer.n_ranks = ctx->peer_n; a.peer.rank = ctx->peer_rank;
+            a.peer.seq = ctx->peer_seq + 1;
         }
-        return ACM_OK;
-    };
-    const int max_passes = cfg.max_iterations + 2;
-    int enq = 0;
-    bool done = false;
-    while (!done && enq < max_passes) {
-        for (int k = 0; k < cfg.check_every && enq < max_passes; ++k, ++enq) {
-            rc = one_iteration();
+        ACM_DISPATCH_LIN(init->model, residual_kind, {
+            rc = launch_lin<M, KIND>(ctx, a, xyz, uv);
             if (rc) return rc;
-        }
+        });
         ACM_CUDA(ctx, cudaMemcpyAsync(h, d, sizeof(LmState), cudaMemcpyDeviceToHost, ctx->stream));
         ACM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        done = h->done != 0;
+        if (use_peer) ctx->peer_seq += (unsigned long long)h->passes;   // one exchange per executed pass, the same count on every rank
+        device_ms = (double)(h->t_end_ns - h->t_begin_ns) * 1e-6;
+        if (h->status == LM_STATUS_PEER_FAILURE) return peer_failure(ctx);
+    } else {
+        // NCCL path: one pass kernel + all-reduce + step kernel per iteration, `check_every` iterations enqueued blind
+        int nacc = 0;
+        int enq = 0;
+        bool done = false;
+        ACM_CUDA(ctx, cudaEventRecord(ctx->t0, ctx->stream));
+        while (!done && enq < max_passes) {
+            for (int k = 0; k < cfg.check_every && enq < max_passes; ++k, ++enq) {
+                rc = enqueue_linearize(ctx, init, residual_kind, d, xyz, uv, cfg.invalid_penalty, &nacc);
+                if (rc) return rc;
+                ACM_DISPATCH_LIN(init->model, residual_kind, (lm_step_kernel<M, KIND><<<1, 128, 0, ctx->stream>>>(d, ctx->d_reduce)));
+                ACM_CHECK_LAUNCH(ctx);
+            }
+            ACM_CUDA(ctx, cudaMemcpyAsync(h, d, sizeof(LmState), cudaMemcpyDeviceToHost, ctx->stream));
+            ACM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            done = h->done != 0;
+        }
+        ACM_CUDA(ctx, cudaEventRecord(ctx->t1, ctx->stream));
+        ACM_CUDA(ctx, cudaEventSynchronize(ctx->t1));
+        float ms = 0.f;
+        ACM_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->t0, ctx->t1));
+        device_ms = ms;
     }
     for (int i = 0; i < P; ++i) out_params[i] = h->x[i];
     result->status = h->status; result->iterations = h->iterations; result->passes = h->passes;
     result->initial_cost = h->initial_cost; result->final_cost = h->cost; result->n_valid = (uint64_t)h->n_valid;
     result->elapsed_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count();
+    result->device_ms = device_ms;
     return ACM_OK;
 }
 
@@ -682,7 +955,7 @@ __global__ void __launch_bounds__(256) project_jacobian_kernel(const __grid_cons
 
 extern "C" int32_t acm_project_jacobian(acm_ctx* ctx, const acm_camera* cam, const acm_points* xyz, acm_points* uv, double* d_jac,
                                         uint8_t* d_status) {
-    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_ENTER(ctx);
     ACM_REQUIRE(ctx, cam && xyz && uv && d_jac, "project_jacobian: null argument");
     ACM_REQUIRE(ctx, xyz->dim == 3 && uv->dim == 2 && xyz->n == uv->n, "project_jacobian: shape mismatch");
     ACM_REQUIRE(ctx, xyz->dtype == ACM_F64 && uv->dtype == ACM_F64, "project_jacobian: f64 buffers required");
@@ -726,7 +999,7 @@ __global__ void __launch_bounds__(256) project_point_jacobian_kernel(const __gri
 
 extern "C" int32_t acm_project_point_jacobian(acm_ctx* ctx, const acm_camera* cam, const acm_points* xyz, acm_points* uv, double* d_jac,
                                               uint8_t* d_status) {
-    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_ENTER(ctx);
     ACM_REQUIRE(ctx, cam && xyz && uv && d_jac, "project_point_jacobian: null argument");
     ACM_REQUIRE(ctx, xyz->dim == 3 && uv->dim == 2 && xyz->n == uv->n, "project_point_jacobian: shape mismatch");
     ACM_REQUIRE(ctx, xyz->dtype == ACM_F64 && uv->dtype == ACM_F64, "project_point_jacobian: f64 buffers required");

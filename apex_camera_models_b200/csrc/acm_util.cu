@@ -120,6 +120,7 @@ static int32_t select_kth(acm_ctx* ctx, const double* d_E, size_t n, unsigned lo
 extern "C" int32_t acm_reprojection_error(acm_ctx* ctx, const acm_camera* cam, const acm_points* xyz, const acm_points* uv,
                                           acm_projection_error* out) {
     if (!ctx || !out) return ACM_ERR_INVALID_ARG;
+    acm_bind(ctx);
     ACM_REQUIRE(ctx, cam && xyz && uv, "reprojection_error: null argument");
     ACM_REQUIRE(ctx, xyz->dim == 3 && uv->dim == 2 && xyz->n == uv->n, "reprojection_error: shape mismatch");
     ACM_REQUIRE(ctx, xyz->dtype == ACM_F64 && uv->dtype == ACM_F64, "reprojection_error: f64 buffers required");
@@ -263,6 +264,7 @@ extern "C" int32_t acm_sample_points(acm_ctx* ctx, const acm_camera* cam, size_t
 extern "C" int32_t acm_sample_points_shard(acm_ctx* ctx, const acm_camera* cam, size_t n_requested, int32_t shard, int32_t n_shards,
                                            acm_points** uv_out, acm_points** xyz_out, size_t* n_kept) {
     if (!ctx || !uv_out || !xyz_out || !n_kept) return ACM_ERR_INVALID_ARG;
+    acm_bind(ctx);
     *uv_out = nullptr; *xyz_out = nullptr; *n_kept = 0;
     ACM_REQUIRE(ctx, cam && cam->width > 0 && cam->height > 0, "sample_points: camera resolution must be set");
     ACM_REQUIRE(ctx, n_shards >= 1 && shard >= 0 && shard < n_shards, "sample_points: shard index out of range");
@@ -653,7 +655,7 @@ void solve_gram_svd(int k, dd* G /* k*k */, const dd* c, double eps, double* x) 
 }  // namespace
 
 extern "C" int32_t acm_linear_estimation(acm_ctx* ctx, acm_camera* cam, const acm_points* xyz, const acm_points* uv) {
-    if (!ctx) return ACM_ERR_INVALID_ARG;
+    ACM_ENTER(ctx);
     ACM_REQUIRE(ctx, cam && xyz && uv, "linear_estimation: null argument");
     ACM_REQUIRE(ctx, xyz->dim == 3 && uv->dim == 2, "linear_estimation: xyz must have dim 3 and uv dim 2");
     ACM_REQUIRE(ctx, xyz->dtype == ACM_F64 && uv->dtype == ACM_F64, "linear_estimation: f64 buffers required");
@@ -683,10 +685,24 @@ extern "C" int32_t acm_linear_estimation(acm_ctx* ctx, acm_camera* cam, const ac
         }
         return ACM_OK;
     };
+    // The minimum-point tests of the reference look at the whole correspondence set; with a communicator attached `n` is
+    // this rank's shard (possibly empty), so the ranks first agree on the global count -- every rank then takes the same
+    // branch and none is left waiting in a collective.
+    double n_global = (double)n;
+    if (ctx->n_ranks > 1) {
+        if (cam->model == ACM_MODEL_PINHOLE) return acm_fail(ctx, ACM_ERR_INVALID_ARG, "the pinhole model has no linear_estimation");
+        h[0] = (double)n;
+        ACM_CUDA(ctx, cudaMemcpyAsync(ctx->d_reduce, h, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        rc = acm_allreduce_sum_f64(ctx, ctx->d_reduce, 1);
+        if (rc) return rc;
+        ACM_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_reduce, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        ACM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        n_global = h[0];
+    }
     switch (cam->model) {
         case ACM_MODEL_UCM: case ACM_MODEL_EUCM: case ACM_MODEL_DOUBLE_SPHERE: {
             if (cam->model == ACM_MODEL_EUCM) {
-                if (n < 1) return acm_fail(ctx, ACM_ERR_INVALID_PARAMS, "Need at least 1 point for EUCM linear estimation");
+                if (n_global < 1) return acm_fail(ctx, ACM_ERR_INVALID_PARAMS, "Need at least 1 point for EUCM linear estimation");
                 cam->params[5] = 1.0;  // eucm.rs:236
             }
             double alpha = 0.0;
@@ -710,7 +726,7 @@ extern "C" int32_t acm_linear_estimation(acm_ctx* ctx, acm_camera* cam, const ac
             break;
         }
         case ACM_MODEL_KANNALA_BRANDT: {
-            if (n < 4) return acm_fail(ctx, ACM_ERR_INVALID_PARAMS, "Not enough points for linear estimation (need at least 4)");
+            if (n_global < 4) return acm_fail(ctx, ACM_ERR_INVALID_PARAMS, "Not enough points for linear estimation (need at least 4)");
             linest_kb_kernel<<<grid, 256, 0, ctx->stream>>>(fx, fy, cx, cy, X, Y, Z, U, V, n, ctx->d_partials, ctx->d_reduce, ctx->d_ticket);
             ACM_CHECK_LAUNCH(ctx);
             rc = fetch(29, 1);
@@ -726,7 +742,7 @@ extern "C" int32_t acm_linear_estimation(acm_ctx* ctx, acm_camera* cam, const ac
             break;
         }
         case ACM_MODEL_RADTAN: {
-            if (n < 3) return acm_fail(ctx, ACM_ERR_INVALID_PARAMS, "Need at least 3 points for RadTan linear estimation");
+            if (n_global < 3) return acm_fail(ctx, ACM_ERR_INVALID_PARAMS, "Need at least 3 points for RadTan linear estimation");
             linest_radtan_kernel<<<grid, 256, 0, ctx->stream>>>(fx, fy, cx, cy, X, Y, Z, U, V, n, ctx->d_partials, ctx->d_reduce, ctx->d_ticket);
             ACM_CHECK_LAUNCH(ctx);
             rc = fetch(18, 0);
@@ -741,7 +757,7 @@ extern "C" int32_t acm_linear_estimation(acm_ctx* ctx, acm_camera* cam, const ac
             return ACM_OK;  // rad_tan.rs:221-233: no validate_params
         }
         case ACM_MODEL_FOV: {
-            if (n < 2) return acm_fail(ctx, ACM_ERR_INVALID_PARAMS, "Need at least 2 point correspondences for linear estimation");
+            if (n_global < 2) return acm_fail(ctx, ACM_ERR_INVALID_PARAMS, "Need at least 2 point correspondences for linear estimation");
             constexpr int NW = 290, C32 = 10, C64 = 2, MAX_SHORT = 32;
             static_assert(NW % C32 == 0, "the pre-filter has no tail group");
             int gx = grid_for(ctx, n, 256, 1);
@@ -784,20 +800,8 @@ extern "C" int32_t acm_linear_estimation(acm_ctx* ctx, acm_camera* cam, const ac
             // shortlist falls back to the exact search over every candidate.  The decision uses
             // all-reduced sums, so every rank takes the same path.
             int n_short = 0;
-            double n_total = (double)n;
-            if (ctx->n_ranks > 1 || n >= 200000) {
-                // the pre-filter is only worth its extra launches on large inputs; the global size decides
-                // so that all ranks agree
-                h[0] = (double)n;
-                if (ctx->n_ranks > 1) {
-                    ACM_CUDA(ctx, cudaMemcpyAsync(ctx->d_reduce, h, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-                    rc = acm_allreduce_sum_f64(ctx, ctx->d_reduce, 1);
-                    if (rc) return rc;
-                    ACM_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_reduce, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-                    ACM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-                }
-                n_total = h[0];
-            }
+            // the pre-filter is only worth its extra launches on large inputs; the global size decides so that all ranks agree
+            const double n_total = n_global;
             if (n_total >= 200000.0) {
                 rc = evaluate(true, nullptr, NW);
                 if (rc) return rc;

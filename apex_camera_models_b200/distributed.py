@@ -96,3 +96,79 @@ def attach_peers(ctx: Context) -> int:
     ctx.peer_attach(world, rank, handles)
     dist.barrier()
     return world
+
+
+class ContextGroup:
+    """Multi-GPU from ONE host thread (acm_comm_init_all): one Context per device of this process, bound
+    into a group whose *_multi entry points drive every GPU from the calling thread -- the form a
+    single-threaded, launcher-less host like the reference's converter `main`
+    (bin/camera_converter.rs:127-343) binds.  Shards are lists with one `Points` per context."""
+
+    def __init__(self, devices):
+        import ctypes as C
+        from . import _native as N
+        self._C, self._N, self._lib = C, N, N.lib
+        self.ctxs = [Context(d) for d in devices]
+        self._arr = (C.c_void_p * len(self.ctxs))(*[c.handle.value for c in self.ctxs])
+        self.ctxs[0].check(self._lib.acm_comm_init_all(self._arr, len(self.ctxs)))
+        self._open = True
+
+    def __len__(self):
+        return len(self.ctxs)
+
+    def _handles(self, pts):
+        C = self._C
+        if len(pts) != len(self.ctxs):
+            raise ValueError("one shard per context expected")
+        return (C.c_void_p * len(pts))(*[p.handle.value for p in pts])
+
+    def linearize(self, cam_block, residual_kind, xyz, uv):
+        ne = self._N.NormalEquations()
+        self.ctxs[0].check(self._lib.acm_linearize_multi(self._arr, len(self), self._C.byref(cam_block), residual_kind, self._handles(xyz),
+                                                          self._handles(uv), self._C.byref(ne)))
+        return ne
+
+    def lm_solve(self, cam_block, residual_kind, xyz, uv, lower=None, upper=None, config=None):
+        C, N = self._C, self._N
+        P = cam_block.n_params
+        lo = (C.c_double * P)(*lower) if lower is not None else None
+        hi = (C.c_double * P)(*upper) if upper is not None else None
+        out = (C.c_double * N.ACM_MAX_PARAMS)()
+        res = N.LMResult()
+        self.ctxs[0].check(self._lib.acm_lm_solve_multi(self._arr, len(self), C.byref(cam_block), residual_kind, self._handles(xyz), self._handles(uv),
+                                                         lo, hi, C.byref(config) if config is not None else None, out, C.byref(res)))
+        return [out[i] for i in range(P)], res
+
+    def linear_estimation(self, cam_block, xyz, uv):
+        self.ctxs[0].check(self._lib.acm_linear_estimation_multi(self._arr, len(self), self._C.byref(cam_block), self._handles(xyz), self._handles(uv)))
+        return cam_block
+
+    def reprojection_error(self, cam_block, xyz, uv):
+        pe = self._N.ProjectionError()
+        self.ctxs[0].check(self._lib.acm_reprojection_error_multi(self._arr, len(self), self._C.byref(cam_block), self._handles(xyz), self._handles(uv),
+                                                                   self._C.byref(pe)))
+        return pe
+
+    def sample_points(self, cam_block, n_requested):
+        """Shard i of the grid on context i -> (uv shards, xyz shards, kept counts)."""
+        from .runtime import Points
+        C = self._C
+        n = len(self)
+        uv = (C.c_void_p * n)(); xyz = (C.c_void_p * n)(); kept = (C.c_size_t * n)()
+        self.ctxs[0].check(self._lib.acm_sample_points_multi(self._arr, n, C.byref(cam_block), n_requested, uv, xyz, kept))
+        U = [Points(c, 2, int(kept[i]), _handle=C.c_void_p(uv[i])) for i, c in enumerate(self.ctxs)]
+        X = [Points(c, 3, int(kept[i]), _handle=C.c_void_p(xyz[i])) for i, c in enumerate(self.ctxs)]
+        return U, X, [int(k) for k in kept]
+
+    def close(self):
+        if getattr(self, "_open", False):
+            self._lib.acm_comm_destroy_all(self._arr, len(self.ctxs))
+            for c in self.ctxs:
+                c.close()
+            self._open = False
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -64,6 +64,7 @@ class OptimizationResult:
     final_cost: float
     n_valid: int
     elapsed_ms: float
+    device_ms: float = 0.0   # first pass to last LM step on the device; device_ms / passes = per-iteration device time
 
     @property
     def converged(self) -> bool:
@@ -119,7 +120,7 @@ class OptimizationCost:
                                     lo, hi, C.byref(cfg), out, C.byref(res)))
         params = np.array(out[:P])
         self.model.set_params(params)
-        r = OptimizationResult(params, res.status, res.iterations, res.passes, res.initial_cost, res.final_cost, int(res.n_valid), res.elapsed_ms)
+        r = OptimizationResult(params, res.status, res.iterations, res.passes, res.initial_cost, res.final_cost, int(res.n_valid), res.elapsed_ms, res.device_ms)
         if verbose or (config and config.verbose):
             print(f"[LM] status={r.status} iterations={r.iterations} passes={r.passes} cost {r.initial_cost:.6e} -> {r.final_cost:.6e}")
         return r

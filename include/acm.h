@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define ACM_ABI_VERSION 1
+#define ACM_ABI_VERSION 2
 
 /* CameraModelEnum (reference src/camera/mod.rs:37-46); ids fixed by SURVEY.md section 8b */
 enum {
@@ -66,7 +66,8 @@ enum {
     ACM_ERR_NO_DEVICE = -6,
     ACM_ERR_ZERO_PROJECTION_POINTS = -7,  /* UtilError::ZeroProjectionPoints */
     ACM_ERR_FOCAL_LENGTH = -8,            /* CameraModelError::FocalLengthMustBePositive */
-    ACM_ERR_PRINCIPAL_POINT = -9          /* CameraModelError::PrincipalPointMustBeFinite */
+    ACM_ERR_PRINCIPAL_POINT = -9,         /* CameraModelError::PrincipalPointMustBeFinite */
+    ACM_ERR_PEER = -10                    /* NVLink peer exchange timed out / was aborted by a peer: re-attach the peers */
 };
 
 enum { ACM_F64 = 0, ACM_F32 = 1 };
@@ -193,7 +194,7 @@ typedef struct acm_lm_config {
     double gradient_tolerance;   /* 1e-6  (:414) max-norm of J^T r */
     double lambda0;              /* initial damping (1e-3) */
     double invalid_penalty;      /* residual given to invalid points; 0 = skipped */
-    int32_t check_every;         /* iterations enqueued between host polls of the done flag (4) */
+    int32_t check_every;         /* NCCL path only: iterations enqueued between host polls of the done flag (4) */
 } acm_lm_config;
 typedef struct acm_lm_result {
     int32_t status;      /* 0 cost tol, 1 parameter tol, 2 gradient tol, 3 max iterations, 4 stalled */
@@ -202,6 +203,7 @@ typedef struct acm_lm_result {
     double initial_cost, final_cost;
     uint64_t n_valid;
     double elapsed_ms;   /* host wall time of the solve */
+    double device_ms;    /* device time of the solve: first pass to last LM step (device_ms / passes = per-iteration device time) */
 } acm_lm_result;
 int32_t acm_lm_default_config(acm_lm_config* cfg);
 /* lower / upper: per-parameter box (Problem::set_variable_bounds), NULL = unbounded */
@@ -298,6 +300,29 @@ int32_t acm_comm_size(const acm_ctx* ctx); /* 1 when no communicator is attached
 int32_t acm_peer_export(acm_ctx* ctx, uint8_t handle[64]);
 int32_t acm_peer_attach(acm_ctx* ctx, int32_t n_ranks, int32_t rank, const uint8_t* handles /* n_ranks * 64 bytes */);
 int32_t acm_peer_detach(acm_ctx* ctx);
+
+/* ---- multi-GPU from ONE host thread (the converter `main`, reference
+ *      bin/camera_converter.rs:127-343, is single-threaded and has no launcher) ----------------
+ * acm_comm_init_all binds n contexts (one per GPU of this process) into a group: peer access between
+ * the devices, the NVLink exchange buffers of acm_peer_* mapped directly (no IPC) and -- when libnccl
+ * is present -- one NCCL communicator per context (ncclCommInitAll).  Afterwards every context behaves
+ * exactly like a rank of the one-process-per-GPU form, and the *_multi entry points below drive all of
+ * them from the calling thread: each context's share runs on a worker thread of the group, the caller
+ * blocks until all are done and gets rank 0's result (results are identical on every rank).
+ * xyz[i] / uv[i] = the shard resident on ctxs[i]'s GPU. */
+int32_t acm_comm_init_all(acm_ctx** ctxs, int32_t n);
+int32_t acm_comm_destroy_all(acm_ctx** ctxs, int32_t n);
+int32_t acm_linearize_multi(acm_ctx** ctxs, int32_t n, const acm_camera* cam, int32_t residual_kind, acm_points* const* xyz,
+                            acm_points* const* uv, acm_normal_equations* out);
+int32_t acm_lm_solve_multi(acm_ctx** ctxs, int32_t n, const acm_camera* init, int32_t residual_kind, acm_points* const* xyz,
+                           acm_points* const* uv, const double* lower, const double* upper, const acm_lm_config* cfg,
+                           double* out_params, acm_lm_result* result);
+int32_t acm_linear_estimation_multi(acm_ctx** ctxs, int32_t n, acm_camera* cam, acm_points* const* xyz, acm_points* const* uv);
+int32_t acm_reprojection_error_multi(acm_ctx** ctxs, int32_t n, const acm_camera* cam, acm_points* const* xyz, acm_points* const* uv,
+                                     acm_projection_error* out);
+/* shard i of acm_sample_points_shard on ctxs[i]; n_kept[i] = that shard's count */
+int32_t acm_sample_points_multi(acm_ctx** ctxs, int32_t n, const acm_camera* cam, size_t n_requested, acm_points** uv_out,
+                                acm_points** xyz_out, size_t* n_kept);
 
 #ifdef __cplusplus
 }

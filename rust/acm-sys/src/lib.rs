@@ -16,6 +16,7 @@ pub const ACM_ERR_NO_DEVICE: i32 = -6;
 pub const ACM_ERR_ZERO_PROJECTION_POINTS: i32 = -7;
 pub const ACM_ERR_FOCAL_LENGTH: i32 = -8;
 pub const ACM_ERR_PRINCIPAL_POINT: i32 = -9;
+pub const ACM_ERR_PEER: i32 = -10;
 pub const ACM_F64: i32 = 0;
 pub const ACM_F32: i32 = 1;
 pub const ACM_RESIDUAL_PIXEL: i32 = 0;
@@ -70,6 +71,7 @@ pub struct acm_lm_result {
     pub final_cost: f64,
     pub n_valid: u64,
     pub elapsed_ms: f64,
+    pub device_ms: f64,
 }
 
 #[repr(C)]
@@ -168,4 +170,13 @@ extern "C" {
     pub fn acm_peer_export(ctx: *mut acm_ctx, handle: *mut u8) -> i32;
     pub fn acm_peer_attach(ctx: *mut acm_ctx, n_ranks: i32, rank: i32, handles: *const u8) -> i32;
     pub fn acm_peer_detach(ctx: *mut acm_ctx) -> i32;
+
+    // multi-GPU from one host thread (the converter `main` is single-threaded: bin/camera_converter.rs:127-343)
+    pub fn acm_comm_init_all(ctxs: *mut *mut acm_ctx, n: i32) -> i32;
+    pub fn acm_comm_destroy_all(ctxs: *mut *mut acm_ctx, n: i32) -> i32;
+    pub fn acm_linearize_multi(ctxs: *mut *mut acm_ctx, n: i32, cam: *const acm_camera, residual_kind: i32, xyz: *const *mut acm_points, uv: *const *mut acm_points, out: *mut acm_normal_equations) -> i32;
+    pub fn acm_lm_solve_multi(ctxs: *mut *mut acm_ctx, n: i32, init: *const acm_camera, residual_kind: i32, xyz: *const *mut acm_points, uv: *const *mut acm_points, lower: *const f64, upper: *const f64, cfg: *const acm_lm_config, out_params: *mut f64, result: *mut acm_lm_result) -> i32;
+    pub fn acm_linear_estimation_multi(ctxs: *mut *mut acm_ctx, n: i32, cam: *mut acm_camera, xyz: *const *mut acm_points, uv: *const *mut acm_points) -> i32;
+    pub fn acm_reprojection_error_multi(ctxs: *mut *mut acm_ctx, n: i32, cam: *const acm_camera, xyz: *const *mut acm_points, uv: *const *mut acm_points, out: *mut acm_projection_error) -> i32;
+    pub fn acm_sample_points_multi(ctxs: *mut *mut acm_ctx, n: i32, cam: *const acm_camera, n_requested: size_t, uv_out: *mut *mut acm_points, xyz_out: *mut *mut acm_points, n_kept: *mut size_t) -> i32;
 }

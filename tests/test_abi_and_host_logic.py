@@ -48,7 +48,7 @@ def test_no_device_fails_loudly():
 
 
 def test_abi_version_and_param_counts():
-    assert N.lib.acm_abi_version() == 1
+    assert N.lib.acm_abi_version() == 2
     assert [N.lib.acm_n_params(m) for m in range(7)] == [4, 9, 8, 5, 6, 6, 5]
     assert N.lib.acm_n_params(7) < 0
 

@@ -10,10 +10,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIBDIR = os.path.join(ROOT, "apex_camera_models_b200", "lib")
 
 
-def _build(tmp_path):
-    exe = str(tmp_path / "host_test")
+def _build(tmp_path, name="host_test"):
+    exe = str(tmp_path / name)
     cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
-           os.path.join(ROOT, "tests", "cpp", "host_test.cpp"), "-o", exe, "-L", LIBDIR, "-lacm", f"-Wl,-rpath,{LIBDIR}"]
+           os.path.join(ROOT, "tests", "cpp", name + ".cpp"), "-o", exe, "-L", LIBDIR, "-lacm", f"-Wl,-rpath,{LIBDIR}"]
     subprocess.run(cmd, check=True)
     return exe
 
@@ -33,3 +33,23 @@ def test_cpp_host_layer_runs_reference_unit_tests(tmp_path):
     r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
     assert "HOST_TEST_OK" in r.stdout
+
+
+def test_single_process_multi_gpu_test_compiles_and_fails_loudly_without_gpu(tmp_path):
+    import torch
+    exe = _build(tmp_path, "multi_gpu_test")
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: covered by the gpu-marked test")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode != 0 and "no CUDA device" in r.stderr
+
+
+@pytest.mark.gpu
+def test_single_process_multi_gpu_and_scalar_host_path(tmp_path):
+    """acm_comm_init_all + acm_*_multi from one host thread (2 contexts in one process) against the same pipeline
+    on one GPU, plus the scalar acm_project_host path.  The multi-GPU half reports MULTI_GPU_SKIPPED on a 1-GPU box."""
+    exe = _build(tmp_path, "multi_gpu_test")
+    r = subprocess.run([exe, "2"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "MULTI_TEST_OK" in r.stdout
+    print(r.stdout)
