@@ -922,20 +922,21 @@ extern "C" int32_t acm_lm_solve(acm_ctx* ctx, const acm_camera* init, int32_t re
 // per-model doc-comments double_sphere.rs:326-332 "2x6", kannala_brandt.rs:309-313 "2x8"):
 // uv + the 2xP Jacobian w.r.t. [fx,fy,cx,cy,dist..], written as 2P rows of n doubles.
 // ---------------------------------------------------------------------------------------
-template <int M>
+// Two points per thread: 16-byte loads of x, y, z, 16-byte streaming stores of u, v and of every Jacobian row (the rows are
+// n doubles apart, so a row pair is 16-byte aligned whenever n is even and the base is); the odd tail and unaligned
+// buffers go through the scalar form of the same body.
+template <int M, int NV>
 __global__ void __launch_bounds__(256) project_jacobian_kernel(const __grid_constant__ CamParams c, LinParams p, const double* __restrict__ X,
                                                                const double* __restrict__ Y, const double* __restrict__ Z,
                                                                double* __restrict__ U, double* __restrict__ V, double* __restrict__ J,
                                                                uint8_t* __restrict__ S, size_t n) {
     using LM_ = Lin<M, ACM_RESIDUAL_PIXEL>;
     constexpr int ND = LM_::ND, P = 4 + ND;
+    const size_t npk = n / NV;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const double x = X[i], y = Y[i], z = Z[i];
-        double u, v;
+    auto one = [&](double x, double y, double z, double& u, double& v, double* row_u, double* row_v) -> int {
         int st = CamModel<M>::template project<false>(c, x, y, z, u, v);
         double ru, rv, au[2 + ND], av[2 + ND];
-        double row_u[P], row_v[P];
 #pragma unroll
         for (int k = 0; k < P; ++k) row_u[k] = row_v[k] = 0.0;
         if (st == ACM_POINT_OK && LM_::eval(p, x, y, z, 0.0, 0.0, ru, rv, au, av)) {
@@ -946,10 +947,30 @@ __global__ void __launch_bounds__(256) project_jacobian_kernel(const __grid_cons
             if (st == ACM_POINT_OK) st = ACM_POINT_NUMERICAL_ERROR;
             u = v = acm_nan();
         }
-        U[i] = u; V[i] = v;
-        if (S) S[i] = (uint8_t)st;
+        return st;
+    };
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npk; i += stride) {
+        if constexpr (NV == 2) {
+            const double2 x = __ldcs(reinterpret_cast<const double2*>(X) + i), y = __ldcs(reinterpret_cast<const double2*>(Y) + i),
+                          z = __ldcs(reinterpret_cast<const double2*>(Z) + i);
+            double u0, v0, u1, v1, ru0[P], rv0[P], ru1[P], rv1[P];
+            const int s0 = one(x.x, y.x, z.x, u0, v0, ru0, rv0), s1 = one(x.y, y.y, z.y, u1, v1, ru1, rv1);
+            __stcs(reinterpret_cast<double2*>(U) + i, make_double2(u0, u1));
+            __stcs(reinterpret_cast<double2*>(V) + i, make_double2(v0, v1));
+            if (S) __stcs(reinterpret_cast<uchar2*>(S) + i, make_uchar2((uint8_t)s0, (uint8_t)s1));
 #pragma unroll
-        for (int k = 0; k < P; ++k) { J[(size_t)k * n + i] = row_u[k]; J[(size_t)(P + k) * n + i] = row_v[k]; }
+            for (int k = 0; k < P; ++k) {
+                __stcs(reinterpret_cast<double2*>(J + (size_t)k * n) + i, make_double2(ru0[k], ru1[k]));
+                __stcs(reinterpret_cast<double2*>(J + (size_t)(P + k) * n) + i, make_double2(rv0[k], rv1[k]));
+            }
+        } else {
+            double u, v, row_u[P], row_v[P];
+            const int st = one(X[i], Y[i], Z[i], u, v, row_u, row_v);
+            U[i] = u; V[i] = v;
+            if (S) S[i] = (uint8_t)st;
+#pragma unroll
+            for (int k = 0; k < P; ++k) { J[(size_t)k * n + i] = row_u[k]; J[(size_t)(P + k) * n + i] = row_v[k]; }
+        }
     }
 }
 
@@ -966,9 +987,16 @@ extern "C" int32_t acm_project_jacobian(acm_ctx* ctx, const acm_camera* cam, con
     make_lin_params(cam, &p);
     const size_t n = xyz->n;
     if (n == 0) return ACM_OK;
-    int grid = grid_for(ctx, n, 256, 4);
-    ACM_DISPATCH_MODEL(cam->model, (project_jacobian_kernel<M><<<grid, 256, 0, ctx->stream>>>(
-        c, p, comp<double>(xyz, 0), comp<double>(xyz, 1), comp<double>(xyz, 2), comp<double>(uv, 0), comp<double>(uv, 1), d_jac, d_status, n)))
+    const bool vec = (n % 2 == 0) && ((reinterpret_cast<uintptr_t>(d_jac) & 15) == 0) && (!d_status || (reinterpret_cast<uintptr_t>(d_status) & 1) == 0);
+    if (vec) {
+        const int grid = grid_for(ctx, n / 2, 256, 4);
+        ACM_DISPATCH_MODEL(cam->model, (project_jacobian_kernel<M, 2><<<grid, 256, 0, ctx->stream>>>(
+            c, p, comp<double>(xyz, 0), comp<double>(xyz, 1), comp<double>(xyz, 2), comp<double>(uv, 0), comp<double>(uv, 1), d_jac, d_status, n)))
+    } else {
+        const int grid = grid_for(ctx, n, 256, 4);
+        ACM_DISPATCH_MODEL(cam->model, (project_jacobian_kernel<M, 1><<<grid, 256, 0, ctx->stream>>>(
+            c, p, comp<double>(xyz, 0), comp<double>(xyz, 1), comp<double>(xyz, 2), comp<double>(uv, 0), comp<double>(uv, 1), d_jac, d_status, n)))
+    }
     ACM_CHECK_LAUNCH(ctx);
     return ACM_OK;
 }
@@ -978,22 +1006,41 @@ extern "C" int32_t acm_project_jacobian(acm_ctx* ctx, const acm_camera* cam, con
 // `compute_jacobian` flag: trait doc reference src/camera/mod.rs:246-252 "Jacobian matrix (2x3)").
 // uv + six rows of n doubles: du/dx, du/dy, du/dz, dv/dx, dv/dy, dv/dz.
 // ---------------------------------------------------------------------------------------
-template <int M>
+template <int M, int NV>
 __global__ void __launch_bounds__(256) project_point_jacobian_kernel(const __grid_constant__ CamParams c, LinParams p, const double* __restrict__ X,
                                                                      const double* __restrict__ Y, const double* __restrict__ Z,
                                                                      double* __restrict__ U, double* __restrict__ V, double* __restrict__ J,
                                                                      uint8_t* __restrict__ S, size_t n) {
+    const size_t npk = n / NV;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const double x = X[i], y = Y[i], z = Z[i];
-        double u, v, ju[3], jv[3];
+    auto one = [&](double x, double y, double z, double& u, double& v, double* ju, double* jv) -> int {
         const int st = CamModel<M>::template project<false>(c, x, y, z, u, v);
         if (st == ACM_POINT_OK) PointJac<M>::eval(p, x, y, z, ju, jv);
         else { u = v = acm_nan(); ju[0] = ju[1] = ju[2] = jv[0] = jv[1] = jv[2] = 0.0; }
-        U[i] = u; V[i] = v;
-        if (S) S[i] = (uint8_t)st;
+        return st;
+    };
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npk; i += stride) {
+        if constexpr (NV == 2) {
+            const double2 x = __ldcs(reinterpret_cast<const double2*>(X) + i), y = __ldcs(reinterpret_cast<const double2*>(Y) + i),
+                          z = __ldcs(reinterpret_cast<const double2*>(Z) + i);
+            double u0, v0, u1, v1, ju0[3], jv0[3], ju1[3], jv1[3];
+            const int s0 = one(x.x, y.x, z.x, u0, v0, ju0, jv0), s1 = one(x.y, y.y, z.y, u1, v1, ju1, jv1);
+            __stcs(reinterpret_cast<double2*>(U) + i, make_double2(u0, u1));
+            __stcs(reinterpret_cast<double2*>(V) + i, make_double2(v0, v1));
+            if (S) __stcs(reinterpret_cast<uchar2*>(S) + i, make_uchar2((uint8_t)s0, (uint8_t)s1));
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { __stcs(J + (size_t)k * n + i, ju[k]); __stcs(J + (size_t)(3 + k) * n + i, jv[k]); }
+            for (int k = 0; k < 3; ++k) {
+                __stcs(reinterpret_cast<double2*>(J + (size_t)k * n) + i, make_double2(ju0[k], ju1[k]));
+                __stcs(reinterpret_cast<double2*>(J + (size_t)(3 + k) * n) + i, make_double2(jv0[k], jv1[k]));
+            }
+        } else {
+            double u, v, ju[3], jv[3];
+            const int st = one(X[i], Y[i], Z[i], u, v, ju, jv);
+            U[i] = u; V[i] = v;
+            if (S) S[i] = (uint8_t)st;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { __stcs(J + (size_t)k * n + i, ju[k]); __stcs(J + (size_t)(3 + k) * n + i, jv[k]); }
+        }
     }
 }
 
@@ -1010,9 +1057,16 @@ extern "C" int32_t acm_project_point_jacobian(acm_ctx* ctx, const acm_camera* ca
     make_lin_params(cam, &p);
     const size_t n = xyz->n;
     if (n == 0) return ACM_OK;
-    int grid = grid_for(ctx, n, 256, 4);
-    ACM_DISPATCH_MODEL(cam->model, (project_point_jacobian_kernel<M><<<grid, 256, 0, ctx->stream>>>(
-        c, p, comp<double>(xyz, 0), comp<double>(xyz, 1), comp<double>(xyz, 2), comp<double>(uv, 0), comp<double>(uv, 1), d_jac, d_status, n)))
+    const bool vec = (n % 2 == 0) && ((reinterpret_cast<uintptr_t>(d_jac) & 15) == 0) && (!d_status || (reinterpret_cast<uintptr_t>(d_status) & 1) == 0);
+    if (vec) {
+        const int grid = grid_for(ctx, n / 2, 256, 4);
+        ACM_DISPATCH_MODEL(cam->model, (project_point_jacobian_kernel<M, 2><<<grid, 256, 0, ctx->stream>>>(
+            c, p, comp<double>(xyz, 0), comp<double>(xyz, 1), comp<double>(xyz, 2), comp<double>(uv, 0), comp<double>(uv, 1), d_jac, d_status, n)))
+    } else {
+        const int grid = grid_for(ctx, n, 256, 4);
+        ACM_DISPATCH_MODEL(cam->model, (project_point_jacobian_kernel<M, 1><<<grid, 256, 0, ctx->stream>>>(
+            c, p, comp<double>(xyz, 0), comp<double>(xyz, 1), comp<double>(xyz, 2), comp<double>(uv, 0), comp<double>(uv, 1), d_jac, d_status, n)))
+    }
     ACM_CHECK_LAUNCH(ctx);
     return ACM_OK;
 }

@@ -186,6 +186,13 @@ def run_ours(args):
     def step():
         ctx.check(lib.acm_linearize_async(ctx.handle, C.byref(cam), N.RESIDUAL_PIXEL, X.handle, UV.handle))
 
+    # --- correctness of the path that is about to be timed: the sharded pass over a fixed 2 M-point slice (every rank
+    # its contiguous share, sums combined by the same fused exchange) against the CPU oracle on rank 0, and every rank
+    # must hold bit-identical sums
+    check = None
+    if not args.no_check:
+        check = oracle_check(acm, N, lib, ctx, kb, cam, rank, world, dist)
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -267,8 +274,16 @@ def run_ours(args):
         ctx.pinned_free(hx); ctx.pinned_free(hu)
 
     extras = None
-    if rank == 0 and world == 1 and not args.no_extras:
-        extras = run_extras(acm, N, lib, ctx, X, UV, n)
+    if not args.no_extras:
+        barrier()
+        mine = run_extras(acm, N, lib, ctx, X, UV, n)
+        if dist is not None:
+            gathered = [None] * world
+            dist.all_gather_object(gathered, mine)
+        else:
+            gathered = [mine]
+        if rank == 0:
+            extras = merge_extras(gathered, n, world)
 
     # --- LM conversion (BASELINE config 4): KB -> Double Sphere, 10 M correspondences sharded over the ranks
     lm = None
@@ -290,14 +305,36 @@ def run_ours(args):
         barrier()
         r = cost.optimize()
         barrier()
-        ms_lm = r.elapsed_ms
+        ms_lm, dev_lm = r.elapsed_ms, r.device_ms
         if dist is not None:
-            t = torch.tensor([ms_lm], dtype=torch.float64, device="cuda")
+            t = torch.tensor([ms_lm, dev_lm], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms_lm = float(t.item())
+            ms_lm, dev_lm = float(t[0].item()), float(t[1].item())
+        params_raw = np.asarray(r.parameters, dtype=np.float64).tobytes()
+        lm_identical = True
+        if dist is not None:
+            allp = acm.distributed.all_gather_bytes(params_raw)
+            lm_identical = all(allp[i * len(params_raw):(i + 1) * len(params_raw)] == params_raw for i in range(world))
         lm = {"workload": "KB->DoubleSphere LM, 10M correspondences (algebraic residual, converter tolerances/bounds)", "ms": ms_lm,
-              "iterations": r.iterations, "passes": r.passes, "status": r.status, "us_per_pass": 1e3 * ms_lm / max(r.passes, 1),
-              "params": [float(v) for v in r.parameters], "final_cost": r.final_cost, "points_per_gpu": m}
+              "device_ms": dev_lm, "iterations": r.iterations, "passes": r.passes, "status": r.status,
+              "us_per_pass": 1e3 * ms_lm / max(r.passes, 1), "device_us_per_pass": 1e3 * dev_lm / max(r.passes, 1),
+              "timing": "ms = host wall of acm_lm_solve (upload of the 1 KB state, ONE kernel launch, read-back); device_ms = %globaltimer from the first pass to the last LM step inside that kernel; max over ranks",
+              "params": [float(v) for v in r.parameters], "final_cost": r.final_cost, "points_per_gpu": m, "rank_identical": bool(lm_identical)}
+        if rank == 0 and not args.no_lm_check:
+            # the same conversion through the CPU oracle (all host threads; it walks the same algorithm): parameters <= 1e-9 relative
+            from oracle import oracle as O
+            O.build()
+            t0 = time.perf_counter()
+            xyz = O.synth_points3(0xACE50004, 0, n_lm_total, COS_MAX, False)
+            uvo, _ = O.project(O.make_model(O.KB, KB_SAMPLE, 512, 512), xyz, nthreads=os.cpu_count() or 1)
+            om = O.make_model(O.DS, KB_SAMPLE[:4] + [0.5, 0.1], 512, 512)
+            O.linear_estimation(om, xyz, uvo)
+            b = acm.CONVERTER_BOUNDS[5]
+            po, ro = O.lm_solve(om, O.RES_ALGEBRAIC, xyz, uvo, [x[0] for x in b], [x[1] for x in b], nthreads=os.cpu_count() or 1)
+            rel = float(np.max(np.abs(np.asarray(r.parameters) - po) / np.abs(po)))
+            lm["vs_oracle"] = {"params_rel": rel, "same_trajectory": bool((r.status, r.iterations, r.passes) == (ro.status, ro.iterations, ro.passes)),
+                               "oracle_s": time.perf_counter() - t0, "ok": bool(rel <= 1e-9)}
+            del xyz, uvo
         Xl.free(); Ul.free()
 
     # --- undistort (BASELINE config 5): 4096x4096 KB fisheye frames (sample intrinsics x8), 32 frames per GPU resident in
@@ -350,8 +387,8 @@ def run_ours(args):
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                              "kernel": "linearize_kernel<DOUBLE_SPHERE, PIXEL>", "algorithmic_bytes_per_launch": n * BYTES_PER_POINT,
                              "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0},
-                "e2e": e2e, "lm_conversion": lm, "undistort_batch": und,
-                "check": {"n_valid": int(ne.n_valid), "cost": float(ne.cost), "H00": float(ne.H[0])}}
+                "e2e": e2e, "lm_conversion": lm, "undistort_batch": und, "check": check,
+                "last_pass": {"n_valid": int(ne.n_valid), "cost": float(ne.cost), "H00": float(ne.H[0])}}
         if world == 1 and not args.no_cpu:
             v1, reps, el = cpu_baseline(args.cpu_points, 10.0, 1)
             ncores = os.cpu_count() or 1
@@ -361,14 +398,80 @@ def run_ours(args):
                                     "all_cores": {"value": vall, "cores": ncores, "note": "OpenMP over every host core: a generous upper bound the reference does not have"}}
         if extras:
             line["extras"] = extras
+            # one roofline entry per fused kernel (model / residual), same definition as the headline entry
+            line["roofline_by_kernel"] = {k: {"bound": "hbm", "achieved": v["gb_s"], "peak": peak, "unit": "GB/s", "frac": v["gb_s"] / peak,
+                                              "frac_of_nominal_8TBs": v["gb_s"] / 8000.0, "ms": v["ms"]}
+                                          for k, v in extras.get("linearize_100M", {}).items()}
+        if check is not None and not check.get("ok", False):
+            line["check_failed"] = True
         print(json.dumps(line))
+        if check is not None and not check.get("ok", False):
+            raise SystemExit("bench.py: the sharded pass disagrees with the oracle (see \"check\")")
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
 
 
+def merge_extras(per_rank, n, world):
+    """Max over ranks of every timing; throughput = points of all ranks / that time (weak scaling: n points per rank)."""
+    out = {}
+    for group, rows in per_rank[0].items():
+        out[group] = {}
+        for name, row in rows.items():
+            merged = {}
+            for key, val in row.items():
+                if key.endswith("ms"):
+                    merged[key] = max(r[group][name][key] for r in per_rank)
+            for key, val in row.items():
+                if key.endswith("_bytes_per_point"):
+                    base = key[: -len("_bytes_per_point")]
+                    ms = merged[(base + "_ms") if base else "ms"]
+                    merged[(base + "_" if base else "") + "gpts_s"] = n * world / ms / 1e6
+                    merged[(base + "_" if base else "") + "gb_s"] = n * val / ms / 1e6          # per GPU
+                    merged[(base + "_" if base else "") + "gb_s_all_gpus"] = n * world * val / ms / 1e6
+            out[group][name] = merged
+    return out
+
+
+CHECK_POINTS = 2_000_000
+CHECK_SEED = 0xACE500C3
+
+
+def oracle_check(acm, N, lib, ctx, kb, cam, rank, world, dist):
+    import ctypes as C
+    lo, hi = acm.shard_range(CHECK_POINTS, rank, world)
+    Xc = acm.Points(ctx, 3, hi - lo)
+    ctx.check(lib.acm_synth_points3(ctx.handle, CHECK_SEED, lo, COS_MAX, 0, Xc.handle))
+    Uc, st = kb.project_batch(Xc)
+    ctx.device_free(st)
+    ne = N.NormalEquations()
+    ctx.check(lib.acm_linearize(ctx.handle, C.byref(cam), N.RESIDUAL_PIXEL, Xc.handle, Uc.handle, C.byref(ne)))
+    Xc.free(); Uc.free()
+    raw = bytes(memoryview(ne))
+    identical = True
+    if dist is not None:
+        allraw = acm.distributed.all_gather_bytes(raw)
+        identical = all(allraw[i * len(raw):(i + 1) * len(raw)] == raw for i in range(world))
+    out = {"points": CHECK_POINTS, "rank_identical": bool(identical), "n_valid": int(ne.n_valid), "cost": float(ne.cost)}
+    if rank == 0:
+        from oracle import oracle as O
+        O.build()
+        P = ne.n_params
+        xyz = O.synth_points3(CHECK_SEED, 0, CHECK_POINTS, COS_MAX, False)
+        uv, _ = O.project(O.make_model(O.KB, KB_SAMPLE, 512, 512), xyz, nthreads=os.cpu_count() or 1)
+        Ho, go, co, no = O.linearize(O.make_model(O.DS, DS_START, 512, 512), O.RES_PIXEL, xyz, uv, nthreads=os.cpu_count() or 1)
+        H = np.array(ne.H[:P * P]).reshape(P, P); g = np.array(ne.g[:P])
+        # entry-wise relative error against the scale of the entry's row/column (g and the off-diagonals cancel)
+        dH = np.abs(H - Ho) / np.sqrt(np.outer(np.diag(Ho), np.diag(Ho)))
+        dg = np.abs(g - go) / np.sqrt(np.diag(Ho) * 2.0 * co)
+        rel = float(max(dH.max(), dg.max(), abs(ne.cost - co) / co))
+        out.update({"vs_oracle_rel": rel, "n_valid_oracle": int(no), "ok": bool(rel <= 1e-9 and int(no) == int(ne.n_valid) and identical)})
+    return out
+
+
 def run_extras(acm, N, lib, ctx, X, UV, n):
-    """Other kernels of the path on the same 100 M points (explanatory, N=1 only)."""
+    """Every other kernel of the path on this rank's 100 M points: the fused pass of every model / residual (config 3),
+    project / unproject / fused round trip for all models in f64 and f32 I/O (config 2), project + Jacobians."""
     import ctypes as C
     out = {}
     def timeit(fn, reps=10):
@@ -389,7 +492,7 @@ def run_extras(acm, N, lib, ctx, X, UV, n):
             if kind == 1 and mid not in (3, 4, 5):
                 continue
             ms = timeit(lambda: ctx.check(lib.acm_linearize_async(ctx.handle, C.byref(cam), kind, X.handle, UV.handle)))
-            lin[f"{names[mid]}/{kname}"] = {"ms": ms, "gpts_s": n / ms / 1e6, "gb_s": n * 40 / ms / 1e6}
+            lin[f"{names[mid]}/{kname}"] = {"ms": ms, "_bytes_per_point": 40}
     out["linearize_100M"] = lin
     pu = {}
     UV2 = acm.Points(ctx, 2, n); X2 = acm.Points(ctx, 3, n)
@@ -401,9 +504,27 @@ def run_extras(acm, N, lib, ctx, X, UV, n):
         ctx.check(lib.acm_synth_pixels(ctx.handle, 7, 0, 512.0, 512.0, UV2.handle))
         ms2 = timeit(lambda: ctx.check(lib.acm_unproject(ctx.handle, C.byref(cam), UV2.handle, X2.handle, C.c_void_p(st))))
         ms3 = timeit(lambda: ctx.check(lib.acm_project_unproject(ctx.handle, C.byref(cam), X.handle, UV2.handle, X2.handle, C.c_void_p(st), C.c_void_p(st2))))
-        pu[names[mid]] = {"project_ms": ms, "project_gb_s": n * 41 / ms / 1e6, "unproject_ms": ms2, "unproject_gb_s": n * 41 / ms2 / 1e6,
-                          "round_trip_fused_ms": ms3, "round_trip_fused_gb_s": n * 66 / ms3 / 1e6}
+        pu[names[mid]] = {"project_ms": ms, "project_bytes_per_point": 41, "unproject_ms": ms2, "unproject_bytes_per_point": 41,
+                          "round_trip_fused_ms": ms3, "round_trip_fused_bytes_per_point": 66}
     out["project_unproject_100M_f64"] = pu
+    # project with compute_jacobian = true (2 x P parameter Jacobian, 2 x 3 point Jacobian), on a 20 M-point prefix:
+    # 24 B in + 16 B uv + 1 B status + 16 P (or 48) B of Jacobian rows out per point
+    nj = min(n, 20_000_000)
+    Xj = acm.Points(ctx, 3, nj); Uj = acm.Points(ctx, 2, nj)
+    for c in range(3):
+        ctx.d2d(Xj.component_ptr(c), X.component_ptr(c), 8 * nj)
+    jac = ctx.device_alloc(8 * nj * 18)
+    pj = {}
+    for mid in range(7):
+        m = acm.MODEL_CLASSES[mid](acm.Intrinsics(*intr), acm.Resolution(512, 512), dist_init[mid], ctx=ctx)
+        cam = m.camera_block()
+        P = cam.n_params
+        msj = timeit(lambda: ctx.check(lib.acm_project_jacobian(ctx.handle, C.byref(cam), Xj.handle, Uj.handle, C.c_void_p(jac), C.c_void_p(st))), reps=5)
+        msp = timeit(lambda: ctx.check(lib.acm_project_point_jacobian(ctx.handle, C.byref(cam), Xj.handle, Uj.handle, C.c_void_p(jac), C.c_void_p(st))), reps=5)
+        pj[names[mid]] = {"param_jacobian_ms": msj * n / nj, "param_jacobian_bytes_per_point": 41 + 16 * P,
+                          "point_jacobian_ms": msp * n / nj, "point_jacobian_bytes_per_point": 41 + 48}
+    out["project_jacobian_f64_scaled_from_20M"] = pj
+    ctx.device_free(jac); Xj.free(); Uj.free()
     UV2.free(); X2.free()
     # f32 I/O (BASELINE config 2 "f64 and f32"): 21 / 21 / 34 B per point, arithmetic still f64 so the masks stay exact
     pu32 = {}
@@ -416,9 +537,8 @@ def run_extras(acm, N, lib, ctx, X, UV, n):
         ctx.check(lib.acm_synth_pixels(ctx.handle, 7, 0, 512.0, 512.0, UVf.handle))
         ms2 = timeit(lambda: ctx.check(lib.acm_unproject(ctx.handle, C.byref(cam), UVf.handle, X2f.handle, C.c_void_p(st))))
         ms3 = timeit(lambda: ctx.check(lib.acm_project_unproject(ctx.handle, C.byref(cam), Xf.handle, UVf.handle, X2f.handle, C.c_void_p(st), C.c_void_p(st2))))
-        pu32[names[mid]] = {"project_ms": ms, "project_gpts_s": n / ms / 1e6, "project_gb_s": n * 21 / ms / 1e6, "unproject_ms": ms2,
-                            "unproject_gpts_s": n / ms2 / 1e6, "unproject_gb_s": n * 21 / ms2 / 1e6, "round_trip_fused_ms": ms3,
-                            "round_trip_fused_gpts_s": n / ms3 / 1e6, "round_trip_fused_gb_s": n * 34 / ms3 / 1e6}
+        pu32[names[mid]] = {"project_ms": ms, "project_bytes_per_point": 21, "unproject_ms": ms2, "unproject_bytes_per_point": 21,
+                            "round_trip_fused_ms": ms3, "round_trip_fused_bytes_per_point": 34}
     out["project_unproject_100M_f32"] = pu32
     Xf.free(); UVf.free(); X2f.free()
     ctx.device_free(st); ctx.device_free(st2)
@@ -438,6 +558,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-check", action="store_true", help="skip the pre-timing comparison of the sharded pass with the CPU oracle")
+    ap.add_argument("--no-lm-check", action="store_true", help="skip the oracle LM run beside the 10 M-correspondence conversion")
     ap.add_argument("--no-lm", action="store_true")
     ap.add_argument("--no-undistort", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true")

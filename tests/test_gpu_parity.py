@@ -358,6 +358,16 @@ def test_golden_vectors_on_gpu(acm, ctx, cameras):
         assert np.all(st == 0) and np.max(np.abs(uv - ref)) < 1e-9
 
 
+def test_pinhole_doc_test_numbers_on_gpu(acm, ctx):
+    """pinhole.rs:145-164: the reference's own numeric known answer, through the scalar trait call and the batch kernel."""
+    m = acm.PinholeModel.new([500.0, 500.0, 320.0, 240.0], ctx=ctx)
+    m.resolution = acm.Resolution(640, 480)
+    uv = m.project([0.1, 0.2, 1.0])
+    assert abs(uv[0] - 370.0) < 1e-6 and abs(uv[1] - 340.0) < 1e-6
+    uvb, st = m.project_batch(np.tile([0.1, 0.2, 1.0], (5000, 1)))
+    assert np.all(st == 0) and np.all(uvb == uv)
+
+
 def test_reference_unit_tests_through_the_trait_surface(acm, ctx, cameras):
     """The reference's error-classification tests (double_sphere.rs:782-801, kannala_brandt.rs:948-974,
     fov.rs:648-666, tests/projection_accuracy.rs) through CameraModel.project / unproject."""
@@ -656,6 +666,80 @@ def test_lm_converges_to_oracle_parameters(acm, ctx, O, cameras, name, kind, rto
     assert np.allclose(r.parameters, oo, rtol=rtol), np.abs(r.parameters - oo) / np.abs(oo)
     assert abs(r.final_cost - ores.final_cost) <= 1e-9 * ores.final_cost + 1e-18  # KB->KB is an exact fit: cost ~ 1e-22
     cost.free()
+
+
+def test_lm_rank_deficient_normal_equations_take_the_retry_path(acm, ctx, O, cameras):
+    """the flag of the Cholesky-retry loop was re-armed while other warps still read it.
+    (a) Every point on the optical axis and lambda0 = 0: the columns of fx, fy and the distortion are exactly zero, the
+    damped system has exact zero pivots, every attempt fails and doubles a lambda that stays 0 -- the loop runs until
+    max_iterations.  Deterministic, so GPU and oracle must agree on every counter, for one block (450 points) and
+    many blocks (200 k points).
+    (b) Kannala-Brandt data on a single cone angle: the four distortion columns are proportional, H is singular up to
+    rounding, the first attempts fail and recover after a few doublings.  The pivots are rounding noise there, so only
+    the outcome is compared (both converge to the same cost), not the trajectory."""
+    for n in (450, 200_000):
+        xyz = np.zeros((n, 3)); xyz[:, 2] = np.linspace(0.5, 3.0, n)
+        uv = np.tile([250.0, 260.0], (n, 1))
+        for name, kind, init in (("double_sphere", 0, [0.5, 0.1]), ("kannala_brandt", 0, [0.0] * 4), ("ucm", 1, [0.5])):
+            cam = {"model_id": cameras[name]["model_id"], "params": [190.0, 190.0, 255.0, 257.0] + init, "width": 512, "height": 512}
+            m, om = gpu_model(acm, ctx, cam), oracle_model(O, cam)
+            cost = acm.OptimizationCost(m, xyz, uv, residual_kind=kind)
+            r = cost.optimize(config=acm.LevenbergMarquardtConfig(max_iterations=60, lambda0=0.0), bounds=None)
+            ocfg = O.lm_default_config(); ocfg.max_iterations = 60; ocfg.lambda0 = 0.0
+            oo, ores = O.lm_solve(om, kind, xyz, uv, None, None, ocfg)
+            assert (r.status, r.iterations, r.passes) == (ores.status, ores.iterations, ores.passes) == (3, 60, 1), (name, n)
+            assert np.array_equal(r.parameters, oo) and np.array_equal(r.parameters, cam["params"]), name
+            assert r.n_valid == n and np.isclose(r.final_cost, ores.final_cost, rtol=1e-12)
+            cost.free()
+    rng = np.random.default_rng(11)
+    n = 50_000
+    phi, rho, th = rng.uniform(0, 2 * np.pi, n), rng.uniform(0.5, 5.0, n), 0.7
+    xyz = np.stack([rho * np.sin(th) * np.cos(phi), rho * np.sin(th) * np.sin(phi), rho * np.cos(th)], axis=1)
+    truth = dict(cameras["kannala_brandt"])
+    uv, st = O.project(oracle_model(O, truth), xyz)
+    assert np.all(st == 0)
+    cam = {"model_id": truth["model_id"], "params": list(np.array(truth["params"][:4]) * [1.01, 0.99, 1.0, 1.0]) + [0.0] * 4, "width": 512, "height": 512}
+    m, om = gpu_model(acm, ctx, cam), oracle_model(O, cam)
+    cost = acm.OptimizationCost(m, xyz, uv, residual_kind=0)
+    r = cost.optimize(config=acm.LevenbergMarquardtConfig(max_iterations=200, lambda0=1e-30), bounds=None)
+    ocfg = O.lm_default_config(); ocfg.max_iterations = 200; ocfg.lambda0 = 1e-30
+    oo, ores = O.lm_solve(om, 0, xyz, uv, None, None, ocfg)
+    assert r.converged and ores.status in (0, 1, 2)
+    assert np.all(np.isfinite(r.parameters)) and r.final_cost <= 1e-6 * r.initial_cost and ores.final_cost <= 1e-6 * ores.initial_cost
+    cost.free()
+
+
+def test_lm_config4_ten_million_correspondences_matches_oracle(acm, ctx, O, cameras):
+    """BASELINE config 4 (camera_converter.rs:378-447 at 10 M correspondences): KB -> Double Sphere, converter inits,
+    bounds and tolerances, canonical (algebraic) residual.  GPU and oracle must take the same trajectory (status,
+    iterations, passes) and end at the same parameters within 1e-9 -- the reductions differ (one thread vs 50 k), so
+    this is the test that the kernel's summation error stays far below the solver's decision thresholds."""
+    from apex_camera_models_b200 import _native as N
+    lib = N.lib
+    n = 10_000_000
+    kbp = cameras["kannala_brandt"]["params"]
+    kb = acm.KannalaBrandtModel(acm.Intrinsics(*kbp[:4]), acm.Resolution(512, 512), kbp[4:], ctx=ctx)
+    X = acm.Points(ctx, 3, n)
+    ctx.check(lib.acm_synth_points3(ctx.handle, 0xACE50004, 0, float(np.cos(np.deg2rad(85.0))), 0, X.handle))
+    UV, st = kb.project_batch(X)
+    ctx.device_free(st)
+    ds = acm.DoubleSphereModel(acm.Intrinsics(*kbp[:4]), acm.Resolution(512, 512), [0.5, 0.1], ctx=ctx)
+    cost = acm.DoubleSphereOptimizationCost(ds, X, UV)
+    cost.linear_estimation()
+    start = ds.params().copy()
+    r = cost.optimize()
+    xyz, uv = X.numpy(), UV.numpy()
+    om = O.make_model(O.DS, list(kbp[:4]) + [0.5, 0.1], 512, 512)
+    assert O.linear_estimation(om, xyz, uv) == 0
+    assert np.allclose(start, om.params(), rtol=1e-12)
+    b = acm.CONVERTER_BOUNDS[5]
+    oo, ores = O.lm_solve(om, O.RES_ALGEBRAIC, xyz, uv, [x[0] for x in b], [x[1] for x in b], nthreads=8)
+    assert (r.status, r.iterations, r.passes) == (ores.status, ores.iterations, ores.passes)
+    assert r.n_valid == ores.n_valid == n
+    assert np.allclose(r.parameters, oo, rtol=1e-9), np.abs(r.parameters - oo) / np.abs(oo)
+    assert abs(r.final_cost - ores.final_cost) <= 1e-9 * ores.final_cost
+    assert r.device_ms > 0.0 and r.device_ms <= r.elapsed_ms + 1e-3
+    X.free(); UV.free()
 
 
 def test_lm_anchors_and_readme_figures(acm, ctx, O, cameras):

@@ -56,6 +56,16 @@ def test_pinhole_round_trip(O):
     assert np.all(np.abs(ray - _norm((1.0, 1.0, 5.0))) < 1e-6)
 
 
+def test_pinhole_doc_test_numbers(O):
+    """pinhole.rs:145-164, the one numeric known answer the reference itself states: fx = fy = 500, c = (320, 240),
+    640 x 480, X = (0.1, 0.2, 1.0) -> (370, 340) within 1e-6."""
+    m = O.make_model(O.PINHOLE, [500.0, 500.0, 320.0, 240.0], 640, 480)
+    st, uv = O.project1(m, (0.1, 0.2, 1.0))
+    assert st == O.OK
+    assert abs(uv[0] - 370.0) < 1e-6 and abs(uv[1] - 340.0) < 1e-6
+    assert uv[0] == 500.0 * 0.1 / 1.0 + 320.0 and uv[1] == 500.0 * 0.2 / 1.0 + 240.0  # the reference's operation order, exactly
+
+
 def test_rad_tan_ten_points(O, cameras):
     """rad_tan.rs:894-943: directions preserved (dot > 0.99) over a spread of points."""
     m = oracle_model(O, cameras["rad_tan"])
