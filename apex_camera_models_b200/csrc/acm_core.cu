@@ -58,6 +58,7 @@ extern "C" int32_t acm_ctx_create(int32_t device, void* cuda_stream, acm_ctx** o
     ctx->peer_local = nullptr; ctx->d_peer_ptrs = nullptr; ctx->peer_n = 0; ctx->peer_rank = 0; ctx->peer_seq = 0; ctx->peer_failed = false;
     ctx->group = nullptr; ctx->lm_tag = 0; ctx->d_lm_ll = nullptr; ctx->lm_ll_cap = 0; ctx->coop_launch = 0;
     ctx->h_small = nullptr; ctx->d_small_alias = nullptr; ctx->small_cap = 0;
+    ctx->cam_cache_valid = false;
     for (int i = 0; i < ACM_MAX_PEERS; ++i) ctx->peer_mapped[i] = nullptr;
 #define CREATE_CUDA(call)                                                                                     \
     do { cudaError_t _e = (call); if (_e != cudaSuccess) { int32_t rc = acm_fail(nullptr, ACM_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(_e)); delete ctx; return rc; } } while (0)
@@ -233,7 +234,23 @@ extern "C" int32_t acm_camera_new(int32_t model, const double* params, size_t n,
     return ACM_OK;
 }
 
+static int32_t make_cam_params_uncached(acm_ctx* ctx, const acm_camera* cam, CamParams* c);
+
+// The host-side gates of the contracted Newton iterations (Kannala-Brandt, RadTan) cost 20-100 us; a context remembers the
+// block of the last camera it prepared, so that a loop of scalar project / unproject calls on one model pays them once.
 int32_t acm_make_cam_params(acm_ctx* ctx, const acm_camera* cam, CamParams* c) {
+    if (ctx && cam && ctx->cam_cache_valid && cam->model == ctx->cam_cache_key.model && cam->width == ctx->cam_cache_key.width &&
+        cam->height == ctx->cam_cache_key.height && cam->n_params == ctx->cam_cache_key.n_params && cam->n_params >= 0 &&
+        cam->n_params <= ACM_MAX_PARAMS && memcmp(cam->params, ctx->cam_cache_key.params, sizeof(double) * cam->n_params) == 0) {
+        *c = ctx->cam_cache_val;
+        return ACM_OK;
+    }
+    int32_t rc = make_cam_params_uncached(ctx, cam, c);
+    if (rc == ACM_OK && ctx) { ctx->cam_cache_key = *cam; ctx->cam_cache_val = *c; ctx->cam_cache_valid = true; }
+    return rc;
+}
+
+static int32_t make_cam_params_uncached(acm_ctx* ctx, const acm_camera* cam, CamParams* c) {
     if (!cam || cam->model < 0 || cam->model > 6) return acm_fail(ctx, ACM_ERR_INVALID_ARG, "invalid camera model id");
     if (cam->n_params != kNParams[cam->model])
         return acm_fail(ctx, ACM_ERR_INVALID_PARAMS, "model %d expects %d parameters, got %d", cam->model, kNParams[cam->model], cam->n_params);
@@ -303,7 +320,7 @@ int32_t acm_make_cam_params(acm_ctx* ctx, const acm_camera* cam, CamParams* c) {
                 L2 += (p + 1) * p * fabs(k[i]) * pow(tb, p - 1);
                 L3 += (p + 1) * p * (p - 1) * fabs(k[i]) * pow(tb, p - 2);
             }
-            c->kb_fast = 0;
+            c->fast_newton = 0;
             if (std::isfinite(L3) && L3 < 1e6) {
                 const int NS = 1024;
                 const double dt = tb / NS;
@@ -319,9 +336,53 @@ int32_t acm_make_cam_params(acm_ctx* ctx, const acm_camera* cam, CamParams* c) {
                 if (m >= 0.5) {
                     const double eta = F0 / m, h = Mb * eta / m;
                     const double radius = h > 1e-12 ? eta * (1.0 - sqrt(1.0 - 2.0 * fmin(h, 0.5))) / h : eta;
-                    if (h <= 0.4 && radius <= tb - rmax && Mb / (2.0 * m) <= 4.0) c->kb_fast = 1;
+                    if (h <= 0.4 && radius <= tb - rmax && Mb / (2.0 * m) <= 4.0) c->fast_newton = 1;
                 }
             }
+            break;
+        }
+        case ACM_MODEL_RADTAN: {
+            // Gate of the contracted 2-D Newton iteration of unproject (acm_models.cuh: unproject_newton_fast).  The kernel
+            // itself is safe for any camera -- every decision it cannot take with a margin goes back to the IEEE loop -- so
+            // the gate only has to keep out cameras for which that would be the common case or for which a perturbation of
+            // a few 1e-15 in an iterate could grow: the reference's own loop is run here (plain IEEE doubles) on a 25 x 25
+            // grid of targets covering the image (the bounds test admits no other pixel) and must stop within 12 steps
+            // everywhere with a Jacobian that is nowhere near singular (|det| >= 0.05 (|j00 j11| + |j10 j01|)) and steps
+            // that shrink (no step larger than the first one).  Sane calibrations (the sample camera: 3 evaluations, det ~ 1)
+            // pass; strong barrel distortion whose mapping folds over inside the image does not and keeps the IEEE loop.
+            c->fast_newton = 0;
+            const double k1 = c->d[0], k2 = c->d[1], p1 = c->d[2], p2 = c->d[3], k3 = c->d[4];
+            bool ok = c->has_resolution && c->fast_div && std::isfinite(k1) && std::isfinite(k2) && std::isfinite(k3) && std::isfinite(p1) &&
+                      std::isfinite(p2) && std::isfinite(c->cx) && std::isfinite(c->cy);
+            const int G = 24;
+            for (int gy = 0; ok && gy <= G; ++gy) {
+                for (int gx = 0; ok && gx <= G; ++gx) {
+                    const double tx = (c->W * gx / G - c->cx) / c->fx, ty = (c->H * gy / G - c->cy) / c->fy;
+                    if (!(fabs(tx) <= 50.0 && fabs(ty) <= 50.0)) { ok = false; break; }
+                    double px = tx, py = ty, first = -1.0;
+                    bool stopped = false;
+                    for (int it = 0; it < 12 && !stopped; ++it) {
+                        const double x = px, y = py, r2 = x * x + y * y, r4 = r2 * r2, r6 = r4 * r2;
+                        const double rad = 1.0 + k1 * r2 + k2 * r4 + k3 * r6;
+                        const double ex = x * rad + 2.0 * p1 * x * y + p2 * (r2 + 2.0 * x * x) - tx;
+                        const double ey = y * rad + p1 * (r2 + 2.0 * y * y) + 2.0 * p2 * x * y - ty;
+                        if (sqrt(ex * ex + ey * ey) < 1e-6) { stopped = true; break; }
+                        const double common = k1 + 2.0 * k2 * r2 + 3.0 * k3 * r4;
+                        const double j00 = rad + x * common * 2.0 * x + 2.0 * p1 * y + p2 * 6.0 * x, j01 = x * common * 2.0 * y + 2.0 * p1 * x + p2 * 2.0 * y;
+                        const double j10 = y * common * 2.0 * x + p1 * 2.0 * x + 2.0 * p2 * y, j11 = rad + y * common * 2.0 * y + p1 * 6.0 * y + 2.0 * p2 * x;
+                        const double det = j00 * j11 - j10 * j01;
+                        if (!(fabs(det) >= 0.05 * (fabs(j00 * j11) + fabs(j10 * j01)))) { ok = false; break; }
+                        const double dx = (j11 * ex - j01 * ey) / det, dy = (j00 * ey - j10 * ex) / det;
+                        const double step = sqrt(dx * dx + dy * dy);
+                        if (first < 0.0) first = step;
+                        if (!(step <= first)) { ok = false; break; }
+                        px -= dx; py -= dy;
+                        if (step < 1e-6) stopped = true;
+                    }
+                    if (!stopped) ok = false;
+                }
+            }
+            c->fast_newton = ok ? 1 : 0;
             break;
         }
         case ACM_MODEL_FOV: {  // fov.rs:296, :340
@@ -334,12 +395,13 @@ int32_t acm_make_cam_params(acm_ctx* ctx, const acm_camera* cam, CamParams* c) {
 }
 
 // 1 when acm_unproject runs the contracted Newton iteration for this camera (Kannala-Brandt cameras that pass the
-// host-side convergence proof above), 0 when it keeps the IEEE loop; negative on an invalid camera block
+// host-side convergence proof above, RadTan cameras that pass the grid gate), 0 when it keeps the IEEE loop; negative on
+// an invalid camera block
 extern "C" int32_t acm_camera_fast_unproject(const acm_camera* cam) {
     CamParams c;
     int32_t rc = acm_make_cam_params(nullptr, cam, &c);
     if (rc) return rc;
-    return (c.model == ACM_MODEL_KANNALA_BRANDT && c.kb_fast) ? 1 : 0;
+    return ((c.model == ACM_MODEL_KANNALA_BRANDT || c.model == ACM_MODEL_RADTAN) && c.fast_newton) ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------------------------

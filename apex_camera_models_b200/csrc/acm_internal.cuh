@@ -25,7 +25,7 @@ struct CamParams {
     int32_t model;
     int32_t has_resolution;  // width > 0 && height > 0 (kannala_brandt.rs:447-448)
     int32_t fast_div;        // 2^-100 <= |fx|, |fy| <= 2^100: acm_div_by() is bit-identical to the division
-    int32_t kb_fast;         // Kannala-Brandt: the host verified that Newton's method converges for every pixel (acm_make_cam_params)
+    int32_t fast_newton;     // Kannala-Brandt / RadTan: the host-side gate allows the contracted Newton iteration of unproject (acm_make_cam_params)
 };
 
 struct acm_points {
@@ -99,6 +99,8 @@ struct acm_ctx {
     std::unordered_map<const void*, int> blocks_per_sm;
     // small-batch host path (acm_project_host / acm_unproject_host with few points): mapped pinned staging, no allocation per call
     void* h_small; void* d_small_alias; size_t small_cap;
+    // last camera block prepared by acm_make_cam_params and its device form (the Newton gates are not free)
+    acm_camera cam_cache_key; CamParams cam_cache_val; bool cam_cache_valid;
 };
 
 // Make the context's device current on the calling thread (contexts of several GPUs may be driven by one thread).

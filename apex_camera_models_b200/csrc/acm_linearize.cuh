@@ -82,7 +82,16 @@ struct LinParams {
     double fx, fy, cx, cy;
     double d[5];
     double k0;  // validity constant: UCM w, EUCM (a-1)/(2a-1), DS w2, FOV tan(w/2)
+    unsigned atab;  // shared-memory address of the atan table (acm_atan_tab_init), set by the streaming kernel for KB / FOV
 };
+
+// -DACM_LIN_ATAN_TAB=1 builds the KB / FOV passes with the table-driven atan2 of acm_math.cuh (16 FP64 instructions instead
+// of 25).  Measured SLOWER on the same box (KB 4453 vs 4780 GB/s, FOV 4920 vs 5245): the index computation, the LDS and
+// the clamps add ~18 non-FP64 instructions per point to loops whose issue slots are as full as their FP64 pipe
+// (KB: 362 instructions per trip against 2 x 186 FP64 issue cycles).  Kept as an A/B aid.
+#ifndef ACM_LIN_ATAN_TAB
+#define ACM_LIN_ATAN_TAB 0
+#endif
 
 __host__ __device__ inline void lin_derive(int model, LinParams& p) {
     const double alpha = p.d[0];
@@ -257,6 +266,8 @@ template <> struct Lin<ACM_MODEL_DOUBLE_SPHERE, ACM_RESIDUAL_ALGEBRAIC> : LinUni
 
 template <> struct Lin<ACM_MODEL_FOV, ACM_RESIDUAL_PIXEL> {
     static constexpr int ND = 1; static constexpr bool UNIT_C = true;
+    // TAB: table-driven atan2 (needs p.atab: only the streaming kernel provides it)
+    template <bool TAB = false>
     static __device__ __forceinline__ bool eval(const LinParams& p, double x, double y, double z, double u, double v,
                                                 double& ru, double& rv, double* au, double* av) {
         // branch-free: the r2 < sqrt(EPS) case (fov.rs:203-207, constant rd) is a select at the end
@@ -269,7 +280,7 @@ template <> struct Lin<ACM_MODEL_FOV, ACM_RESIDUAL_PIXEL> {
         const double r2s = small ? 1.0 : r2;
         double ir;
         const double r = fast_sqrt<true>(r2s, ir);
-        const double a = fast_atan2_q1(t2 * r, z);
+        const double a = TAB ? acm_atan2_q1_tab(t2 * r, z, p.atab) : fast_atan2_q1(t2 * r, z);
         const double da = z * r * tt1 * fast_rcp(fma(t2 * t2, r2s, z * z));
         const double irw = iw * ir;
         double rd = a * irw;
@@ -405,7 +416,9 @@ template <int M, int KIND> struct LinOps {
     static constexpr int NACC = L::N, COST = L::COST, COUNT = L::COUNT;
     static __device__ __forceinline__ void point(double* acc, const LinParams& p, double x, double y, double z, double u, double v) {
         double ru, rv, au[2 + ND], av[2 + ND];
-        const bool ok = E::eval(p, x, y, z, u, v, ru, rv, au, av);
+        bool ok;
+        if constexpr (M == ACM_MODEL_FOV && ACM_LIN_ATAN_TAB) ok = E::template eval<true>(p, x, y, z, u, v, ru, rv, au, av);
+        else ok = E::eval(p, x, y, z, u, v, ru, rv, au, av);
         lin_accumulate_masked<ND, E::UNIT_C>(acc, ok, ru, rv, au, av);
     }
     // `x` = the parameter vector the pass was evaluated at (unused here: fx, fy are folded in during the pass)
@@ -429,7 +442,7 @@ template <> struct LinOps<ACM_MODEL_KANNALA_BRANDT, ACM_RESIDUAL_PIXEL> {
         double r = fast_sqrt<true>(x * x + y * y, ir);
         const bool on_axis = !(r >= LIN_EPS);
         r = on_axis ? 0.0 : r;
-        const double th = fast_atan2_q1(r, ok ? z : 1.0);
+        const double th = ACM_LIN_ATAN_TAB ? acm_atan2_q1_tab(r, ok ? z : 1.0, p.atab) : fast_atan2_q1(r, ok ? z : 1.0);
         const double xr = on_axis ? 0.0 : x * ir, yr = on_axis ? 0.0 : y * ir;
         const double t2 = th * th, t3 = t2 * th, t5 = t3 * t2, t7 = t5 * t2, t9 = t7 * t2;
         const double thd = fma(p.d[3], t9, fma(p.d[2], t7, fma(p.d[1], t5, fma(p.d[0], t3, th))));

@@ -108,12 +108,71 @@ template <> struct CamModel<ACM_MODEL_RADTAN> {
         if (BOUNDS && acm_outside(c, u, v)) return ACM_PROJECTION_OUTSIDE_IMAGE;
         return ACM_POINT_OK;
     }
+    // Contracted form of the Newton loop below (rad_tan.rs:440-515) for cameras that pass the host-side gate
+    // (CamParams::fast_newton, acm_make_cam_params): Horner / FMA evaluation of the distortion and of its 2x2 Jacobian
+    // (the terms shared, ~50 FP64 instructions per step instead of ~106 separately rounded ones) and one MUFU-seeded
+    // reciprocal of the determinant instead of an IEEE division + four quotients.
+    // The reference returns the iterate at which one of its two tests fires -- `error.norm() < 1e-6` before a step,
+    // `delta.norm() < 1e-6` after it -- so that iterate (typically two steps from the start, ~1e-9 from the root) IS the
+    // result, and a different stopping decision would move it by up to 1e-6.  The contracted iterates track the IEEE
+    // ones to a few 1e-15 (a Newton step contracts perturbations), which moves the two squared norms by <= ~1e-7
+    // relative near their threshold (the error is a difference of O(1) quantities, |e| ~ 1e-6 there).  Every decision
+    // is therefore taken with a guard band of 1e-5 relative around 1e-12; a value inside the band, a determinant that
+    // is not clearly non-zero, a non-finite intermediate or the 100th iteration all return -1 ("ambiguous") and the
+    // caller redoes the point with the IEEE loop.  ~2e-5 of the decisions land in a band; a warp with such a point pays
+    // the IEEE loop once.  Status bytes stay bit-exact, rays agree with the reference's iterate to ~1e-14.
+    // (Iterating the two points of a packet in ONE loop -- two independent chains per trip -- measured SLOWER, 2146 vs
+    // 2628 GB/s on the same box: the selects that freeze a finished point cost more than the second chain hides.)
+    static __device__ __forceinline__ int unproject_newton_fast(const CamParams& c, double tx, double ty, double& px, double& py) {
+        const double k1 = c.d[0], k2 = c.d[1], p1 = c.d[2], p2 = c.d[3], k3 = c.d[4];
+        const double k2x2 = k2 + k2, k3x3 = 3.0 * k3, p1x2 = p1 + p1, p2x2 = p2 + p2, p1x6 = 6.0 * p1, p2x6 = 6.0 * p2;  // kernel-invariant
+        const double T = 1e-12, BAND = 1e-17;   // threshold of the squared norms, half-width of the guard band
+        px = tx; py = ty;
+#pragma unroll 1
+        for (int it = 0; it < 100; ++it) {
+            const double x = px, y = py;
+            const double r2 = __fma_rn(x, x, __dmul_rn(y, y));
+            const double rad = __fma_rn(r2, __fma_rn(r2, __fma_rn(r2, k3, k2), k1), 1.0);
+            const double xy = __dmul_rn(x, y), x2 = __dadd_rn(x, x), y2 = __dadd_rn(y, y);
+            const double ex = __fma_rn(x, rad, __fma_rn(p1x2, xy, __fma_rn(p2, __fma_rn(x2, x, r2), -tx)));
+            const double ey = __fma_rn(y, rad, __fma_rn(p1, __fma_rn(y2, y, r2), __fma_rn(p2x2, xy, -ty)));
+            const double e2 = __fma_rn(ex, ex, __dmul_rn(ey, ey));
+            if (!(fabs(e2 - T) > BAND)) return -1;      // inside the band, or NaN
+            if (e2 < T) return ACM_POINT_OK;             // error.norm() < 1e-6
+            const double common = __fma_rn(r2, __fma_rn(r2, k3x3, k2x2), k1);
+            const double dx_ = __dmul_rn(common, x2), dy_ = __dmul_rn(common, y2);   // d(rad)/dx, d(rad)/dy
+            const double cross = __fma_rn(p1x2, x, __dmul_rn(p2x2, y));
+            const double j00 = __fma_rn(x, dx_, __fma_rn(p1x2, y, __fma_rn(p2x6, x, rad)));
+            const double j01 = __fma_rn(x, dy_, cross);
+            const double j10 = __fma_rn(y, dx_, cross);
+            const double j11 = __fma_rn(y, dy_, __fma_rn(p1x6, y, __fma_rn(p2x2, x, rad)));
+            const double a = __dmul_rn(j00, j11), b = __dmul_rn(j10, j01);
+            const double det = __dsub_rn(a, b);
+            if (!(fabs(det) > 1e-9 * (fabs(a) + fabs(b)))) return -1;   // det == 0.0 of the reference cannot be decided here (or NaN)
+            const double idet = acm_rcp(det);
+            const double dx = __dmul_rn(__fma_rn(j11, ex, -__dmul_rn(j01, ey)), idet);
+            const double dy = __dmul_rn(__fma_rn(j00, ey, -__dmul_rn(j10, ex)), idet);
+            px = __dsub_rn(px, dx); py = __dsub_rn(py, dy);
+            const double d2 = __fma_rn(dx, dx, __dmul_rn(dy, dy));
+            if (!(fabs(d2 - T) > BAND)) return -1;
+            if (d2 < T) return ACM_POINT_OK;             // delta.norm() < 1e-6
+        }
+        return -1;   // 100 steps without a stop: let the IEEE loop give the verdict
+    }
+
     template <bool IEEE = ACM_TAIL_DEFAULT>
     static __device__ int unproject(const CamParams& c, double u, double v, double& rx, double& ry, double& rz) {
         if (acm_outside(c, u, v)) return ACM_POINT_IS_OUTSIDE_IMAGE;
         const double k1 = c.d[0], k2 = c.d[1], p1 = c.d[2], p2 = c.d[3], k3 = c.d[4];
         const double tx = acm_mx(c, u), ty = acm_my(c, v);
         double px = tx, py = ty;
+        if (!IEEE && c.fast_newton) {
+            if (unproject_newton_fast(c, tx, ty, px, py) == ACM_POINT_OK) {
+                acm_normalize<false>(px, py, 1.0, rx, ry, rz);
+                return ACM_POINT_OK;
+            }
+            px = tx; py = ty;   // ambiguous: the reference's own arithmetic decides
+        }
         for (int it = 0; it < 100; ++it) {
             double x = px, y = py;
             double r2 = x * x + y * y;
@@ -181,7 +240,7 @@ template <> struct CamModel<ACM_MODEL_KANNALA_BRANDT> {
         if (c.has_resolution && acm_outside(c, u, v)) return ACM_POINT_IS_OUTSIDE_IMAGE;
         const double k1 = c.d[0], k2 = c.d[1], k3 = c.d[2], k4 = c.d[3];
         double mx = acm_mx(c, u), my = acm_my(c, v);
-        if (!IEEE && c.kb_fast) {
+        if (!IEEE && c.fast_newton) {
             // The host proved (Kantorovich bound in acm_make_cam_params) that Newton's method converges for every ru in
             // (1e-6, pi/2] of this camera: the reference's loop returns Ok for every such pixel and its iterate lies within
             // ~1e-12 of the root.  The only status decisions left are ru > 1e-6 and ru > 0, taken exactly on r2; the iteration
@@ -427,3 +486,4 @@ template <> struct CamModel<ACM_MODEL_FOV> {
         case ACM_MODEL_FOV: { constexpr int M = ACM_MODEL_FOV; __VA_ARGS__; break; }          \
         default: return acm_fail(ctx, ACM_ERR_INVALID_ARG, "unknown camera model id %d", (int)(model_id)); \
     }
+

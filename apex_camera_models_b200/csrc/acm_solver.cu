@@ -274,25 +274,27 @@ __device__ __forceinline__ unsigned long long acm_globaltimer() {
 #define ACM_SPIN_LIMIT_CYCLES 4000000000LL  // ~2 s: a lost peer (or a bug) ends the solve instead of hanging the GPU
 
 // Warp-collective: total of col[0..nb) -- lane-strided sequential sums, then the fixed shuffle tree --
-// where the cells are filled by the other blocks of this grid.  Up to 8 cells per lane are polled
-// per trip (one L2 round trip per 256 blocks).
+// where the cells are filled by the other blocks of this grid.  BATCH cells per lane are polled per
+// trip (8: one L2 round trip per 256 blocks; 16 pushed the Double Sphere solve kernel over its 170-register cap and
+// the spill landed in the streaming loop).  The summation order does not depend on BATCH.
+template <int BATCH>
 __device__ __forceinline__ double warp_sum_cells(const LLCell* __restrict__ col, int nb, int lane, unsigned long long tag, bool& bad) {
     double a = 0.0;
-    for (int b0 = lane; b0 < nb; b0 += 32 * 8) {
-        ulonglong2 c[8];
+    for (int b0 = lane; b0 < nb; b0 += 32 * BATCH) {
+        ulonglong2 c[BATCH];
         unsigned pending = 0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) if (b0 + 32 * j < nb) pending |= 1u << j;
+        for (int j = 0; j < BATCH; ++j) if (b0 + 32 * j < nb) pending |= 1u << j;
         const long long t0 = clock64();
         while (pending) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) if (pending & (1u << j)) c[j] = ll_load(col + b0 + 32 * j);
+            for (int j = 0; j < BATCH; ++j) if (pending & (1u << j)) c[j] = ll_load(col + b0 + 32 * j);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) if ((pending & (1u << j)) && ll_ready(c[j], tag)) pending &= ~(1u << j);
+            for (int j = 0; j < BATCH; ++j) if ((pending & (1u << j)) && ll_ready(c[j], tag)) pending &= ~(1u << j);
             if (pending && clock64() - t0 > ACM_SPIN_LIMIT_CYCLES) { bad = true; break; }
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) if (b0 + 32 * j < nb) a += ll_value(c[j]);
+        for (int j = 0; j < BATCH; ++j) if (b0 + 32 * j < nb) a += ll_value(c[j]);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
@@ -359,21 +361,28 @@ __device__ __forceinline__ double warp_peer_exchange(const PeerArgs& peer, unsig
 //   (3 deep, 128 threads), RadTan 4.09 -> 4.25 (2 deep; 5.1 with the structured accumulation; 128-thread blocks capped at 168
 //   registers for 12 warps/SM measured 4.2-4.8); Pinhole (already at 7.1 TB/s) is faster without the ring.
 // MIN_BLOCKS > 1 caps the registers through __launch_bounds__.
-template <int M> struct LinStreamDefault { static constexpr int DEPTH = 0, BLOCK = 256, MIN_BLOCKS = 0; };
+// PTS = points evaluated per loop trip and thread (2 = one 16-byte packet per array, 4 = two packets: four independent
+// evaluation chains for the scheduler to interleave; needs an even DEPTH >= 2).
+template <int M> struct LinStreamDefault { static constexpr int DEPTH = 0, BLOCK = 256, MIN_BLOCKS = 0, PTS = 2; };
 #ifndef ACM_LIN_NO_RING  // A/B aid: -DACM_LIN_NO_RING builds every model with the register prefetch
-template <> struct LinStreamDefault<ACM_MODEL_DOUBLE_SPHERE> { static constexpr int DEPTH = 3, BLOCK = 256, MIN_BLOCKS = 0; };
-template <> struct LinStreamDefault<ACM_MODEL_EUCM> { static constexpr int DEPTH = 3, BLOCK = 256, MIN_BLOCKS = 0; };
-template <> struct LinStreamDefault<ACM_MODEL_UCM> { static constexpr int DEPTH = 2, BLOCK = 256, MIN_BLOCKS = 0; };
-template <> struct LinStreamDefault<ACM_MODEL_FOV> { static constexpr int DEPTH = 3, BLOCK = 128, MIN_BLOCKS = 0; };
-template <> struct LinStreamDefault<ACM_MODEL_RADTAN> { static constexpr int DEPTH = 2, BLOCK = 256, MIN_BLOCKS = 0; };
+template <> struct LinStreamDefault<ACM_MODEL_DOUBLE_SPHERE> { static constexpr int DEPTH = 3, BLOCK = 256, MIN_BLOCKS = 0, PTS = 2; };
+template <> struct LinStreamDefault<ACM_MODEL_EUCM> { static constexpr int DEPTH = 3, BLOCK = 256, MIN_BLOCKS = 0, PTS = 2; };
+template <> struct LinStreamDefault<ACM_MODEL_UCM> { static constexpr int DEPTH = 2, BLOCK = 256, MIN_BLOCKS = 0, PTS = 2; };
+template <> struct LinStreamDefault<ACM_MODEL_FOV> { static constexpr int DEPTH = 2, BLOCK = 128, MIN_BLOCKS = 0, PTS = 4; };
+template <> struct LinStreamDefault<ACM_MODEL_RADTAN> { static constexpr int DEPTH = 2, BLOCK = 256, MIN_BLOCKS = 0, PTS = 2; };
 #endif
 // KB (37 accumulators, 166 registers): 3 blocks of 128 threads.  Same-box A/B (scripts/ab_lin.sh; boxes of the pool differ by
 // up to 40 % on this FP64-bound kernel, so only same-box comparisons count): register prefetch 4.42 TB/s, ring 1 deep 3.95,
 // 2 deep 4.51, 3 deep 4.59; capped at 128 registers (MIN_BLOCKS = 4, 36-byte spill) 4.19.
-template <> struct LinStreamDefault<ACM_MODEL_KANNALA_BRANDT> { static constexpr int DEPTH = 3, BLOCK = 128, MIN_BLOCKS = 0; };
+// Round 2, same-box A/B (profiles/r02_ab_pts4.log): four points per trip, FOV 5262 -> 5463 GB/s (2 deep), KB 4789 -> 4861 (4 deep);
+// RadTan loses (5348 -> 5139 / 4255) and keeps two.
+template <> struct LinStreamDefault<ACM_MODEL_KANNALA_BRANDT> { static constexpr int DEPTH = 4, BLOCK = 128, MIN_BLOCKS = 0, PTS = 4; };
 template <int M> struct LinStream : LinStreamDefault<M> {};
 #ifdef ACM_EXP_MODEL  // tuning aid: -DACM_EXP_MODEL=<id> -DACM_EXP_DEPTH= -DACM_EXP_BLOCK= -DACM_EXP_MINB= overrides one model
-template <> struct LinStream<ACM_EXP_MODEL> { static constexpr int DEPTH = ACM_EXP_DEPTH, BLOCK = ACM_EXP_BLOCK, MIN_BLOCKS = ACM_EXP_MINB; };
+#ifndef ACM_EXP_PTS
+#define ACM_EXP_PTS 2
+#endif
+template <> struct LinStream<ACM_EXP_MODEL> { static constexpr int DEPTH = ACM_EXP_DEPTH, BLOCK = ACM_EXP_BLOCK, MIN_BLOCKS = ACM_EXP_MINB, PTS = ACM_EXP_PTS; };
 #endif
 
 struct LinKernelArgs {
@@ -402,8 +411,13 @@ __device__ __forceinline__ void lin_stream_pass(const LinKernelArgs& a, const Li
     constexpr int DEPTH = LinStream<M>::DEPTH;
     __shared__ double wsum[NWARP][NACC];
     extern __shared__ double2 lin_ring[];
-    const LinParams p = p_in;
+    LinParams p = p_in;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if constexpr ((M == ACM_MODEL_KANNALA_BRANDT || M == ACM_MODEL_FOV) && ACM_LIN_ATAN_TAB) {
+        __shared__ __align__(16) double lin_atab[2 * 65];
+        if (!primed) { acm_atan_tab_init(lin_atab); __syncthreads(); }   // a solve fills it in its first pass
+        p.atab = (unsigned)__cvta_generic_to_shared(lin_atab);
+    }
     const int nb = (int)gridDim.x;
     const size_t npairs = a.n >> 1;
     const size_t stride = (size_t)nb * BS;
@@ -436,7 +450,35 @@ __device__ __forceinline__ void lin_stream_pass(const LinKernelArgs& a, const Li
 #pragma unroll
     for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
     size_t i = i0;
-    if constexpr (DEPTH > 0) {
+    if constexpr (DEPTH > 0 && LinStream<M>::PTS == 4) {
+        // two packets (four points) per trip: the four evaluation chains are independent, the points still enter every
+        // accumulator in the same order as in the two-point form, so the sums are bit-identical
+        static_assert(DEPTH % 2 == 0, "PTS = 4 consumes the ring two stages at a time");
+        int stage = 0;
+        auto ld = [&](int st, int q) { return lin_ring[(st * 5 + q) * BS + tid]; };
+#pragma unroll 1
+        while (i + stride < npairs) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH > 1 ? DEPTH - 2 : 0) : "memory");
+            const double2 x0 = ld(stage, 0), y0 = ld(stage, 1), z0 = ld(stage, 2), u0 = ld(stage, 3), v0 = ld(stage, 4);
+            const double2 x1 = ld(stage + 1, 0), y1 = ld(stage + 1, 1), z1 = ld(stage + 1, 2), u1 = ld(stage + 1, 3), v1 = ld(stage + 1, 4);
+            LM_::point(acc, p, x0.x, y0.x, z0.x, u0.x, v0.x);
+            LM_::point(acc, p, x0.y, y0.y, z0.y, u0.y, v0.y);
+            LM_::point(acc, p, x1.x, y1.x, z1.x, u1.x, v1.x);
+            LM_::point(acc, p, x1.y, y1.y, z1.y, u1.y, v1.y);
+            issue(stage, i + (size_t)DEPTH * stride);
+            issue(stage + 1, i + (size_t)(DEPTH + 1) * stride);
+            stage = (stage + 2 == DEPTH) ? 0 : stage + 2;
+            i += 2 * stride;
+        }
+        if (i < npairs) {   // odd number of packets: the last one alone
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            const double2 x0 = ld(stage, 0), y0 = ld(stage, 1), z0 = ld(stage, 2), u0 = ld(stage, 3), v0 = ld(stage, 4);
+            LM_::point(acc, p, x0.x, y0.x, z0.x, u0.x, v0.x);
+            LM_::point(acc, p, x0.y, y0.y, z0.y, u0.y, v0.y);
+            i += stride;
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else if constexpr (DEPTH > 0) {
         int stage = 0;
 #pragma unroll 1
         while (i < npairs) {
@@ -536,7 +578,7 @@ __device__ __forceinline__ bool lin_pass(const LinKernelArgs& a, LmState* sh, Lm
     bool bad = false;
 #pragma unroll 1
     for (int slot = (int)blockIdx.x + nb * warp; slot < NACC; slot += nb * NWARP) {
-        double tot = warp_sum_cells(a.partials + (size_t)slot * nb, nb, lane, tag, bad);
+        double tot = warp_sum_cells<8>(a.partials + (size_t)slot * nb, nb, lane, tag, bad);
         if (a.peer.bufs && !bad) tot = warp_peer_exchange(a.peer, seq, slot, tot, lane, bad);
         if (bad) tot = acm_qnan();
         if (lane == 0) {
