@@ -1,5 +1,8 @@
 // Context, memory, point buffers (AoS <-> SoA), camera parameter blocks, NCCL plumbing.
 #include <dlfcn.h>
+
+#include <atomic>
+#include <chrono>
 #include <math.h>
 #include <stdarg.h>
 #include <stdlib.h>
@@ -696,23 +699,38 @@ static int32_t host_map(acm_ctx* ctx, const acm_camera* cam, const double* in_ao
     ACM_REQUIRE(ctx, cam && (n == 0 || (in_aos && out_aos)), "host map: null argument");
     if (n == 0) return ACM_OK;
     if (n <= ACM_SMALL_BATCH) {
-        // scalar / small-batch calls (the trait's project(&p)): mapped pinned staging owned by the context, one kernel, one sync
+        // scalar / small-batch calls (the trait's project(&p)): mapped pinned staging owned by the context, ONE kernel that
+        // reads and writes host memory directly.  Single-block batches (n <= 128) do not even synchronise the stream: the
+        // kernel publishes a sequence number in the staging area when its results are out and the host spins on it.
         const size_t in_dim = is_project ? 3 : 2, out_dim = is_project ? 2 : 3;
+        const size_t flag_off = (size_t)ACM_SMALL_BATCH * (5 * sizeof(double) + 8);
         if (!ctx->h_small) {
-            const size_t bytes = (size_t)ACM_SMALL_BATCH * (5 * sizeof(double) + 8);
-            ACM_CUDA(ctx, cudaHostAlloc(&ctx->h_small, bytes, cudaHostAllocMapped));
+            ACM_CUDA(ctx, cudaHostAlloc(&ctx->h_small, flag_off + 64, cudaHostAllocMapped));
             ACM_CUDA(ctx, cudaHostGetDevicePointer(&ctx->d_small_alias, ctx->h_small, 0));
-            ctx->small_cap = ACM_SMALL_BATCH;
+            memset(ctx->h_small, 0, flag_off + 64);
+            ctx->small_cap = ACM_SMALL_BATCH; ctx->small_seq = 0;
         }
         double* h_in = static_cast<double*>(ctx->h_small);
         double* h_out = h_in + 3 * (size_t)ACM_SMALL_BATCH;
         uint8_t* h_st = reinterpret_cast<uint8_t*>(h_in + 5 * (size_t)ACM_SMALL_BATCH);
-        double* d_in = static_cast<double*>(ctx->d_small_alias);
+        volatile unsigned long long* h_flag = reinterpret_cast<volatile unsigned long long*>(static_cast<char*>(ctx->h_small) + flag_off);
+        char* d_base = static_cast<char*>(ctx->d_small_alias);
+        double* d_in = reinterpret_cast<double*>(d_base);
         memcpy(h_in, in_aos, n * in_dim * sizeof(double));
-        int32_t rcs = acm_small_map(ctx, cam, d_in, d_in + 3 * (size_t)ACM_SMALL_BATCH,
-                                    reinterpret_cast<uint8_t*>(d_in + 5 * (size_t)ACM_SMALL_BATCH), (int)n, is_project);
+        const unsigned long long seq = ++ctx->small_seq;
+        int32_t rcs = acm_small_map(ctx, cam, d_in, d_in + 3 * (size_t)ACM_SMALL_BATCH, reinterpret_cast<uint8_t*>(d_in + 5 * (size_t)ACM_SMALL_BATCH),
+                                    (int)n, is_project, reinterpret_cast<unsigned long long*>(d_base + flag_off), seq);
         if (rcs) return rcs;
-        ACM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        bool done = false;
+        if (n <= 128) {
+            const auto t0 = std::chrono::steady_clock::now();
+            for (unsigned spins = 0; !done; ++spins) {
+                if (*h_flag == seq) { done = true; break; }
+                if ((spins & 1023u) == 1023u && std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(50)) break;  // slow device: fall back
+            }
+            std::atomic_thread_fence(std::memory_order_acquire);
+        }
+        if (!done) ACM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         memcpy(out_aos, h_out, n * out_dim * sizeof(double));
         if (status) memcpy(status, h_st, n);
         return ACM_OK;

@@ -98,7 +98,7 @@ struct acm_ctx {
     // query: attributes and occupancy are per device, so they are cached per context, keyed by the kernel's address
     std::unordered_map<const void*, int> blocks_per_sm;
     // small-batch host path (acm_project_host / acm_unproject_host with few points): mapped pinned staging, no allocation per call
-    void* h_small; void* d_small_alias; size_t small_cap;
+    void* h_small; void* d_small_alias; size_t small_cap; unsigned long long small_seq;
     // last camera block prepared by acm_make_cam_params and its device form (the Newton gates are not free)
     acm_camera cam_cache_key; CamParams cam_cache_val; bool cam_cache_valid;
 };
@@ -165,7 +165,8 @@ int32_t acm_allreduce_max_u8(acm_ctx* ctx, uint8_t* d_buf, size_t count);
 int32_t acm_rank_gather_to_host(acm_ctx* ctx, int count);  // d_reduce[0..count) of every rank -> h_reduce[rank][count]
 // project / unproject of n <= ACM_SMALL_BATCH AoS points that sit in device-visible (mapped pinned) memory (acm_exact.cu)
 #define ACM_SMALL_BATCH 2048
-int32_t acm_small_map(acm_ctx* ctx, const acm_camera* cam, const double* d_in, double* d_out, uint8_t* d_status, int n, bool is_project);
+int32_t acm_small_map(acm_ctx* ctx, const acm_camera* cam, const double* d_in, double* d_out, uint8_t* d_status, int n, bool is_project,
+                      unsigned long long* d_done_flag, unsigned long long seq);
 int32_t acm_points_upload_any(acm_ctx* ctx, acm_points* p, const double* host_aos, size_t n, size_t dst_offset);
 
 template <typename T>

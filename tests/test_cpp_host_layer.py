@@ -49,7 +49,8 @@ def test_single_process_multi_gpu_and_scalar_host_path(tmp_path):
     """acm_comm_init_all + acm_*_multi from one host thread (2 contexts in one process) against the same pipeline
     on one GPU, plus the scalar acm_project_host path.  The multi-GPU half reports MULTI_GPU_SKIPPED on a 1-GPU box."""
     exe = _build(tmp_path, "multi_gpu_test")
-    r = subprocess.run([exe, "2"], capture_output=True, text=True, timeout=600)
+    ndev = os.environ.get("ACM_MULTI_NDEV", "2")   # 2 contexts by default; ACM_MULTI_NDEV=8 drives a whole box from one thread
+    r = subprocess.run([exe, ndev], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "MULTI_TEST_OK" in r.stdout
     print(r.stdout)
