@@ -575,22 +575,63 @@ __device__ __forceinline__ bool lin_pass(const LinKernelArgs& a, LmState* sh, Lm
     lin_stream_pass<M, KIND, BS>(a, p, tag, SOLVE && pass > 0, SOLVE);
 
     // ---- reducer warps: sum j belongs to warp (j / nb) % NWARP of block j % nb
+    const bool solve_peers = SOLVE && a.peer.bufs != nullptr;
     bool bad = false;
 #pragma unroll 1
     for (int slot = (int)blockIdx.x + nb * warp; slot < NACC; slot += nb * NWARP) {
         double tot = warp_sum_cells<8>(a.partials + (size_t)slot * nb, nb, lane, tag, bad);
-        if (a.peer.bufs && !bad) tot = warp_peer_exchange(a.peer, seq, slot, tot, lane, bad);
         if (bad) tot = acm_qnan();
-        if (lane == 0) {
-            if (SOLVE) ll_store(a.bcast + slot, tot, tag);
-            else a.out[slot] = tot;
+        if (solve_peers) {
+            // multi-GPU solve: the rank's total goes straight into every rank's exchange buffer; the blocks of every GPU
+            // collect from there (one hop less than exchanging here and re-broadcasting)
+            if (lane < a.peer.n_ranks) ll_store(peer_cell(a.peer.bufs[lane], (int)(seq & 1ULL), a.peer.rank, slot), tot, seq);
+        } else {
+            if (a.peer.bufs && !bad) tot = warp_peer_exchange(a.peer, seq, slot, tot, lane, bad);
+            if (lane == 0) {
+                if (SOLVE) ll_store(a.bcast + slot, tot, tag);
+                else a.out[slot] = tot;
+            }
         }
     }
     if (!SOLVE) return false;
 
     // ---- every block: collect the totals, take the LM step out of shared memory
     int nan_seen = 0;
-    if (tid < NACC) {
+    if (solve_peers) {
+        // n_ranks x NACC cells of this GPU's exchange buffer, spread over the threads of the block (<= 4 each, polled
+        // together), staged in shared memory, then added in rank order: bit-identical on every block of every GPU
+        constexpr int CELLS = (NACC * ACM_MAX_PEERS + BS - 1) / BS;
+        __shared__ double xch[ACM_MAX_PEERS][NACC];
+        const int set = (int)(seq & 1ULL);
+        unsigned char* const mine = a.peer.bufs[a.peer.rank];
+        const unsigned long long* abort_word = reinterpret_cast<const unsigned long long*>(mine);
+        const int total = NACC * a.peer.n_ranks;
+        ulonglong2 c[CELLS];
+        unsigned pending = 0, polls = 0;
+#pragma unroll
+        for (int q = 0; q < CELLS; ++q) if (tid + q * BS < total) pending |= 1u << q;
+        const long long t0 = clock64();
+        while (pending) {
+#pragma unroll
+            for (int q = 0; q < CELLS; ++q)
+                if (pending & (1u << q)) { const int i = tid + q * BS; c[q] = ll_load(peer_cell(mine, set, i / NACC, i % NACC)); }
+#pragma unroll
+            for (int q = 0; q < CELLS; ++q) if ((pending & (1u << q)) && ll_ready(c[q], seq)) pending &= ~(1u << q);
+            if (pending && (++polls & 255u) == 0 && (ld_volatile_u64(abort_word) != 0ULL || clock64() - t0 > ACM_SPIN_LIMIT_CYCLES)) break;
+        }
+#pragma unroll
+        for (int q = 0; q < CELLS; ++q) { const int i = tid + q * BS; if (i < total) xch[i / NACC][i % NACC] = ll_value(c[q]); }
+        if (pending) {   // a peer is gone: raise the sticky abort flag on every rank
+            for (int r = 0; r < a.peer.n_ranks; ++r) st_volatile_u64(reinterpret_cast<unsigned long long*>(a.peer.bufs[r]), 1ULL);
+        }
+        const int lost = __syncthreads_or(pending != 0u);
+        if (tid < NACC) {
+            double v = 0.0;
+            for (int r = 0; r < a.peer.n_ranks; ++r) v += xch[r][tid];
+            if (lost) v = acm_qnan();
+            work->red[tid] = v; nan_seen = !(v == v);
+        }
+    } else if (tid < NACC) {
         const long long t0 = clock64();
         for (;;) {
             const ulonglong2 c = ll_load(a.bcast + tid);

@@ -271,6 +271,23 @@ def test_rust_ffi_crate_declares_every_header_symbol():
     consts = set(re.findall(r"sys::(ACM_[A-Z0-9_]+)", wrapper))
     have = set(re.findall(r"pub const (ACM_[A-Z0-9_]+)", sys_rs))
     assert consts <= have, sorted(consts - have)
+    # the drop-in: `impl CameraModel for GpuCamera<M>` with every method of the reference's trait (src/camera/mod.rs:241-340) ...
+    m = re.search(r"impl<M: CameraModel \+ GpuModelId> CameraModel for GpuCamera<M> \{(.*?)\n\}\n", wrapper, re.S)
+    assert m, "the wrapper crate must implement the reference's trait for GpuCamera"
+    trait_methods = {"project", "unproject", "load_from_yaml", "save_to_yaml", "validate_params", "get_resolution", "get_intrinsics",
+                     "get_distortion", "get_model_name"}
+    assert set(re.findall(r"fn ([a-z_]+)\s*\(", m.group(1))) == trait_methods
+    # ... a model id for each of the seven reference model types ...
+    assert set(re.findall(r"impl GpuModelId for (\w+)", wrapper)) == {"PinholeModel", "RadTanModel", "KannalaBrandtModel", "UcmModel", "EucmModel",
+                                                                      "DoubleSphereModel", "FovModel"}
+    # ... the README-era facade (README.md:70-81), one newtype per target model with the five methods ...
+    assert set(re.findall(r"optimization_cost!\((\w+),", wrapper)) == {"DoubleSphereOptimizationCost", "KannalaBrandtOptimizationCost", "RadTanOptimizationCost",
+                                                                        "UcmOptimizationCost", "EucmOptimizationCost", "FovOptimizationCost"}
+    macro = re.search(r"macro_rules! optimization_cost \{(.*?)\n\}\n", wrapper, re.S).group(1)
+    assert {"new", "linear_estimation", "optimize", "get_intrinsics", "get_distortion"} <= set(re.findall(r"pub fn ([a-z_]+)", macro))
+    # ... and the single-thread multi-GPU group over the *_multi entry points
+    assert {"acm_comm_init_all", "acm_lm_solve_multi", "acm_linear_estimation_multi", "acm_reprojection_error_multi", "acm_sample_points_multi",
+            "acm_linearize_multi", "acm_comm_destroy_all"} <= used
 
 
 def test_export_point_correspondences_format(tmp_path):
