@@ -26,6 +26,7 @@
 #include <stdlib.h>
 
 #include <chrono>
+#include <vector>
 
 struct LmState {
     double x[ACM_MAX_PARAMS], xt[ACM_MAX_PARAMS];
@@ -75,9 +76,10 @@ __device__ __forceinline__ bool chol_solve_work(LmWork* w) {
             for (int k = 0; k < j; ++k) sum -= L[i * (i + 1) / 2 + k] * L[j * (j + 1) / 2 + k];
             if (i == j) {
                 if (!(sum > 0.0)) return false;
-                const double d = sqrt(sum);
-                L[i * (i + 1) / 2 + i] = d;
-                inv[i] = 1.0 / d;
+                // only 1 / L_ii is ever used.  The serial sqrt + division chain of the P pivots was a third of the step
+                // (~300 cycles each); a MUFU-seeded rsqrt (<= 2 ulp, ~80 cycles) perturbs the step no more than the FMA
+                // contraction of this file already does relative to the oracle's separately rounded operations.
+                inv[i] = (sum > 1e-280 && sum < 1e280) ? acm_rsqrt(sum) : 1.0 / sqrt(sum);
             } else {
                 L[i * (i + 1) / 2 + j] = sum * inv[j];
             }
@@ -173,7 +175,11 @@ __device__ __forceinline__ void lm_step_smem(LmState* sh, LmWork* w, int tid) {
                 if (sh->iterations >= sh->max_iter) { sh->status = 3; sh->done = 1; flag_ok = -1; }
                 else sh->iterations++;
             }
-            if (tid < P) { const double d = sqrt(sh->H[tid * P + tid]); w->invD[tid] = (d > 1e-300) ? 1.0 / d : 1.0; }
+            if (tid < P) {
+                const double h = sh->H[tid * P + tid];
+                if (h > 1e-280 && h < 1e280) w->invD[tid] = acm_rsqrt(h);
+                else { const double d = sqrt(h); w->invD[tid] = (d > 1e-300) ? 1.0 / d : 1.0; }
+            }
             __syncthreads();
             ok = flag_ok;
             if (ok < 0) break;  // uniform; thread 0 does not touch the flag again on this path
@@ -398,6 +404,7 @@ struct LinKernelArgs {
     LLCell* bcast;                // [64] totals, reducer warps -> every block (mode 2)
     unsigned long long tag0;      // first hand-off tag of this launch (mode 2 uses tag0 + pass)
     double* out;                  // [NACC] totals (modes 0, 1)
+    long long* trace;             // debug (ACM_LM_TRACE=1): clock64 stamps of block 0, 6 per pass
 };
 
 // One streaming pass of this block over its grid-stride share + the block partial (fixed shuffle tree, then the
@@ -521,13 +528,38 @@ __device__ __forceinline__ void lin_stream_pass(const LinKernelArgs& a, const Li
     // invalid points carry the residual (pen, pen): cost += pen^2 per invalid point
     if (a.pen2x2 != 0.0) acc[LM_::COST] += a.pen2x2 * ((double)npts - acc[LM_::COUNT]);
 
-    // ---- block partial: fixed shuffle tree, then the warps in order
+    if (a.trace != nullptr && prime_next && blockIdx.x == 0 && tid == 0) a.trace[6 * (int)(tag - a.tag0) + 1] = clock64();
+    // ---- block partial: warp totals, then the warps in order.
+    // Warp totals: the shuffle tree costs 15 instructions per accumulator and warp (435 for Double Sphere: 1.2 us of every
+    // pass with 12 warps per SM, measured with ACM_LM_TRACE).  Where the drained cp.async ring is large enough, the warp
+    // transposes instead: lane L stores accumulator k at [k][(L + k) & 31] (conflict-free), lane k then adds row k with four
+    // interleaved partial sums in a fixed order -- ~3 instructions per accumulator.  Deterministic either way.
+    constexpr size_t kRingBytes = (size_t)DEPTH * 5 * BS * sizeof(double2);
+    constexpr bool kTranspose = kRingBytes >= (size_t)NWARP * NACC * 32 * sizeof(double) && NACC <= 32;
+    if constexpr (kTranspose) {
+        __syncthreads();   // every warp has drained its ring slots: the ring is scratch now
+        double* tr = reinterpret_cast<double*>(lin_ring) + (size_t)warp * NACC * 32;
 #pragma unroll
-    for (int k = 0; k < NACC; ++k) {
-        double v = acc[k];
+        for (int k = 0; k < NACC; ++k) tr[k * 32 + ((lane + k) & 31)] = acc[k];
+        __syncwarp();
+        if (lane < NACC) {
+            const double* row = tr + lane * 32;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if (lane == 0) wsum[warp][k] = v;
+            for (int j = 0; j < 32; j += 4) {   // element j of the row = the value of lane j, stored at column (j + lane) & 31
+                s0 += row[(j + 0 + lane) & 31]; s1 += row[(j + 1 + lane) & 31];
+                s2 += row[(j + 2 + lane) & 31]; s3 += row[(j + 3 + lane) & 31];
+            }
+            wsum[warp][lane] = (s0 + s1) + (s2 + s3);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) {
+            double v = acc[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+            if (lane == 0) wsum[warp][k] = v;
+        }
     }
     __syncthreads();
     if (tid < NACC) {
@@ -572,7 +604,10 @@ __device__ __forceinline__ bool lin_pass(const LinKernelArgs& a, LmState* sh, Lm
         if (done) return false;  // converged earlier in this enqueue batch (uniform over the grid)
         lin_derive(M, p);
     }
+    const bool tr = SOLVE && a.trace != nullptr && blockIdx.x == 0 && tid == 0;
+    if (tr) a.trace[6 * pass + 0] = clock64();
     lin_stream_pass<M, KIND, BS>(a, p, tag, SOLVE && pass > 0, SOLVE);
+    if (tr) a.trace[6 * pass + 2] = clock64();
 
     // ---- reducer warps: sum j belongs to warp (j / nb) % NWARP of block j % nb
     const bool solve_peers = SOLVE && a.peer.bufs != nullptr;
@@ -594,6 +629,7 @@ __device__ __forceinline__ bool lin_pass(const LinKernelArgs& a, LmState* sh, Lm
         }
     }
     if (!SOLVE) return false;
+    if (tr) a.trace[6 * pass + 3] = clock64();
 
     // ---- every block: collect the totals, take the LM step out of shared memory
     int nan_seen = 0;
@@ -640,6 +676,7 @@ __device__ __forceinline__ bool lin_pass(const LinKernelArgs& a, LmState* sh, Lm
         }
     }
     nan_seen = __syncthreads_or(nan_seen);
+    if (tr) a.trace[6 * pass + 4] = clock64();
     if (nan_seen) {
         // a hand-off timed out or a sum is NaN: stop here (every block takes the same decision)
         if (tid == 0) { sh->passes++; sh->status = 4; sh->done = 1; }
@@ -647,6 +684,7 @@ __device__ __forceinline__ bool lin_pass(const LinKernelArgs& a, LmState* sh, Lm
     } else {
         lm_step_smem<M, KIND>(sh, work, tid);
     }
+    if (tr) a.trace[6 * pass + 5] = clock64();
     return true;
 }
 
@@ -960,12 +998,28 @@ extern "C" int32_t acm_lm_solve(acm_ctx* ctx, const acm_camera* init, int32_t re
             a.peer.bufs = ctx->d_peer_ptrs; a.peer.n_ranks = ctx->peer_n; a.peer.rank = ctx->peer_rank;
             a.peer.seq = ctx->peer_seq + 1;
         }
+        const bool want_trace = getenv("ACM_LM_TRACE") != nullptr;   // debug: per-phase clock64 stamps of block 0 -> stderr
+        if (want_trace) {
+            rc = acm_ensure_scratch(ctx, (size_t)max_passes * 6 * sizeof(long long));
+            if (rc) return rc;
+            ACM_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, (size_t)max_passes * 6 * sizeof(long long), ctx->stream));
+            a.trace = static_cast<long long*>(ctx->d_scratch);
+        }
         ACM_DISPATCH_LIN(init->model, residual_kind, {
             rc = launch_lin<M, KIND>(ctx, a, xyz, uv);
             if (rc) return rc;
         });
         ACM_CUDA(ctx, cudaMemcpyAsync(h, d, sizeof(LmState), cudaMemcpyDeviceToHost, ctx->stream));
         ACM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (want_trace) {
+            std::vector<long long> t((size_t)max_passes * 6);
+            ACM_CUDA(ctx, cudaMemcpy(t.data(), a.trace, t.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+            for (int k = 0; k < h->passes && k < max_passes; ++k) {
+                const long long* q = &t[6 * k];
+                fprintf(stderr, "[acm lm trace] rank %d pass %2d cycles: stream %lld  block-reduce %lld  reducers %lld  collect %lld  step %lld  | total %lld\n",
+                        ctx->peer_rank, k, q[1] - q[0], q[2] - q[1], q[3] - q[2], q[4] - q[3], q[5] - q[4], q[5] - q[0]);
+            }
+        }
         if (use_peer) ctx->peer_seq += (unsigned long long)h->passes;   // one exchange per executed pass, the same count on every rank
         device_ms = (double)(h->t_end_ns - h->t_begin_ns) * 1e-6;
         if (h->status == LM_STATUS_PEER_FAILURE) return peer_failure(ctx);
