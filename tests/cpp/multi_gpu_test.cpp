@@ -159,6 +159,28 @@ int main(int argc, char** argv) {
     // a group is not a bag of contexts: wrong arrays are rejected, not silently mis-sharded
     std::vector<acm_ctx*> swapped(ctx.rbegin(), ctx.rend());
     CHECK(acm_linearize_multi(swapped.data(), G, &ds1, ACM_RESIDUAL_ALGEBRAIC, Xs.data(), Us.data(), &neG) == ACM_ERR_INVALID_ARG);
+    // A lost peer must end in a hard error on EVERY rank, not in ranks that drift apart: rank 0 solves alone,
+    // nobody delivers the other ranks' sums, its kernel gives up after ~2 s, raises the sticky abort flag in every rank's
+    // exchange buffer and the call returns ACM_ERR_PEER.  The next group call fails on all ranks at once (rank 0 on the
+    // host, the others as soon as their kernels see the flag); re-creating the group clears it.
+    {
+        acm_lm_result rr;
+        double pp[ACM_MAX_PARAMS];
+        const auto t0 = std::chrono::steady_clock::now();
+        CHECK(acm_lm_solve(ctx[0], &ds1, ACM_RESIDUAL_ALGEBRAIC, Xs[0], Us[0], lo, hi, nullptr, pp, &rr) == ACM_ERR_PEER);
+        const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        std::printf("PEER_TIMEOUT_S %.2f (%s)\n", sec, acm_last_error(ctx[0]));
+        CHECK(sec > 0.5 && sec < 20.0);
+        const auto t1 = std::chrono::steady_clock::now();
+        CHECK(acm_lm_solve_multi(ctx.data(), G, &ds1, ACM_RESIDUAL_ALGEBRAIC, Xs.data(), Us.data(), lo, hi, nullptr, pp, &rr) == ACM_ERR_PEER);
+        CHECK(std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count() < 1.0);   // fails fast: the flag is sticky
+        CHECK(acm_linearize_multi(ctx.data(), G, &ds1, ACM_RESIDUAL_ALGEBRAIC, Xs.data(), Us.data(), &neG) == ACM_ERR_PEER);
+        OK(ctx[0], acm_comm_destroy_all(ctx.data(), G));
+        OK(ctx[0], acm_comm_init_all(ctx.data(), G));
+        OK(ctx[0], acm_lm_solve_multi(ctx.data(), G, &ds1, ACM_RESIDUAL_ALGEBRAIC, Xs.data(), Us.data(), lo, hi, nullptr, pp, &rr));
+        CHECK(rr.status == r1.status && rr.iterations == r1.iterations);
+        for (int i = 0; i < 6; ++i) CHECK(close_rel(pp[i], par1[i], 1e-11));
+    }
     for (int g = 0; g < G; ++g) { acm_points_destroy(ctx[g], Xs[g]); acm_points_destroy(ctx[g], Us[g]); }
     OK(ctx[0], acm_comm_destroy_all(ctx.data(), G));
     for (int g = 0; g < G; ++g) acm_ctx_destroy(ctx[g]);
