@@ -26,3 +26,14 @@ for interp in (acm.InterpolationMethod.Bilinear, acm.InterpolationMethod.Nearest
     print("undistort", int(interp), out.mean(), out2.mean())
 ctx.sync()
 print("ok")
+# round 2: scalar host path (mapped staging + completion flag), small batches, Jacobian kernels (vector and scalar forms)
+p = kb.project([0.1, 0.2, 1.0]); r = kb.unproject(p)
+uvb, stb = kb.project_batch(np.tile([0.1, 0.2, 1.0], (777, 1)))
+rt = acm.RadTanModel(acm.Intrinsics(461.629, 460.152, 362.68, 246.049), acm.Resolution(752, 480), [-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05, 0.0], ctx=ctx)
+px = np.random.default_rng(1).uniform([0, 0], [752, 480], size=(50_001, 2))
+rays, st = rt.unproject_batch(px)
+for n in (4096, 4097):
+    pts = np.random.default_rng(2).normal(size=(n, 3)) * [0.3, 0.3, 0.1] + [0, 0, 1.5]
+    for m in (kb, rt):
+        m.project_jacobian_batch(pts); m.project_point_jacobian_batch(pts)
+print("round-2 paths ok", p, int((st == 0).sum()))
