@@ -656,7 +656,16 @@ __global__ void __launch_bounds__(256, 3) undistort_bilinear_list_kernel(const _
 #define UND_BOX_W 128
 #define UND_BOX_ROWS 10      // tallest box (the shared-memory tile holds this many rows)
 #define UND_MIN_ROWS 4       // one tensor map per box height UND_MIN_ROWS .. UND_BOX_ROWS: a warp fetches only the rows it needs
-#define UND_STAGES 4
+// Round 2, same-box A/B (4096^2, 32 frames): 4 stages x 1 frame 39.2 / 23.9 us per frame (bilinear / nearest), 2 stages x 2
+// frames 38.4 / 21.6 (one barrier wait and one re-arm per two frames), 3 x 2 and 6 x 1 slower (shared memory costs a resident
+// block).  Addressing the output rows as a warp-uniform frame base + 32-bit lane offsets instead of a per-lane pointer
+// that is advanced per frame cost 18 % in the bilinear kernel (46.3 us) -- kept out.
+#ifndef UND_STAGES
+#define UND_STAGES 2       // ring depth in stages
+#endif
+#ifndef UND_FPS
+#define UND_FPS 2          // frames per stage: one TMA box {UND_BOX_W, rows, UND_FPS}, one barrier wait and one re-arm per UND_FPS frames
+#endif
 
 struct UndMaps { CUtensorMap m[UND_BOX_ROWS - UND_MIN_ROWS + 1]; };
 
@@ -685,7 +694,7 @@ __global__ void __launch_bounds__(256, 3) undistort_bilinear_tma_kernel(const __
                                                                      int H, int n_frames, uint32_t* __restrict__ list,
                                                                      uint32_t* __restrict__ list_count) {
     constexpr uint32_t TIE_E = 640u;
-    constexpr int TILE = UND_BOX_W * UND_BOX_ROWS;
+    constexpr int TILE = UND_FPS * UND_BOX_W * UND_BOX_ROWS;   // one stage = UND_FPS frames of the box
     // dynamic shared memory: tiles[8 warps][STAGES][TILE] | mbarriers[8][STAGES] | wx[4][256] | wy[4][256]
     // (the f64 weights are only read by the rare exact re-blend; keeping them out of registers is what
     // lets three blocks stay resident)
@@ -751,7 +760,8 @@ __global__ void __launch_bounds__(256, 3) undistort_bilinear_tma_kernel(const __
     const uint32_t tile0 = und_smem_u32(tiles + warp * UND_STAGES * TILE), bar0 = und_smem_u32(bars + warp * UND_STAGES);
     const int box_rows = any_valid ? max(by_max - box_y + 1, UND_MIN_ROWS) : UND_MIN_ROWS;
     const CUtensorMap* const in_map = &in_maps.m[box_rows - UND_MIN_ROWS];
-    const uint32_t box_bytes = (uint32_t)(box_rows * UND_BOX_W);
+    const uint32_t frame_stride = (uint32_t)(box_rows * UND_BOX_W);   // the box is stored densely: frame h of a stage starts at h * rows * 128
+    const uint32_t box_bytes = UND_FPS * frame_stride;
     uint32_t so[4];  // shared-memory address of the aligned tap window in stage 0
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -762,7 +772,6 @@ __global__ void __launch_bounds__(256, 3) undistort_bilinear_tma_kernel(const __
     const uint32_t out_sel = (lane % 3 == 0) ? 0x4210u : (lane % 3 == 1) ? 0x5421u : 0x6542u;
     const int valid_px = min(32, W - x0);                     // multiple of 4 because W % 16 == 0
     const int n_rows = (lane < 24 && 4 * lane + 3 < 3 * valid_px) ? min(4, H - y0) : 0;  // rows this lane stores
-    uint8_t* dst = out + ((size_t)y0 * W + x0) * 3 + 4 * lane;
     if (lane == 0) {
 #pragma unroll
         for (int sidx = 0; sidx < UND_STAGES; ++sidx) und_mbar_init(bar0 + 8 * sidx, 1);
@@ -771,9 +780,9 @@ __global__ void __launch_bounds__(256, 3) undistort_bilinear_tma_kernel(const __
         if (any_valid) {
 #pragma unroll
             for (int sidx = 0; sidx < UND_STAGES; ++sidx) {
-                if (sidx < n_frames) {
+                if (sidx * UND_FPS < n_frames) {   // a box that reaches past the last frame is zero-filled and still counts in full
                     und_mbar_expect_tx(bar0 + 8 * sidx, box_bytes);
-                    und_tma_load_3d(tile0 + sidx * TILE, in_map, bar0 + 8 * sidx, box_x, box_y, sidx);
+                    und_tma_load_3d(tile0 + sidx * TILE, in_map, bar0 + 8 * sidx, box_x, box_y, sidx * UND_FPS);
                 }
             }
         }
@@ -782,8 +791,9 @@ __global__ void __launch_bounds__(256, 3) undistort_bilinear_tma_kernel(const __
     int stage = 0;
     uint32_t parity = 0;
     const long long t_begin = clock64();
-    for (int f = 0; f < n_frames; ++f, dst += frame_bytes) {
-        uint32_t px[4] = {0u, 0u, 0u, 0u};  // [R G B .] per pixel
+    uint8_t* dst = out + ((size_t)y0 * W + x0) * 3 + 4 * lane;
+    for (int f0 = 0; f0 < n_frames; f0 += UND_FPS) {
+        const uint32_t stage_off = (uint32_t)(stage * TILE);
         if (any_valid) {
             const uint32_t bar = bar0 + 8 * stage;
             int spins = 0;
@@ -791,68 +801,77 @@ __global__ void __launch_bounds__(256, 3) undistort_bilinear_tma_kernel(const __
                 // a lost TMA must not hang the GPU: give up after ~2 s
                 if ((++spins & 255) == 0 && clock64() - t_begin > 4000000000LL) __trap();
             }
-            const uint32_t stage_off = (uint32_t)(stage * TILE);
-            uint32_t redo = slow;
-            uint32_t tz[4];
-            if (NEAREST) {  // the sample is the pixel itself (undistort.rs:79-90): 3 bytes out of two aligned words
+        }
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    uint32_t a0, a1;
-                    const uint32_t addr = so[k] + stage_off;
-                    asm volatile("ld.shared.u32 %0, [%2];\n ld.shared.u32 %1, [%2+4];" : "=r"(a0), "=r"(a1) : "r"(addr));
-                    px[k] = ((valid >> k) & 1u) ? (__byte_perm(a0, a1, sel[k]) & 0xFFFFFFu) : 0u;
+        for (int h = 0; h < UND_FPS; ++h) {
+            const int f = f0 + h;
+            if (f >= n_frames) break;
+            uint32_t px[4] = {0u, 0u, 0u, 0u};  // [R G B .] per pixel
+            if (any_valid) {
+                const uint32_t tile_off = stage_off + (uint32_t)h * frame_stride;
+                uint32_t redo = slow;
+                uint32_t tz[4];
+                if (NEAREST) {  // the sample is the pixel itself (undistort.rs:79-90): 3 bytes out of two aligned words
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        uint32_t a0, a1;
+                        const uint32_t addr = so[k] + tile_off;
+                        asm volatile("ld.shared.u32 %0, [%2];\n ld.shared.u32 %1, [%2+4];" : "=r"(a0), "=r"(a1) : "r"(addr));
+                        px[k] = ((valid >> k) & 1u) ? (__byte_perm(a0, a1, sel[k]) & 0xFFFFFFu) : 0u;
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        uint32_t a0, a1, a2, b0, b1, b2;
+                        const uint32_t addr = so[k] + tile_off;
+                        asm volatile("ld.shared.u32 %0, [%6];\n ld.shared.u32 %1, [%6+4];\n ld.shared.u32 %2, [%6+8];\n"
+                                     "ld.shared.u32 %3, [%6+128];\n ld.shared.u32 %4, [%6+132];\n ld.shared.u32 %5, [%6+136];"
+                                     : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(b0), "=r"(b1), "=r"(b2) : "r"(addr));
+                        const uint32_t A = __byte_perm(a0, a1, sel[k]), B = __byte_perm(a1, a2, sel[k]);     // [r0 g0 b0 r1] [g1 b1 . .]
+                        const uint32_t A2 = __byte_perm(b0, b1, sel[k]), B2 = __byte_perm(b1, b2, sel[k]);
+                        const uint32_t PR = __byte_perm(A, A2, 0x7430);                                       // [r00 r10 r01 r11]
+                        const uint32_t T0 = __byte_perm(A, B, 0x5241), T1 = __byte_perm(A2, B2, 0x5241);      // [g0 g1 b0 b1]
+                        const uint32_t PG = __byte_perm(T0, T1, 0x5410), PB = __byte_perm(T0, T1, 0x7632);
+                        const uint32_t sr = (__dp2a_hi(w23[k], PR, __dp2a_lo(w01[k], PR, 0u)) << 8) + __dp4a(PR, wlo[k], 1u << 23);
+                        const uint32_t sg = (__dp2a_hi(w23[k], PG, __dp2a_lo(w01[k], PG, 0u)) << 8) + __dp4a(PG, wlo[k], 1u << 23);
+                        const uint32_t sb = (__dp2a_hi(w23[k], PB, __dp2a_lo(w01[k], PB, 0u)) << 8) + __dp4a(PB, wlo[k], 1u << 23);
+                        px[k] = __byte_perm(__byte_perm(sr, sg, 0x4473), sb, 0x4710);                         // [sr.3 sg.3 sb.3 .]
+                        // distance of the 24-bit fraction to a rounding tie, scaled by 2^8 so that the 32-bit wrap does the
+                        // masking: ((s + E) mod 2^24) < 2E  <=>  (s * 2^8 + E * 2^8) mod 2^32 < 2E * 2^8
+                        tz[k] = min(min(sr * 256u + TIE_E * 256u, sg * 256u + TIE_E * 256u), sb * 256u + TIE_E * 256u);
+                    }
+                    if (min(min(tz[0], tz[1]), min(tz[2], tz[3])) < 2u * TIE_E * 256u) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) redo |= (tz[k] < 2u * TIE_E * 256u ? 1u : 0u) << k;
+                    }
                 }
-            } else {
+                if (redo) {  // rare: redo these pixels with the reference's f64 expression from global memory
+                    const uint8_t* src = in + (size_t)f * frame_bytes;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                uint32_t a0, a1, a2, b0, b1, b2;
-                const uint32_t addr = so[k] + stage_off;
-                asm volatile("ld.shared.u32 %0, [%6];\n ld.shared.u32 %1, [%6+4];\n ld.shared.u32 %2, [%6+8];\n"
-                             "ld.shared.u32 %3, [%6+128];\n ld.shared.u32 %4, [%6+132];\n ld.shared.u32 %5, [%6+136];"
-                             : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(b0), "=r"(b1), "=r"(b2) : "r"(addr));
-                const uint32_t A = __byte_perm(a0, a1, sel[k]), B = __byte_perm(a1, a2, sel[k]);     // [r0 g0 b0 r1] [g1 b1 . .]
-                const uint32_t A2 = __byte_perm(b0, b1, sel[k]), B2 = __byte_perm(b1, b2, sel[k]);
-                const uint32_t PR = __byte_perm(A, A2, 0x7430);                                       // [r00 r10 r01 r11]
-                const uint32_t T0 = __byte_perm(A, B, 0x5241), T1 = __byte_perm(A2, B2, 0x5241);      // [g0 g1 b0 b1]
-                const uint32_t PG = __byte_perm(T0, T1, 0x5410), PB = __byte_perm(T0, T1, 0x7632);
-                const uint32_t sr = (__dp2a_hi(w23[k], PR, __dp2a_lo(w01[k], PR, 0u)) << 8) + __dp4a(PR, wlo[k], 1u << 23);
-                const uint32_t sg = (__dp2a_hi(w23[k], PG, __dp2a_lo(w01[k], PG, 0u)) << 8) + __dp4a(PG, wlo[k], 1u << 23);
-                const uint32_t sb = (__dp2a_hi(w23[k], PB, __dp2a_lo(w01[k], PB, 0u)) << 8) + __dp4a(PB, wlo[k], 1u << 23);
-                px[k] = __byte_perm(__byte_perm(sr, sg, 0x4473), sb, 0x4710);                         // [sr.3 sg.3 sb.3 .]
-                // distance of the 24-bit fraction to a rounding tie, scaled by 2^8 so that the 32-bit wrap does the
-                // masking: ((s + E) mod 2^24) < 2E  <=>  (s * 2^8 + E * 2^8) mod 2^32 < 2E * 2^8
-                tz[k] = min(min(sr * 256u + TIE_E * 256u, sg * 256u + TIE_E * 256u), sb * 256u + TIE_E * 256u);
-            }
-            if (min(min(tz[0], tz[1]), min(tz[2], tz[3])) < 2u * TIE_E * 256u) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) redo |= (tz[k] < 2u * TIE_E * 256u ? 1u : 0u) << k;
-            }
-            }
-            if (redo) {  // rare: redo these pixels with the reference's f64 expression from global memory
-                const uint8_t* src = in + (size_t)f * frame_bytes;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if ((redo >> k) & 1u) {
-                        // rebuild the byte offset of p00 from the tile address and the byte selector
-                        const uint32_t rel = so[k] - tile0;
-                        const int o00 = (box_y + (int)(rel / UND_BOX_W)) * row_stride + box_x + (int)(rel % UND_BOX_W) + (int)(sel[k] & 3u);
-                        uint8_t o[3];
-                        blend_exact_px(src + o00, row_stride, s_wx[k * 256 + threadIdx.x], s_wy[k * 256 + threadIdx.x], o);
-                        px[k] = o[0] | (o[1] << 8) | ((uint32_t)o[2] << 16);
+                    for (int k = 0; k < 4; ++k) {
+                        if ((redo >> k) & 1u) {
+                            // rebuild the byte offset of p00 from the tile address and the byte selector
+                            const uint32_t rel = so[k] - tile0;
+                            const int o00 = (box_y + (int)(rel / UND_BOX_W)) * row_stride + box_x + (int)(rel % UND_BOX_W) + (int)(sel[k] & 3u);
+                            uint8_t o[3];
+                            blend_exact_px(src + o00, row_stride, s_wx[k * 256 + threadIdx.x], s_wy[k * 256 + threadIdx.x], o);
+                            px[k] = o[0] | (o[1] << 8) | ((uint32_t)o[2] << 16);
+                        }
                     }
                 }
             }
-        }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t pa = __shfl_sync(0xffffffffu, px[k], src_lane);
-            const uint32_t pb = __shfl_sync(0xffffffffu, px[k], (src_lane + 1) & 31);
-            if (k < n_rows) __stcs(reinterpret_cast<uint32_t*>(dst + (size_t)k * row_stride), __byte_perm(pa, pb, out_sel));
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t pa = __shfl_sync(0xffffffffu, px[k], src_lane);
+                const uint32_t pb = __shfl_sync(0xffffffffu, px[k], (src_lane + 1) & 31);
+                if (k < n_rows) __stcs(reinterpret_cast<uint32_t*>(dst + (size_t)k * row_stride), __byte_perm(pa, pb, out_sel));
+            }
+            dst += frame_bytes;
         }
         // every lane's tile reads of this stage have been consumed by the shuffles above
-        if (any_valid && lane == 0 && f + UND_STAGES < n_frames) {
+        if (any_valid && lane == 0 && f0 + UND_STAGES * UND_FPS < n_frames) {
             und_mbar_expect_tx(bar0 + 8 * stage, box_bytes);
-            und_tma_load_3d(tile0 + stage * TILE, in_map, bar0 + 8 * stage, box_x, box_y, f + UND_STAGES);
+            und_tma_load_3d(tile0 + stage * TILE, in_map, bar0 + 8 * stage, box_x, box_y, f0 + UND_STAGES * UND_FPS);
         }
         if (++stage == UND_STAGES) { stage = 0; parity ^= 1u; }
     }
@@ -922,7 +941,7 @@ static bool make_frame_tensor_map(CUtensorMap* map, const uint8_t* d_in, int W, 
     if (!encode) return false;
     const cuuint64_t gdim[3] = {(cuuint64_t)3 * W, (cuuint64_t)H, (cuuint64_t)n_frames};
     const cuuint64_t gstride[2] = {(cuuint64_t)3 * W, (cuuint64_t)3 * W * H};  // bytes, dims 1 and 2
-    const cuuint32_t box[3] = {UND_BOX_W, (cuuint32_t)box_rows, 1};
+    const cuuint32_t box[3] = {UND_BOX_W, (cuuint32_t)box_rows, UND_FPS};
     const cuuint32_t estride[3] = {1, 1, 1};
     return encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(d_in), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -965,7 +984,7 @@ extern "C" int32_t acm_undistort_rgb8(acm_ctx* ctx, const acm_camera* cam, const
         uint32_t* d_count = static_cast<uint32_t*>(ctx->d_scratch);
         uint32_t* d_list = d_count + 64;
         ACM_CUDA(ctx, cudaMemsetAsync(d_count, 0, sizeof(uint32_t), ctx->stream));
-        constexpr int und_smem_bytes = 8 * UND_STAGES * UND_BOX_W * UND_BOX_ROWS + 8 * UND_STAGES * 8 + 2 * 4 * 256 * 8;
+        constexpr int und_smem_bytes = 8 * UND_STAGES * UND_FPS * UND_BOX_W * UND_BOX_ROWS + 8 * UND_STAGES * 8 + 2 * 4 * 256 * 8;
         if (interpolation == ACM_INTERP_BILINEAR) {
             ACM_DISPATCH_MODEL(cam->model, (cudaFuncSetAttribute(undistort_bilinear_tma_kernel<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, und_smem_bytes)))
             ACM_DISPATCH_MODEL(cam->model, (undistort_bilinear_tma_kernel<M, false><<<fgrid, 256, und_smem_bytes, ctx->stream>>>(c, t[0], t[1], t[2], t[3], map, d_in, d_out, W, H, (int)n_frames, d_list, d_count)))
