@@ -320,6 +320,29 @@ def run_ours(args):
               "us_per_pass": 1e3 * ms_lm / max(r.passes, 1), "device_us_per_pass": 1e3 * dev_lm / max(r.passes, 1),
               "timing": "ms = host wall of acm_lm_solve (upload of the 1 KB state, ONE kernel launch, read-back); device_ms = %globaltimer from the first pass to the last LM step inside that kernel; max over ranks",
               "params": [float(v) for v in r.parameters], "final_cost": r.final_cost, "points_per_gpu": m, "rank_identical": bool(lm_identical)}
+        # --- the converter steps around the solve, sharded the same way: linear estimation,
+        # reprojection statistics of the converged model over the sharded correspondences, sample_points over the sharded grid
+        lin_start = [float(v) for v in start]
+        err = acm.compute_reprojection_error(dsl, Xl, Ul)      # statistics of the WHOLE set on every rank (sums / histogram all-reduced)
+        n_req = 1_000_000
+        s_uv, s_xyz = acm.sample_points(kb, n_req, device=True, shard=(rank, world))
+        su = s_uv.numpy()
+        kept_local = int(su.shape[0])
+        xor_local = int(np.bitwise_xor.reduce(su.view(np.uint64).ravel())) if kept_local else 0   # order-independent, exact
+        s_uv.free(); s_xyz.free()
+        pipe_local = np.array([kept_local, xor_local & 0xFFFFFFFF, xor_local >> 32], dtype=np.float64)
+        if dist is not None:
+            tl = [torch.zeros(3, dtype=torch.float64, device="cuda") for _ in range(world)]
+            dist.all_gather(tl, torch.tensor(pipe_local, device="cuda"))
+            pipe_all = [t.cpu().numpy() for t in tl]
+            te = torch.tensor([err.mean, err.median, err.max, float(err.count)], dtype=torch.float64, device="cuda")
+            tmin, tmax = te.clone(), te.clone()
+            dist.all_reduce(tmin, op=dist.ReduceOp.MIN); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            stats_identical = bool(torch.equal(tmin, tmax))
+        else:
+            pipe_all = [pipe_local]; stats_identical = True
+        lm["pipeline"] = {"reprojection_error": {"mean": err.mean, "median": err.median, "max": err.max, "count": int(err.count), "rank_identical": stats_identical},
+                          "sample_points": {"requested": n_req, "kept_per_rank": [int(p[0]) for p in pipe_all]}}
         if rank == 0 and not args.no_lm_check:
             # the same conversion through the CPU oracle (all host threads; it walks the same algorithm): parameters <= 1e-9 relative
             from oracle import oracle as O
@@ -329,11 +352,27 @@ def run_ours(args):
             uvo, _ = O.project(O.make_model(O.KB, KB_SAMPLE, 512, 512), xyz, nthreads=os.cpu_count() or 1)
             om = O.make_model(O.DS, KB_SAMPLE[:4] + [0.5, 0.1], 512, 512)
             O.linear_estimation(om, xyz, uvo)
+            om_lin = om.params().copy()
             b = acm.CONVERTER_BOUNDS[5]
             po, ro = O.lm_solve(om, O.RES_ALGEBRAIC, xyz, uvo, [x[0] for x in b], [x[1] for x in b], nthreads=os.cpu_count() or 1)
             rel = float(np.max(np.abs(np.asarray(r.parameters) - po) / np.abs(po)))
+            lin_o = om_lin
+            lin_rel = float(np.max(np.abs(np.asarray(lin_start) - lin_o) / np.maximum(np.abs(lin_o), 1e-300)))
+            omf = O.make_model(O.DS, [float(v) for v in r.parameters], 512, 512)
+            eo = O.reprojection_error(omf, xyz, uvo)
+            stat_rel = float(max(abs(err.mean - eo.mean) / eo.mean, abs(err.median - eo.median) / eo.median, abs(err.max - eo.max) / eo.max))
+            uvs, _ = O.sample_points(O.make_model(O.KB, KB_SAMPLE, 512, 512), n_req)
+            xor_o = int(np.bitwise_xor.reduce(uvs.view(np.uint64).ravel()))
+            xor_g = 0
+            for p in pipe_all:
+                xor_g ^= int(p[1]) | (int(p[2]) << 32)
+            kept_g = sum(int(p[0]) for p in pipe_all)
             lm["vs_oracle"] = {"params_rel": rel, "same_trajectory": bool((r.status, r.iterations, r.passes) == (ro.status, ro.iterations, ro.passes)),
-                               "oracle_s": time.perf_counter() - t0, "ok": bool(rel <= 1e-9)}
+                               "linear_estimation_rel": lin_rel, "reprojection_stats_rel": stat_rel, "reprojection_count_equal": bool(int(err.count) == int(eo.count)),
+                               "sample_points_kept": [kept_g, int(uvs.shape[0])], "sample_points_pixels_identical": bool(kept_g == uvs.shape[0] and xor_g == xor_o),
+                               "oracle_s": time.perf_counter() - t0}
+            v = lm["vs_oracle"]
+            v["ok"] = bool(rel <= 1e-9 and lin_rel <= 1e-9 and stat_rel <= 1e-9 and v["reprojection_count_equal"] and v["sample_points_pixels_identical"] and stats_identical)
             del xyz, uvo
         Xl.free(); Ul.free()
 
@@ -407,6 +446,8 @@ def run_ours(args):
         print(json.dumps(line))
         if check is not None and not check.get("ok", False):
             raise SystemExit("bench.py: the sharded pass disagrees with the oracle (see \"check\")")
+        if lm and lm.get("vs_oracle") and not lm["vs_oracle"].get("ok", False):
+            raise SystemExit("bench.py: the sharded converter pipeline disagrees with the oracle (see \"lm_conversion.vs_oracle\")")
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
