@@ -159,6 +159,38 @@ int main(int argc, char** argv) {
     // a group is not a bag of contexts: wrong arrays are rejected, not silently mis-sharded
     std::vector<acm_ctx*> swapped(ctx.rbegin(), ctx.rend());
     CHECK(acm_linearize_multi(swapped.data(), G, &ds1, ACM_RESIDUAL_ALGEBRAIC, Xs.data(), Us.data(), &neG) == ACM_ERR_INVALID_ARG);
+    // The minimum-point tests of linear_estimation look at the GLOBAL count (with local counts some ranks
+    // returned InvalidParams before the collective and the others hung in it).  5 correspondences over G ranks: shards of
+    // 0..3 points, KB needs 4 in total -> every rank succeeds and agrees with one GPU; 3 correspondences -> every rank fails.
+    {
+        acm_ctx* c1 = nullptr;
+        OK(nullptr, acm_ctx_create(0, nullptr, &c1));   // a second, ungrouped context on device 0 for the single-GPU answer
+        for (size_t total : {(size_t)5, (size_t)3}) {
+            std::vector<double> hx(3 * total), hu(2 * total);
+            for (size_t i = 0; i < total; ++i) { hx[3 * i] = 0.1 * (double)(i + 1); hx[3 * i + 1] = -0.07 * (double)(i + 1); hx[3 * i + 2] = 1.0 + 0.1 * (double)i; }
+            std::vector<uint8_t> st(total);
+            OK(c1, acm_project_host(c1, &kb, hx.data(), total, hu.data(), st.data()));
+            acm_points *x1 = nullptr, *u1 = nullptr;
+            OK(c1, acm_points_create(c1, 3, total, ACM_F64, &x1)); OK(c1, acm_points_create(c1, 2, total, ACM_F64, &u1));
+            OK(c1, acm_points_upload_aos_f64(c1, x1, hx.data(), total)); OK(c1, acm_points_upload_aos_f64(c1, u1, hu.data(), total));
+            acm_camera k1 = make(ACM_MODEL_KANNALA_BRANDT, {KB[0], KB[1], KB[2], KB[3], 0, 0, 0, 0}, 512, 512), kG = k1;
+            const int32_t rc1 = acm_linear_estimation(c1, &k1, x1, u1);
+            std::vector<acm_points*> xs(G, nullptr), us(G, nullptr);
+            for (int g = 0; g < G; ++g) {
+                const size_t a = total * g / G, b = total * (g + 1) / G;
+                OK(ctx[g], acm_points_create(ctx[g], 3, b - a, ACM_F64, &xs[g])); OK(ctx[g], acm_points_create(ctx[g], 2, b - a, ACM_F64, &us[g]));
+                if (b > a) { OK(ctx[g], acm_points_upload_aos_f64(ctx[g], xs[g], hx.data() + 3 * a, b - a)); OK(ctx[g], acm_points_upload_aos_f64(ctx[g], us[g], hu.data() + 2 * a, b - a)); }
+                OK(ctx[g], acm_ctx_sync(ctx[g]));
+            }
+            const int32_t rcG = acm_linear_estimation_multi(ctx.data(), G, &kG, xs.data(), us.data());
+            CHECK(rcG == rc1);
+            CHECK(total >= 4 ? rc1 == ACM_OK : rc1 == ACM_ERR_INVALID_PARAMS);
+            if (rc1 == ACM_OK) for (int i = 4; i < 8; ++i) CHECK(close_rel(kG.params[i], k1.params[i], 1e-9) || std::fabs(kG.params[i] - k1.params[i]) < 1e-12);
+            for (int g = 0; g < G; ++g) { acm_points_destroy(ctx[g], xs[g]); acm_points_destroy(ctx[g], us[g]); }
+            acm_points_destroy(c1, x1); acm_points_destroy(c1, u1);
+        }
+        acm_ctx_destroy(c1);
+    }
     // A lost peer must end in a hard error on EVERY rank, not in ranks that drift apart: rank 0 solves alone,
     // nobody delivers the other ranks' sums, its kernel gives up after ~2 s, raises the sticky abort flag in every rank's
     // exchange buffer and the call returns ACM_ERR_PEER.  The next group call fails on all ranks at once (rank 0 on the
