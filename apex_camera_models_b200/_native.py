@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ACM_LIB_PATH") or os.path.join(_HERE, "lib", "libacm.so")  # the override is a tuning aid (A/B of two builds)
 
 ACM_MAX_PARAMS = 9
+ABI_VERSION = 2  # include/acm.h ACM_ABI_VERSION: acm_lm_result gained device_ms, the *_multi entry points
 F64, F32 = 0, 1
 RESIDUAL_PIXEL, RESIDUAL_ALGEBRAIC = 0, 1
 INTERP_NEAREST, INTERP_BILINEAR = 0, 1
@@ -141,6 +142,8 @@ def load() -> C.CDLL:
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError => the build is stale
         fn.restype, fn.argtypes = res, args
+    if lib.acm_abi_version() != ABI_VERSION:
+        raise ImportError(f"{LIB_PATH} has ABI version {lib.acm_abi_version()}, this package binds version {ABI_VERSION}: rebuild with `python __graft_entry__.py`")
     return lib
 
 

@@ -6,6 +6,7 @@
 use libc::{c_char, c_void, size_t};
 
 pub const ACM_MAX_PARAMS: usize = 9;
+pub const ACM_ABI_VERSION: i32 = 2;
 pub const ACM_OK: i32 = 0;
 pub const ACM_ERR_INVALID_ARG: i32 = -1;
 pub const ACM_ERR_CUDA: i32 = -2;

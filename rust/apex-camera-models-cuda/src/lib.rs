@@ -49,6 +49,9 @@ static GLOBAL_CONTEXT: OnceLock<Result<Arc<Context>, String>> = OnceLock::new();
 
 impl Context {
     pub fn new(device: i32) -> Result<Self, CameraModelError> {
+        if unsafe { sys::acm_abi_version() } != sys::ACM_ABI_VERSION {
+            return Err(CameraModelError::NumericalError("libacm.so ABI version differs from the one acm-sys binds".into()));
+        }
         let mut h = ptr::null_mut();
         let rc = unsafe { sys::acm_ctx_create(device, ptr::null_mut(), &mut h) };
         if rc != sys::ACM_OK {
