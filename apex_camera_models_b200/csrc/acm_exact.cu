@@ -121,8 +121,20 @@ __global__ void __launch_bounds__(256, (PuStream<PU_PROJECT, M>::PIPE ? 3 : 0)) 
 // ---------------------------------------------------------------------------------------
 // unproject: uv -> ray + status
 // ---------------------------------------------------------------------------------------
+// resident 256-thread blocks per SM the unproject kernel is compiled for (register cap): 3 with the pipelined stream; the Newton
+// models are bound by the latency of their dependent chains: RadTan gains 2.6 % from a 4th block (64 registers), Kannala-Brandt
+// nothing (profiles/r02_ab_unproj_occ.log; -DACM_EXP_UNPROJ_MINB_RT / _KB: A/B aid)
+#ifndef ACM_EXP_UNPROJ_MINB_RT
+#define ACM_EXP_UNPROJ_MINB_RT 4
+#endif
+#ifndef ACM_EXP_UNPROJ_MINB_KB
+#define ACM_EXP_UNPROJ_MINB_KB 3
+#endif
+template <int M> struct UnprojBounds { static constexpr int MINB = PuStream<PU_UNPROJECT, M>::PIPE ? 3 : 0; };
+template <> struct UnprojBounds<ACM_MODEL_RADTAN> { static constexpr int MINB = ACM_EXP_UNPROJ_MINB_RT; };
+template <> struct UnprojBounds<ACM_MODEL_KANNALA_BRANDT> { static constexpr int MINB = ACM_EXP_UNPROJ_MINB_KB; };
 template <int M, typename T, bool IEEE = ACM_TAIL_DEFAULT>
-__global__ void __launch_bounds__(256, (PuStream<PU_UNPROJECT, M>::PIPE ? 3 : 0)) unproject_kernel(const __grid_constant__ CamParams c, const T* __restrict__ U,
+__global__ void __launch_bounds__(256, UnprojBounds<M>::MINB) unproject_kernel(const __grid_constant__ CamParams c, const T* __restrict__ U,
                                                         const T* __restrict__ V, T* __restrict__ X, T* __restrict__ Y,
                                                         T* __restrict__ Z, uint8_t* __restrict__ S, size_t n) {
     using VT = typename Vec<T>::type;
