@@ -384,11 +384,14 @@ __device__ __forceinline__ void lin_accumulate(double* acc, double ru, double rv
 }
 
 // Reduced accumulator vector -> dense symmetric H (P x P), g, cost, count.
-template <int ND, bool UNIT_C>
-__host__ __device__ inline void lin_unpack(const double* r, double* H, double* g, double* cost, double* count) {  // params not needed
+// FULL = false (the LM step): only the structurally non-zero entries of the UPPER triangle are written -- the caller zeroed H
+// once and mirrors while it copies -- so the serial part of the step is ~25 independent load/store pairs (__restrict__ lets
+// the loads run ahead of the stores) instead of P^2 zero stores, the fill and P(P-1)/2 dependent load-store mirrors.
+template <int ND, bool UNIT_C, bool FULL = true>
+__host__ __device__ inline void lin_unpack(const double* __restrict__ r, double* __restrict__ H, double* __restrict__ g, double* __restrict__ cost, double* __restrict__ count) {  // params not needed
     using L = AccLayout<ND>;
     constexpr int P = 4 + ND;
-    for (int i = 0; i < P * P; ++i) H[i] = 0.0;
+    if (FULL) for (int i = 0; i < P * P; ++i) H[i] = 0.0;
     const double cnt = r[L::COUNT];
     H[0 * P + 0] = r[L::HFF]; H[1 * P + 1] = r[L::HFF + 1];
     H[0 * P + 2] = r[L::HFC]; H[1 * P + 3] = r[L::HFC + 1];
@@ -400,7 +403,7 @@ __host__ __device__ inline void lin_unpack(const double* r, double* H, double* g
         g[4 + k] = r[L::GD + k];
     }
     g[0] = r[L::GF]; g[1] = r[L::GF + 1]; g[2] = r[L::GC]; g[3] = r[L::GC + 1];
-    for (int a = 0; a < P; ++a) for (int b = 0; b < a; ++b) H[a * P + b] = H[b * P + a];
+    if (FULL) for (int a = 0; a < P; ++a) for (int b = 0; b < a; ++b) H[a * P + b] = H[b * P + a];
     *cost = 0.5 * r[L::COST];
     *count = cnt;
 }
@@ -422,9 +425,10 @@ template <int M, int KIND> struct LinOps {
         lin_accumulate_masked<ND, E::UNIT_C>(acc, ok, ru, rv, au, av);
     }
     // `x` = the parameter vector the pass was evaluated at (unused here: fx, fy are folded in during the pass)
-    __host__ __device__ static void unpack(const double* r, const double* x, double* H, double* g, double* cost, double* count) {
+    template <bool FULL = true>
+    __host__ __device__ static void unpack(const double* __restrict__ r, const double* __restrict__ x, double* __restrict__ H, double* __restrict__ g, double* __restrict__ cost, double* __restrict__ count) {
         (void)x;
-        lin_unpack<ND, E::UNIT_C>(r, H, g, cost, count);
+        lin_unpack<ND, E::UNIT_C, FULL>(r, H, g, cost, count);
     }
 };
 
@@ -475,9 +479,10 @@ template <> struct LinOps<ACM_MODEL_KANNALA_BRANDT, ACM_RESIDUAL_PIXEL> {
         acc[COST] = fma(ru, ru, fma(rv, rv, acc[COST]));
         acc[COUNT] += ok ? 1.0 : 0.0;
     }
-    __host__ __device__ static void unpack(const double* r, const double* x, double* H, double* g, double* cost, double* count) {
+    template <bool FULL = true>
+    __host__ __device__ static void unpack(const double* __restrict__ r, const double* __restrict__ x, double* __restrict__ H, double* __restrict__ g, double* __restrict__ cost, double* __restrict__ count) {
         (void)x;
-        for (int i = 0; i < P * P; ++i) H[i] = 0.0;
+        if (FULL) for (int i = 0; i < P * P; ++i) H[i] = 0.0;
         const double cnt = r[COUNT];
         H[0 * P + 0] = r[HFF]; H[1 * P + 1] = r[HFF + 1];
         H[0 * P + 2] = r[HFC]; H[1 * P + 3] = r[HFC + 1];
@@ -489,7 +494,7 @@ template <> struct LinOps<ACM_MODEL_KANNALA_BRANDT, ACM_RESIDUAL_PIXEL> {
             g[4 + k] = r[GD + k];
         }
         g[0] = r[GF]; g[1] = r[GF + 1]; g[2] = r[GC]; g[3] = r[GC + 1];
-        for (int a = 0; a < P; ++a) for (int b = 0; b < a; ++b) H[a * P + b] = H[b * P + a];
+        if (FULL) for (int a = 0; a < P; ++a) for (int b = 0; b < a; ++b) H[a * P + b] = H[b * P + a];
         *cost = 0.5 * r[COST];
         *count = cnt;
     }
@@ -561,10 +566,11 @@ template <> struct LinOps<ACM_MODEL_RADTAN, ACM_RESIDUAL_PIXEL> {
         acc[COUNT] += ok ? 1.0 : 0.0;
     }
     // parameter index of k1, k2, p1, p2, k3 = 4, 5, 6, 7, 8; radial power i = 1, 2, 3 <-> k1, k2, k3
-    __host__ __device__ static void unpack(const double* r, const double* x, double* H, double* g, double* cost, double* count) {
+    template <bool FULL = true>
+    __host__ __device__ static void unpack(const double* __restrict__ r, const double* __restrict__ x, double* __restrict__ H, double* __restrict__ g, double* __restrict__ cost, double* __restrict__ count) {
         const double fx = x[0], fy = x[1];
         const int KI[3] = {4, 5, 8};
-        for (int i = 0; i < P * P; ++i) H[i] = 0.0;
+        if (FULL) for (int i = 0; i < P * P; ++i) H[i] = 0.0;
         const double cnt = r[COUNT];
         H[0 * P + 0] = r[HFF]; H[1 * P + 1] = r[HFF + 1];
         H[0 * P + 2] = r[HFC]; H[1 * P + 3] = r[HFC + 1];
@@ -590,7 +596,7 @@ template <> struct LinOps<ACM_MODEL_RADTAN, ACM_RESIDUAL_PIXEL> {
         H[6 * P + 7] = 2.0 * fx * fx * r[PP + 3] + 2.0 * fy * fy * r[PP + 4];
         H[7 * P + 7] = fx * fx * r[PP + 1] + 4.0 * fy * fy * r[PP + 0];
         g[0] = r[GF]; g[1] = r[GF + 1]; g[2] = r[GC]; g[3] = r[GC + 1];
-        for (int a = 0; a < P; ++a) for (int b = 0; b < a; ++b) H[a * P + b] = H[b * P + a];
+        if (FULL) for (int a = 0; a < P; ++a) for (int b = 0; b < a; ++b) H[a * P + b] = H[b * P + a];
         *cost = 0.5 * r[COST];
         *count = cnt;
     }

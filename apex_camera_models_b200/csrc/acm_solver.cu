@@ -50,9 +50,8 @@ static_assert(sizeof(LmState) % sizeof(double) == 0, "LmState is copied as doubl
 // cycles and the first version spent most of its 12 us on ~50 of them.
 // ---------------------------------------------------------------------------------------
 struct LmWork {
-    double Ht[ACM_MAX_PARAMS * ACM_MAX_PARAMS], A[ACM_MAX_PARAMS * ACM_MAX_PARAMS], L[ACM_MAX_PARAMS * ACM_MAX_PARAMS];
-    double gt[ACM_MAX_PARAMS], invD[ACM_MAX_PARAMS], gs[ACM_MAX_PARAMS], st[ACM_MAX_PARAMS], dx[ACM_MAX_PARAMS], yv[ACM_MAX_PARAMS],
-        invdiag[ACM_MAX_PARAMS];
+    double Ht[ACM_MAX_PARAMS * ACM_MAX_PARAMS], A[ACM_MAX_PARAMS * ACM_MAX_PARAMS];
+    double gt[ACM_MAX_PARAMS], invD[ACM_MAX_PARAMS], gs[ACM_MAX_PARAMS], st[ACM_MAX_PARAMS];
     double red[64];
 };
 
@@ -140,91 +139,132 @@ __device__ __forceinline__ bool lm_decide(int P, LmState* s, const LmWork* w, do
     return false;
 }
 
+// 1 / sqrt of a diagonal entry of H (Jacobi scaling); degenerate entries scale by 1
+__device__ __forceinline__ double lm_inv_sqrt_diag(double h) {
+    if (h > 1e-280 && h < 1e280) return acm_rsqrt(h);
+    const double d = sqrt(h);
+    return (d > 1e-300) ? 1.0 / d : 1.0;
+}
+
 // Cooperative step on a state that already sits in shared memory (`sh`), with the reduced sums of
-// the pass in w->red (the pass ran at the trial point sh->xt).  Thread 0 decides and factors, the
-// element-wise parts (copies, scaled matrix, trial point, quadratic-model rows) are spread over the
-// first 81 threads.  The arithmetic of every scalar is the same as in the serial reference
-// (oracle/acm_oracle_solver.c), including the order of the few sums, so both walk the same
-// trajectory.  Every thread of the block must call it (barriers inside); on return the state is
-// consistent and visible to the whole block.
+// the pass in w->red (the pass ran at the trial point sh->xt).  The arithmetic of every scalar is
+// the same as in the serial reference (oracle/acm_oracle_solver.c), including the order of the few
+// sums, so both walk the same trajectory.  Every thread of the block must call it (barriers
+// inside); on return the state is consistent and visible to the whole block.
+//
+// Four barriers on the common path (round 1 took ten, and 5.4 k of the ~15 k fixed cycles of a pass):
+//   thread 0     unpack (upper triangle only; w->Ht's other entries stay zero from the kernel start), decide, count the iteration
+//   -- barrier --
+//   P*P threads  accepted state <- trial state (mirroring the triangle), scaled damped matrix straight from the source
+//                (every thread takes the rsqrt of the two diagonal entries it needs itself)
+//   -- barrier --
+//   thread 0     Cholesky solve (retry loop with a larger lambda: rare)
+//   -- barrier --
+//   warp 0       trial point, quadratic model, norms: lane i owns parameter i, values move by shuffle
+//   -- barrier --
 template <int M, int KIND>
-__device__ __forceinline__ void lm_step_smem(LmState* sh, LmWork* w, int tid) {
+__device__ __forceinline__ void lm_step_smem(LmState* sh, LmWork* w, int tid, long long* stamps = nullptr) {
     constexpr int P = LinOps<M, KIND>::P;
-    __shared__ int flag_accept, flag_ok;
+    __shared__ int flag_accept, flag_go;
     __shared__ double s_cost_t, s_cnt;
     if (sh->done) return;  // uniform: shared state, read after the caller's barrier
     if (tid == 0) {
         double cost_t, cnt;
-        LinOps<M, KIND>::unpack(w->red, sh->xt, w->Ht, w->gt, &cost_t, &cnt);
+        if (stamps) stamps[0] = clock64();
+        LinOps<M, KIND>::template unpack<false>(w->red, sh->xt, w->Ht, w->gt, &cost_t, &cnt);
         s_cost_t = cost_t; s_cnt = cnt;
+        if (stamps) stamps[1] = clock64();
         flag_accept = lm_decide(P, sh, w, cost_t) ? 1 : 0;
+        if (stamps) stamps[2] = clock64();
+        int go = 0;   // 1: solve for the next trial point, -1 / 0: the solve is over
+        if (!sh->done) {
+            if (sh->iterations >= sh->max_iter) { sh->status = 3; sh->done = 1; go = -1; }
+            else { sh->iterations++; go = 1; }
+        }
+        flag_go = go;
     }
     __syncthreads();
-    if (flag_accept) {
-        if (tid < P) { sh->x[tid] = sh->xt[tid]; sh->g[tid] = w->gt[tid]; }
-        if (tid < P * P) sh->H[tid] = w->Ht[tid];
-        if (tid == 0) { sh->cost = s_cost_t; sh->n_valid = s_cnt; }
+    const int accept = flag_accept;
+    int go = flag_go;   // thread 0 rewrites the flag only behind the next barrier
+    {
+        // the source of (H, g) at the accepted point: the trial sums when the trial point was accepted, else the kept state
+        const double* const Hs = accept ? w->Ht : sh->H;
+        if (tid < P * P) {
+            const int i = tid / P, j = tid - i * P;
+            const double h = Hs[accept ? (i <= j ? tid : j * P + i) : tid];
+            if (go > 0) {
+                double a = h * lm_inv_sqrt_diag(Hs[i * P + i]) * lm_inv_sqrt_diag(Hs[j * P + j]);
+                if (i == j) a += sh->lambda;
+                w->A[tid] = a;
+            }
+            if (accept) sh->H[tid] = h;   // nobody reads sh->H in this phase when accept is set
+        }
+        if (tid < P) {
+            const double g = accept ? w->gt[tid] : sh->g[tid];
+            if (go > 0) {
+                const double d = lm_inv_sqrt_diag(Hs[tid * P + tid]);
+                w->invD[tid] = d;
+                w->gs[tid] = -g * d;
+            }
+            if (accept) { sh->x[tid] = sh->xt[tid]; sh->g[tid] = g; }
+        }
+        if (accept && tid == 0) { sh->cost = s_cost_t; sh->n_valid = s_cnt; }
     }
     __syncthreads();
-    if (!sh->done) {
-        // next trial point from (H, g, lambda) at the accepted x
-        int ok;
+    if (stamps && tid == 0) stamps[3] = clock64();
+    if (go > 0) {
         for (;;) {
             if (tid == 0) {
-                flag_ok = 1;
-                if (sh->iterations >= sh->max_iter) { sh->status = 3; sh->done = 1; flag_ok = -1; }
-                else sh->iterations++;
-            }
-            if (tid < P) {
-                const double h = sh->H[tid * P + tid];
-                if (h > 1e-280 && h < 1e280) w->invD[tid] = acm_rsqrt(h);
-                else { const double d = sqrt(h); w->invD[tid] = (d > 1e-300) ? 1.0 / d : 1.0; }
+                int r = 1;
+                if (!chol_solve_work<P>(w)) {
+                    sh->lambda *= sh->nu; sh->nu *= 2.0;
+                    r = 0;
+                    if (sh->lambda > 1e30) { sh->status = 4; sh->done = 1; r = -1; }
+                    else if (sh->iterations >= sh->max_iter) { sh->status = 3; sh->done = 1; r = -1; }
+                    else sh->iterations++;
+                }
+                flag_go = r;
+                if (stamps) stamps[4] = clock64();
             }
             __syncthreads();
-            ok = flag_ok;
-            if (ok < 0) break;  // uniform; thread 0 does not touch the flag again on this path
+            go = flag_go;
+            if (go != 0) break;
+            // retry with the larger damping (rare: rank-deficient normal equations)
             if (tid < P * P) {
                 const int i = tid / P, j = tid - i * P;
                 double a = sh->H[tid] * w->invD[i] * w->invD[j];
                 if (i == j) a += sh->lambda;
                 w->A[tid] = a;
             }
-            if (tid < P) w->gs[tid] = -sh->g[tid] * w->invD[tid];
-            __syncthreads();
-            if (tid == 0) {
-                if (!chol_solve_work<P>(w)) {
-                    sh->lambda *= sh->nu; sh->nu *= 2.0;
-                    flag_ok = 0;
-                    if (sh->lambda > 1e30) { sh->status = 4; sh->done = 1; flag_ok = -1; }
-                }
-            }
-            __syncthreads();
-            ok = flag_ok;      // register copy taken between two barriers ...
-            __syncthreads();   // ... so nobody re-arms the flag at the loop top before everybody has read it
-            if (ok != 0) break;
+            __syncthreads();   // also: everybody has read the flag before thread 0 writes it again
         }
-        if (ok > 0) {
+        if (go > 0 && tid < 32) {
+            double x_i = 0.0, dx_i = 0.0, g_i = 0.0;
             if (tid < P) {
-                sh->xt[tid] = clampd(sh->x[tid] + w->st[tid] * w->invD[tid], sh->lower[tid], sh->upper[tid]);
-                w->dx[tid] = sh->xt[tid] - sh->x[tid];
+                x_i = sh->x[tid]; g_i = sh->g[tid];
+                const double xt = clampd(x_i + w->st[tid] * w->invD[tid], sh->lower[tid], sh->upper[tid]);
+                sh->xt[tid] = xt;
+                dx_i = xt - x_i;
             }
-            __syncthreads();
-            if (tid < P) {
-                double hd = 0.0;
-#pragma unroll 1
-                for (int j = 0; j < P; ++j) hd += sh->H[tid * P + j] * w->dx[j];
-                w->yv[tid] = w->dx[tid] * (sh->g[tid] + 0.5 * hd);   // row of the quadratic model
+            double hd = 0.0;
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                const double dx_j = __shfl_sync(0xffffffffu, dx_i, j);
+                if (tid < P) hd += sh->H[tid * P + j] * dx_j;
             }
-            __syncthreads();
-            if (tid == 0) {
-                double xnorm = 0.0, dnorm = 0.0, pred = 0.0;
-#pragma unroll 1
-                for (int i = 0; i < P; ++i) { xnorm += sh->x[i] * sh->x[i]; dnorm += w->dx[i] * w->dx[i]; pred -= w->yv[i]; }
-                sh->xnorm = sqrt(xnorm); sh->dnorm = sqrt(dnorm); sh->pred = pred;
+            const double yv_i = dx_i * (g_i + 0.5 * hd);   // row of the quadratic model
+            double xnorm = 0.0, dnorm = 0.0, pred = 0.0;
+#pragma unroll
+            for (int i = 0; i < P; ++i) {
+                const double xs = __shfl_sync(0xffffffffu, x_i, i), ds = __shfl_sync(0xffffffffu, dx_i, i), ys = __shfl_sync(0xffffffffu, yv_i, i);
+                xnorm += xs * xs; dnorm += ds * ds; pred -= ys;
             }
+            if (tid == 0) { sh->xnorm = sqrt(xnorm); sh->pred = pred; }
+            if (tid == 1) sh->dnorm = sqrt(dnorm);
         }
     }
     __syncthreads();
+    if (stamps && tid == 0) stamps[5] = clock64();
 }
 
 // Stand-alone step kernel: used when an NCCL all-reduce sits between the pass and the step (ranks
@@ -238,6 +278,7 @@ __global__ void __launch_bounds__(128) lm_step_kernel(LmState* __restrict__ s, c
     const double* gw = reinterpret_cast<const double*>(s);
     for (int i = threadIdx.x; i < NW; i += blockDim.x) shw[i] = __ldcg(gw + i);
     for (int i = threadIdx.x; i < LinOps<M, KIND>::NACC; i += blockDim.x) work.red[i] = __ldcg(red + i);
+    for (int i = threadIdx.x; i < ACM_MAX_PARAMS * ACM_MAX_PARAMS; i += blockDim.x) work.Ht[i] = 0.0;   // the step fills the non-zero upper triangle only
     __syncthreads();
     if (sh.done) return;
     lm_step_smem<M, KIND>(&sh, &work, threadIdx.x);
@@ -391,6 +432,25 @@ template <int M> struct LinStream : LinStreamDefault<M> {};
 template <> struct LinStream<ACM_EXP_MODEL> { static constexpr int DEPTH = ACM_EXP_DEPTH, BLOCK = ACM_EXP_BLOCK, MIN_BLOCKS = ACM_EXP_MINB, PTS = ACM_EXP_PTS; };
 #endif
 
+// The solve form of the kernel (128-thread blocks) has its own ring depth / points per trip / register cap: it carries the trial
+// parameters in registers (the one-pass form reads them from the constant bank) and peaks at 152-168 registers outside the
+// streaming loop.  Default: three blocks per SM (<= 170 registers, no spill); the wide models (KB, RadTan) are left uncapped.
+// Same-box A/B of two uncapped blocks per SM against three capped ones (profiles/r02_ab_lm_stream*.log, us per pass at
+// 1.25 M / 10 M correspondences): Double Sphere 15.1 -> 13.9 / 67.7 -> 66.4 (taken); EUCM 13.7 -> 12.7 / 63.4 -> 64.3 and UCM
+// 11.4 -> 10.4 / 62.2 -> 70.3 (better from L2, worse from HBM: kept at three); FOV worse at both.  Four points per trip fit
+// 166 registers for Double Sphere but gain nothing (15.2 / 70.0).
+// -DACM_EXP_SOLVE_MODEL=<id> -DACM_EXP_SOLVE_DEPTH= -DACM_EXP_SOLVE_PTS= -DACM_EXP_SOLVE_MINB= overrides one model.
+template <int M> struct SolveStreamDefault {
+    static constexpr int DEPTH = LinStream<M>::DEPTH, PTS = LinStream<M>::PTS;
+    static constexpr int MIN_BLOCKS = (M == ACM_MODEL_KANNALA_BRANDT || M == ACM_MODEL_RADTAN) ? 0 : (M == ACM_MODEL_DOUBLE_SPHERE ? 2 : 3);
+};
+template <int M> struct SolveStream : SolveStreamDefault<M> {};
+#ifdef ACM_EXP_SOLVE_MODEL
+template <> struct SolveStream<ACM_EXP_SOLVE_MODEL> { static constexpr int DEPTH = ACM_EXP_SOLVE_DEPTH, PTS = ACM_EXP_SOLVE_PTS, MIN_BLOCKS = ACM_EXP_SOLVE_MINB; };
+#endif
+template <int M, bool SOLVE> struct StreamCfg { static constexpr int DEPTH = LinStream<M>::DEPTH, PTS = LinStream<M>::PTS; };
+template <int M> struct StreamCfg<M, true> { static constexpr int DEPTH = SolveStream<M>::DEPTH, PTS = SolveStream<M>::PTS; };
+
 struct LinKernelArgs {
     LinParams hp;                 // parameters of a single evaluation (mode 0)
     LmState* lm;                  // device-resident LM state (modes 1, 2)
@@ -405,17 +465,18 @@ struct LinKernelArgs {
     unsigned long long tag0;      // first hand-off tag of this launch (mode 2 uses tag0 + pass)
     double* out;                  // [NACC] totals (modes 0, 1)
     long long* trace;             // debug (ACM_LM_TRACE=1): clock64 stamps of block 0, 6 per pass
+    int trace_pass;               // debug (ACM_LM_TRACE=2): >= 0 = every block stamps %globaltimer at the start, after the stream and at the end of this pass
 };
 
 // One streaming pass of this block over its grid-stride share + the block partial (fixed shuffle tree, then the
 // warps in order) handed to the reducer warps as tagged cells.
 // PRIMED: the first DEPTH packets of this pass are already in flight (issued while the previous pass's sums travelled).
-template <int M, int KIND, int BS>
+template <int M, int KIND, int BS, bool SOLVE>
 __device__ __forceinline__ void lin_stream_pass(const LinKernelArgs& a, const LinParams& p_in, unsigned long long tag, bool primed, bool prime_next) {
     using LM_ = LinOps<M, KIND>;
     constexpr int NACC = LM_::NACC;
     constexpr int NWARP = BS / 32;
-    constexpr int DEPTH = LinStream<M>::DEPTH;
+    constexpr int DEPTH = StreamCfg<M, SOLVE>::DEPTH;
     __shared__ double wsum[NWARP][NACC];
     extern __shared__ double2 lin_ring[];
     LinParams p = p_in;
@@ -457,7 +518,7 @@ __device__ __forceinline__ void lin_stream_pass(const LinKernelArgs& a, const Li
 #pragma unroll
     for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
     size_t i = i0;
-    if constexpr (DEPTH > 0 && LinStream<M>::PTS == 4) {
+    if constexpr (DEPTH > 0 && StreamCfg<M, SOLVE>::PTS == 4) {
         // two packets (four points) per trip: the four evaluation chains are independent, the points still enter every
         // accumulator in the same order as in the two-point form, so the sums are bit-identical
         static_assert(DEPTH % 2 == 0, "PTS = 4 consumes the ring two stages at a time");
@@ -606,26 +667,49 @@ __device__ __forceinline__ bool lin_pass(const LinKernelArgs& a, LmState* sh, Lm
     }
     const bool tr = SOLVE && a.trace != nullptr && blockIdx.x == 0 && tid == 0;
     if (tr) a.trace[6 * pass + 0] = clock64();
-    lin_stream_pass<M, KIND, BS>(a, p, tag, SOLVE && pass > 0, SOLVE);
+    const bool trb = SOLVE && a.trace != nullptr && pass == a.trace_pass && tid == 0;
+    if (trb) a.trace[12 * a.max_passes + 3 * (int)blockIdx.x + 0] = (long long)acm_globaltimer();
+    lin_stream_pass<M, KIND, BS, SOLVE>(a, p, tag, SOLVE && pass > 0, SOLVE);
     if (tr) a.trace[6 * pass + 2] = clock64();
+    if (trb) a.trace[12 * a.max_passes + 3 * (int)blockIdx.x + 1] = (long long)acm_globaltimer();
 
-    // ---- reducer warps: sum j belongs to warp (j / nb) % NWARP of block j % nb
     const bool solve_peers = SOLVE && a.peer.bufs != nullptr;
     bool bad = false;
+    if (SOLVE) {
+        // ---- reducer blocks (solve): sum j belongs to block j % nb, whose warps split the nb cells between them so that
+        // every lane polls at most 4 cells in ONE trip (444 blocks: two dependent L2 round trips with a single warp per sum);
+        // the warp totals are added in warp order.  The host keeps nb >= NACC for the solve, so the loop runs once.
+        __shared__ double wsum[NWARP];
+        const int chunk = (nb + NWARP - 1) / NWARP;
 #pragma unroll 1
-    for (int slot = (int)blockIdx.x + nb * warp; slot < NACC; slot += nb * NWARP) {
-        double tot = warp_sum_cells<8>(a.partials + (size_t)slot * nb, nb, lane, tag, bad);
-        if (bad) tot = acm_qnan();
-        if (solve_peers) {
-            // multi-GPU solve: the rank's total goes straight into every rank's exchange buffer; the blocks of every GPU
-            // collect from there (one hop less than exchanging here and re-broadcasting)
-            if (lane < a.peer.n_ranks) ll_store(peer_cell(a.peer.bufs[lane], (int)(seq & 1ULL), a.peer.rank, slot), tot, seq);
-        } else {
-            if (a.peer.bufs && !bad) tot = warp_peer_exchange(a.peer, seq, slot, tot, lane, bad);
-            if (lane == 0) {
-                if (SOLVE) ll_store(a.bcast + slot, tot, tag);
-                else a.out[slot] = tot;
+        for (int slot = (int)blockIdx.x; slot < NACC; slot += nb) {
+            const int c0 = warp * chunk, len = max(0, min(chunk, nb - c0));
+            const double part = warp_sum_cells<4>(a.partials + (size_t)slot * nb + c0, len, lane, tag, bad);
+            if (lane == 0) wsum[warp] = part;
+            bad = __syncthreads_or(bad) != 0;
+            if (warp == 0) {
+                double tot = wsum[0];
+#pragma unroll
+                for (int k = 1; k < NWARP; ++k) tot += wsum[k];
+                if (bad) tot = acm_qnan();
+                if (solve_peers) {
+                    // multi-GPU solve: the rank's total goes straight into every rank's exchange buffer; the blocks of every GPU
+                    // collect from there (one hop less than exchanging here and re-broadcasting)
+                    if (lane < a.peer.n_ranks) ll_store(peer_cell(a.peer.bufs[lane], (int)(seq & 1ULL), a.peer.rank, slot), tot, seq);
+                } else if (lane == 0) {
+                    ll_store(a.bcast + slot, tot, tag);
+                }
             }
+            if (slot + nb < NACC) __syncthreads();   // wsum is reused (block-uniform condition)
+        }
+    } else {
+        // ---- reducer warps (one pass): sum j belongs to warp (j / nb) % NWARP of block j % nb
+#pragma unroll 1
+        for (int slot = (int)blockIdx.x + nb * warp; slot < NACC; slot += nb * NWARP) {
+            double tot = warp_sum_cells<8>(a.partials + (size_t)slot * nb, nb, lane, tag, bad);
+            if (bad) tot = acm_qnan();
+            if (a.peer.bufs && !bad) tot = warp_peer_exchange(a.peer, seq, slot, tot, lane, bad);
+            if (lane == 0) a.out[slot] = tot;
         }
     }
     if (!SOLVE) return false;
@@ -682,19 +766,15 @@ __device__ __forceinline__ bool lin_pass(const LinKernelArgs& a, LmState* sh, Lm
         if (tid == 0) { sh->passes++; sh->status = 4; sh->done = 1; }
         __syncthreads();
     } else {
-        lm_step_smem<M, KIND>(sh, work, tid);
+        lm_step_smem<M, KIND>(sh, work, tid, (a.trace != nullptr && blockIdx.x == 0) ? a.trace + 6 * a.max_passes + 6 * pass : nullptr);
     }
     if (tr) a.trace[6 * pass + 5] = clock64();
+    if (trb) a.trace[12 * a.max_passes + 3 * (int)blockIdx.x + 2] = (long long)acm_globaltimer();
     return true;
 }
 
-// Launch bounds: the one-pass form keeps the per-model tuning of LinStream.  The solve form carries the trial
-// parameters in registers (the one-pass form reads them from the constant bank) and peaks at 152-168 registers
-// outside the streaming loop; it runs in 128-thread blocks, three per SM (<= 170 registers, no spill), except for the
-// wide models (KB, RadTan), which are left uncapped.
-template <int M> struct SolveBounds { static constexpr int MIN_BLOCKS = (M == ACM_MODEL_KANNALA_BRANDT || M == ACM_MODEL_RADTAN) ? 0 : 3; };
 template <int M, int KIND, int BS, bool SOLVE>
-__global__ void __launch_bounds__(BS, (SOLVE ? (BS == 128 ? SolveBounds<M>::MIN_BLOCKS : 0) : (BS == LinStream<M>::BLOCK ? LinStream<M>::MIN_BLOCKS : 0))) lin_kernel(const __grid_constant__ LinKernelArgs a) {
+__global__ void __launch_bounds__(BS, (SOLVE ? (BS == 128 ? SolveStream<M>::MIN_BLOCKS : 0) : (BS == LinStream<M>::BLOCK ? LinStream<M>::MIN_BLOCKS : 0))) lin_kernel(const __grid_constant__ LinKernelArgs a) {
     static_assert(LinOps<M, KIND>::NACC <= 64, "hand-off layout assumes <= 64 accumulators");
     constexpr int NSTATE = sizeof(LmState) / sizeof(double);
     __shared__ LmState sh;
@@ -707,11 +787,12 @@ __global__ void __launch_bounds__(BS, (SOLVE ? (BS == 128 ? SolveBounds<M>::MIN_
     double* shw = reinterpret_cast<double*>(&sh);
     const double* gw = reinterpret_cast<const double*>(a.lm);
     for (int i = tid; i < NSTATE; i += BS) shw[i] = __ldcg(gw + i);
+    for (int i = tid; i < ACM_MAX_PARAMS * ACM_MAX_PARAMS; i += BS) work.Ht[i] = 0.0;   // the step fills the non-zero upper triangle only
     __syncthreads();
     if (blockIdx.x == 0 && tid == 0) sh.t_begin_ns = (long long)acm_globaltimer();
 #pragma unroll 1
     for (int pass = 0; lin_pass<M, KIND, BS, SOLVE>(a, &sh, &work, pass); ++pass) {}
-    if constexpr (LinStream<M>::DEPTH > 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if constexpr (StreamCfg<M, SOLVE>::DEPTH > 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (blockIdx.x == 0) {
         __syncthreads();
         if (tid == 0) {
@@ -744,13 +825,16 @@ static int32_t ensure_ll(acm_ctx* ctx, size_t blocks) {
 
 template <int M, int KIND, int BS>
 static int32_t launch_lin_bs(acm_ctx* ctx, LinKernelArgs& a, const acm_points* xyz, const acm_points* uv) {
-    constexpr size_t ring_bytes = (size_t)LinStream<M>::DEPTH * 5 * BS * sizeof(double2);
+    const size_t ring_bytes = (size_t)(a.mode == 2 ? StreamCfg<M, true>::DEPTH : StreamCfg<M, false>::DEPTH) * 5 * BS * sizeof(double2);
     const void* fn = a.mode == 2 ? reinterpret_cast<const void*>(&lin_kernel<M, KIND, BS, true>) : reinterpret_cast<const void*>(&lin_kernel<M, KIND, BS, false>);
     int bps = 0;
     int32_t rc = acm_kernel_blocks_per_sm(ctx, fn, BS, ring_bytes, &bps);
     if (rc) return rc;
     const size_t n = xyz->n;
-    const int grid = grid_for(ctx, (n >> 1) + 1, BS, bps);
+    int grid = grid_for(ctx, (n >> 1) + 1, BS, bps);
+    // the solve gives every sum its own reducer block (a few hundred correspondences would otherwise queue all sums on the
+    // warps of one or two blocks: 6.4 k of the 15 k cycles of a pass at n = 450); blocks without points contribute zeros
+    if (a.mode == 2 && grid < LinOps<M, KIND>::NACC) grid = LinOps<M, KIND>::NACC;
     rc = ensure_ll(ctx, (size_t)ctx->sm_count * 16);
     if (rc) return rc;
     ACM_REQUIRE(ctx, (size_t)grid <= (size_t)ctx->sm_count * 16, "linearize: grid larger than the hand-off buffer");
@@ -999,11 +1083,14 @@ extern "C" int32_t acm_lm_solve(acm_ctx* ctx, const acm_camera* init, int32_t re
             a.peer.seq = ctx->peer_seq + 1;
         }
         const bool want_trace = getenv("ACM_LM_TRACE") != nullptr;   // debug: per-phase clock64 stamps of block 0 -> stderr
+        const size_t trace_words = (size_t)max_passes * 12 + (size_t)ctx->sm_count * 16 * 3;
+        a.trace_pass = -1;
         if (want_trace) {
-            rc = acm_ensure_scratch(ctx, (size_t)max_passes * 6 * sizeof(long long));
+            rc = acm_ensure_scratch(ctx, trace_words * sizeof(long long));
             if (rc) return rc;
-            ACM_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, (size_t)max_passes * 6 * sizeof(long long), ctx->stream));
+            ACM_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, trace_words * sizeof(long long), ctx->stream));
             a.trace = static_cast<long long*>(ctx->d_scratch);
+            if (atoi(getenv("ACM_LM_TRACE")) >= 2) a.trace_pass = getenv("ACM_LM_TRACE_PASS") ? atoi(getenv("ACM_LM_TRACE_PASS")) : 3;
         }
         ACM_DISPATCH_LIN(init->model, residual_kind, {
             rc = launch_lin<M, KIND>(ctx, a, xyz, uv);
@@ -1012,12 +1099,26 @@ extern "C" int32_t acm_lm_solve(acm_ctx* ctx, const acm_camera* init, int32_t re
         ACM_CUDA(ctx, cudaMemcpyAsync(h, d, sizeof(LmState), cudaMemcpyDeviceToHost, ctx->stream));
         ACM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (want_trace) {
-            std::vector<long long> t((size_t)max_passes * 6);
+            std::vector<long long> t(trace_words);
             ACM_CUDA(ctx, cudaMemcpy(t.data(), a.trace, t.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+            if (a.trace_pass >= 0) {
+                // per-block skew of one pass: offsets (ns) from the earliest block's start
+                const long long* q = &t[(size_t)max_passes * 12];
+                long long t_min = 0;
+                int nbk = 0;
+                for (int b = 0; b < ctx->sm_count * 16 && q[3 * b]; ++b) { t_min = (b == 0 || q[3 * b] < t_min) ? q[3 * b] : t_min; nbk = b + 1; }
+                for (int b = 0; b < nbk; ++b)
+                    fprintf(stderr, "[acm lm skew] rank %d pass %d block %3d ns: start %lld  stream-end %lld  pass-end %lld\n", ctx->peer_rank, a.trace_pass, b,
+                            q[3 * b] - t_min, q[3 * b + 1] - t_min, q[3 * b + 2] - t_min);
+            }
             for (int k = 0; k < h->passes && k < max_passes; ++k) {
                 const long long* q = &t[6 * k];
                 fprintf(stderr, "[acm lm trace] rank %d pass %2d cycles: stream %lld  block-reduce %lld  reducers %lld  collect %lld  step %lld  | total %lld\n",
                         ctx->peer_rank, k, q[1] - q[0], q[2] - q[1], q[3] - q[2], q[4] - q[3], q[5] - q[4], q[5] - q[0]);
+                const long long* u = &t[6 * (size_t)max_passes + 6 * k];
+                if (u[0] && u[5])
+                    fprintf(stderr, "[acm lm trace]          step cycles: unpack %lld  decide %lld  scale %lld  solve %lld  trial point %lld\n",
+                            u[1] - u[0], u[2] - u[1], u[3] - u[2], u[4] - u[3], u[5] - u[4]);
             }
         }
         if (use_peer) ctx->peer_seq += (unsigned long long)h->passes;   // one exchange per executed pass, the same count on every rank
