@@ -106,8 +106,13 @@ __device__ __forceinline__ bool chol_solve_work(LmWork* w) {
 __device__ inline double clampd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 // Decision part of the step (thread 0): accept / reject the trial point, update the damping,
-// test convergence.  Returns true when the trial point was accepted.
-__device__ __forceinline__ bool lm_decide(int P, LmState* s, const LmWork* w, double cost_t) {
+// test convergence.  Returns true when the trial point was accepted.  The gradient maximum is taken up front (P independent
+// loads) so that it overlaps the division behind it: a dependent f64 operation costs ~20 cycles here.
+template <int P>
+__device__ __forceinline__ bool lm_decide(LmState* s, const LmWork* w, double cost_t) {
+    double gmax = 0.0;
+#pragma unroll
+    for (int i = 0; i < P; ++i) gmax = fmax(gmax, fabs(w->gt[i]));
     s->passes++;
     if (!(cost_t == cost_t)) { s->status = 4; s->done = 1; return false; }  // NaN sums (NaN observations): stop
     if (s->first) {
@@ -123,9 +128,6 @@ __device__ __forceinline__ bool lm_decide(int P, LmState* s, const LmWork* w, do
         s->lambda *= (f > 1.0 / 3.0) ? f : 1.0 / 3.0;
         s->nu = 2.0;
         if (s->lambda < 1e-15) s->lambda = 1e-15;
-        double gmax = 0.0;
-#pragma unroll 1
-        for (int i = 0; i < P; ++i) gmax = fmax(gmax, fabs(w->gt[i]));
         if (dcost <= s->cost_tol * cost_old) { s->status = 0; s->done = 1; }
         else if (small_step) { s->status = 1; s->done = 1; }
         else if (gmax <= s->grad_tol) { s->status = 2; s->done = 1; }
@@ -140,10 +142,15 @@ __device__ __forceinline__ bool lm_decide(int P, LmState* s, const LmWork* w, do
 }
 
 // 1 / sqrt of a diagonal entry of H (Jacobi scaling); degenerate entries scale by 1
+// (the fast value is computed unconditionally -- garbage outside its range, replaced behind a rarely taken branch -- so that
+// two calls interleave instead of queueing behind each other's branches)
 __device__ __forceinline__ double lm_inv_sqrt_diag(double h) {
-    if (h > 1e-280 && h < 1e280) return acm_rsqrt(h);
-    const double d = sqrt(h);
-    return (d > 1e-300) ? 1.0 / d : 1.0;
+    double r = acm_rsqrt(h);
+    if (!(h > 1e-280 && h < 1e280)) {
+        const double d = sqrt(h);
+        r = (d > 1e-300) ? 1.0 / d : 1.0;
+    }
+    return r;
 }
 
 // Cooperative step on a state that already sits in shared memory (`sh`), with the reduced sums of
@@ -174,7 +181,7 @@ __device__ __forceinline__ void lm_step_smem(LmState* sh, LmWork* w, int tid, lo
         LinOps<M, KIND>::template unpack<false>(w->red, sh->xt, w->Ht, w->gt, &cost_t, &cnt);
         s_cost_t = cost_t; s_cnt = cnt;
         if (stamps) stamps[1] = clock64();
-        flag_accept = lm_decide(P, sh, w, cost_t) ? 1 : 0;
+        flag_accept = lm_decide<P>(sh, w, cost_t) ? 1 : 0;
         if (stamps) stamps[2] = clock64();
         int go = 0;   // 1: solve for the next trial point, -1 / 0: the solve is over
         if (!sh->done) {
@@ -192,21 +199,21 @@ __device__ __forceinline__ void lm_step_smem(LmState* sh, LmWork* w, int tid, lo
         if (tid < P * P) {
             const int i = tid / P, j = tid - i * P;
             const double h = Hs[accept ? (i <= j ? tid : j * P + i) : tid];
+            double dj = 0.0;
             if (go > 0) {
-                double a = h * lm_inv_sqrt_diag(Hs[i * P + i]) * lm_inv_sqrt_diag(Hs[j * P + j]);
+                // thread 0 (which factors next) takes one rsqrt, the others two independent ones
+                dj = lm_inv_sqrt_diag(Hs[j * P + j]);
+                const double di = (i == j) ? dj : lm_inv_sqrt_diag(Hs[i * P + i]);
+                double a = h * di * dj;
                 if (i == j) a += sh->lambda;
                 w->A[tid] = a;
             }
             if (accept) sh->H[tid] = h;   // nobody reads sh->H in this phase when accept is set
-        }
-        if (tid < P) {
-            const double g = accept ? w->gt[tid] : sh->g[tid];
-            if (go > 0) {
-                const double d = lm_inv_sqrt_diag(Hs[tid * P + tid]);
-                w->invD[tid] = d;
-                w->gs[tid] = -g * d;
+            if (tid < P) {   // row 0: j == tid, so dj is this parameter's scale
+                const double g = accept ? w->gt[tid] : sh->g[tid];
+                if (go > 0) { w->invD[tid] = dj; w->gs[tid] = -g * dj; }
+                if (accept) { sh->x[tid] = sh->xt[tid]; sh->g[tid] = g; }
             }
-            if (accept) { sh->x[tid] = sh->xt[tid]; sh->g[tid] = g; }
         }
         if (accept && tid == 0) { sh->cost = s_cost_t; sh->n_valid = s_cnt; }
     }
