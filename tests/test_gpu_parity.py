@@ -801,6 +801,32 @@ def test_lm_config4_ten_million_correspondences_matches_oracle(acm, ctx, O, came
     X.free(); UV.free()
 
 
+@pytest.mark.parametrize("name,kind", [("double_sphere", 1), ("ucm", 0), ("eucm", 0)])
+def test_lm_grid_sizes_take_the_oracle_trajectory(acm, ctx, O, cameras, name, kind):
+    """The solve kernel's grid follows the problem size (never fewer blocks than sums; the reducer blocks split the
+    column of block partials over their warps, unevenly when the grid is not a multiple of the warp count): sizes that
+    give 29..52 (floor), 79, 131 and the resident maximum of blocks must all walk the oracle's trajectory."""
+    kbp = cameras["kannala_brandt"]["params"]
+    truth = oracle_model(O, cameras["kannala_brandt"])
+    for n in (130, 4_099, 20_011, 33_333, 90_001, 123_457):
+        xyz = O.synth_points3(0xACE50010 + n, 0, n, np.cos(np.deg2rad(80.0)), False)
+        uv, st = O.project(truth, xyz)
+        assert np.all(st == 0)
+        cam = {"model_id": cameras[name]["model_id"], "params": list(kbp[:4]) + INITS[name], "width": 512, "height": 512}
+        m, om = gpu_model(acm, ctx, cam), oracle_model(O, cam)
+        m.linear_estimation(xyz, uv)
+        O.linear_estimation(om, xyz, uv)
+        b = acm.CONVERTER_BOUNDS[m.MODEL_ID]
+        lo, hi = [x[0] for x in b], [x[1] for x in b]
+        cost = acm.OptimizationCost(m, xyz, uv, residual_kind=kind)
+        r = cost.optimize()
+        oo, ores = O.lm_solve(om, kind, xyz, uv, lo, hi)
+        assert (r.status, r.iterations, r.passes) == (ores.status, ores.iterations, ores.passes), (name, n)
+        assert r.n_valid == ores.n_valid == n
+        assert np.allclose(r.parameters, oo, rtol=1e-9), (name, n, np.abs(r.parameters - oo) / np.abs(oo))
+        cost.free()
+
+
 def test_lm_anchors_and_readme_figures(acm, ctx, O, cameras):
     """KB -> DS / UCM on the 450 correspondences ends at the survey's anchors (scipy, 1e-15) and at
     the README's 0.008 px / 0.145 px (README.md:163-164)."""
