@@ -7,9 +7,10 @@
 //
 // Per pass: every thread accumulates the normal equations of its grid-stride share in registers
 // (cp.async ring), the block combines them (fixed shuffle tree + fixed warp order) and hands its
-// partial to the *reducer warp* of each sum: sum j is owned by warp 0 of block j (sums wrap around
-// when the grid is smaller), which adds the partials in a fixed order, exchanges the total with the
-// same warp on the other GPUs over NVLink peer memory, and broadcasts the result to every block.
+// partial to the *reducer* of each sum -- one pass: a warp of block j (sums wrap around when the grid is
+// smaller); solve: the whole block j, its warps splitting the column of partials -- which adds the
+// partials in a fixed order, exchanges the total with its twin on the other GPUs over NVLink peer
+// memory (solve: stores it into every GPU's exchange buffer), and broadcasts the result to every block.
 // All three hand-offs travel as "flag-in-data" cells (a double split over two 8-byte words, each
 // carrying half of a 64-bit tag -- 8-byte accesses are single-copy atomic, so a reader that sees
 // the tag sees the data): no fence, no atomic, no barrier, one L2 (or NVLink) trip per hand-off.
@@ -468,7 +469,7 @@ struct LinKernelArgs {
     size_t n;
     double pen2x2;                // 2 * invalid_penalty^2: cost of one invalid point
     LLCell* partials;             // [NACC][gridDim.x] block partials
-    LLCell* bcast;                // [64] totals, reducer warps -> every block (mode 2)
+    LLCell* bcast;                // [64] totals, reducer blocks -> every block (mode 2, single GPU)
     unsigned long long tag0;      // first hand-off tag of this launch (mode 2 uses tag0 + pass)
     double* out;                  // [NACC] totals (modes 0, 1)
     long long* trace;             // debug (ACM_LM_TRACE=1): clock64 stamps of block 0, 6 per pass
@@ -476,7 +477,7 @@ struct LinKernelArgs {
 };
 
 // One streaming pass of this block over its grid-stride share + the block partial (fixed shuffle tree, then the
-// warps in order) handed to the reducer warps as tagged cells.
+// warps in order) handed to the reducers as tagged cells.
 // PRIMED: the first DEPTH packets of this pass are already in flight (issued while the previous pass's sums travelled).
 template <int M, int KIND, int BS, bool SOLVE>
 __device__ __forceinline__ void lin_stream_pass(const LinKernelArgs& a, const LinParams& p_in, unsigned long long tag, bool primed, bool prime_next) {
