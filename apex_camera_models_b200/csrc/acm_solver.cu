@@ -451,10 +451,17 @@ template <> struct LinStream<ACM_EXP_MODEL> { static constexpr int DEPTH = ACM_E
 template <int M> struct SolveStreamDefault {
     static constexpr int DEPTH = LinStream<M>::DEPTH, PTS = LinStream<M>::PTS;
     static constexpr int MIN_BLOCKS = (M == ACM_MODEL_KANNALA_BRANDT || M == ACM_MODEL_RADTAN) ? 0 : (M == ACM_MODEL_DOUBLE_SPHERE ? 2 : 3);
+    // from this many correspondences per GPU on, the solve runs one uncapped 256-thread block per SM instead (half the blocks to
+    // reduce over, same warps): Double Sphere 68.3 -> 66.0 us per pass at 10 M, 37.8 -> 37.2 at 5 M, 22.1 -> 22.3 at 2.5 M, slower at 450; UCM and FOV lose
+    // 10-15 % at 10 M, EUCM gains 0.5 % (profiles/r02_ab_lm_stream2.log, _stream3.log).  0 = never.
+    static constexpr size_t WIDE_BLOCK_FROM = (M == ACM_MODEL_DOUBLE_SPHERE) ? 4000000 : 0;
 };
 template <int M> struct SolveStream : SolveStreamDefault<M> {};
 #ifdef ACM_EXP_SOLVE_MODEL
-template <> struct SolveStream<ACM_EXP_SOLVE_MODEL> { static constexpr int DEPTH = ACM_EXP_SOLVE_DEPTH, PTS = ACM_EXP_SOLVE_PTS, MIN_BLOCKS = ACM_EXP_SOLVE_MINB; };
+template <> struct SolveStream<ACM_EXP_SOLVE_MODEL> {
+    static constexpr int DEPTH = ACM_EXP_SOLVE_DEPTH, PTS = ACM_EXP_SOLVE_PTS, MIN_BLOCKS = ACM_EXP_SOLVE_MINB;
+    static constexpr size_t WIDE_BLOCK_FROM = 0;
+};
 #endif
 template <int M, bool SOLVE> struct StreamCfg { static constexpr int DEPTH = LinStream<M>::DEPTH, PTS = LinStream<M>::PTS; };
 template <int M> struct StreamCfg<M, true> { static constexpr int DEPTH = SolveStream<M>::DEPTH, PTS = SolveStream<M>::PTS; };
@@ -873,7 +880,8 @@ static int32_t launch_lin_bs(acm_ctx* ctx, LinKernelArgs& a, const acm_points* x
 // ACM_LIN_BLOCK=128|256 overrides (tuning aid).
 template <int M, int KIND>
 static int32_t launch_lin(acm_ctx* ctx, LinKernelArgs& a, const acm_points* xyz, const acm_points* uv) {
-    int bs = a.mode == 2 ? 128 : LinStream<M>::BLOCK;
+    int bs = LinStream<M>::BLOCK;
+    if (a.mode == 2) bs = (SolveStream<M>::WIDE_BLOCK_FROM != 0 && xyz->n >= SolveStream<M>::WIDE_BLOCK_FROM) ? 256 : 128;
     const char* e = getenv("ACM_LIN_BLOCK");
     if (e && (atoi(e) == 128 || atoi(e) == 256)) bs = atoi(e);
     if (bs == 128) return launch_lin_bs<M, KIND, 128>(ctx, a, xyz, uv);
