@@ -424,7 +424,7 @@ template <> struct LinStreamDefault<ACM_MODEL_DOUBLE_SPHERE> { static constexpr 
 template <> struct LinStreamDefault<ACM_MODEL_EUCM> { static constexpr int DEPTH = 3, BLOCK = 256, MIN_BLOCKS = 0, PTS = 2; };
 template <> struct LinStreamDefault<ACM_MODEL_UCM> { static constexpr int DEPTH = 2, BLOCK = 256, MIN_BLOCKS = 0, PTS = 2; };
 template <> struct LinStreamDefault<ACM_MODEL_FOV> { static constexpr int DEPTH = 4, BLOCK = 256, MIN_BLOCKS = 0, PTS = 4; };
-template <> struct LinStreamDefault<ACM_MODEL_RADTAN> { static constexpr int DEPTH = 2, BLOCK = 256, MIN_BLOCKS = 0, PTS = 2; };
+template <> struct LinStreamDefault<ACM_MODEL_RADTAN> { static constexpr int DEPTH = 3, BLOCK = 256, MIN_BLOCKS = 0, PTS = 2; };
 #endif
 // KB (37 accumulators, 166 registers): 3 blocks of 128 threads.  Same-box A/B (scripts/ab_lin.sh; boxes of the pool differ by
 // up to 40 % on this FP64-bound kernel, so only same-box comparisons count): register prefetch 4.42 TB/s, ring 1 deep 3.95,
@@ -432,7 +432,9 @@ template <> struct LinStreamDefault<ACM_MODEL_RADTAN> { static constexpr int DEP
 // Round 2, same-box A/B (profiles/r02_ab_pts4.log): four points per trip, FOV 5262 -> 5463 GB/s (2 deep), KB 4789 -> 4861 (4 deep);
 // RadTan loses (5348 -> 5139 / 4255) and keeps two.  FOV in 256-thread blocks (the compiler then takes 126 registers instead of
 // 96, two blocks per SM): 5365 -> 5667 GB/s 4 deep, 5535 2 deep (profiles/r02_ab_fov_occ*.log); capping the registers for more
-// warps loses (80 registers, 24 warps: 5144); KB in 256-thread blocks is unchanged (4761 -> 4781).
+// warps loses (80 registers, 24 warps: 5144); KB in 256-thread blocks is unchanged (4761 -> 4781).  RadTan (198 registers, one
+// 256-thread block per SM, long_scoreboard 0.56 per issue with the ring 2 deep): 3 deep 5345 -> 5560, 4 deep 5561; two 128-thread
+// blocks 4876 (profiles/r02_ab_radtan_ring.log).
 template <> struct LinStreamDefault<ACM_MODEL_KANNALA_BRANDT> { static constexpr int DEPTH = 4, BLOCK = 128, MIN_BLOCKS = 0, PTS = 4; };
 template <int M> struct LinStream : LinStreamDefault<M> {};
 #ifdef ACM_EXP_MODEL  // tuning aid: -DACM_EXP_MODEL=<id> -DACM_EXP_DEPTH= -DACM_EXP_BLOCK= -DACM_EXP_MINB= overrides one model
@@ -451,7 +453,8 @@ template <> struct LinStream<ACM_EXP_MODEL> { static constexpr int DEPTH = ACM_E
 // 166 registers for Double Sphere but gain nothing (15.2 / 70.0).
 // -DACM_EXP_SOLVE_MODEL=<id> -DACM_EXP_SOLVE_DEPTH= -DACM_EXP_SOLVE_PTS= -DACM_EXP_SOLVE_MINB= overrides one model.
 template <int M> struct SolveStreamDefault {
-    static constexpr int DEPTH = (M == ACM_MODEL_FOV) ? 2 : LinStream<M>::DEPTH, PTS = LinStream<M>::PTS;   // FOV: the one-pass form is 4 deep in 256-thread blocks
+    // FOV, RadTan: the one-pass form runs deeper rings in 256-thread blocks; the solve keeps the depth it was measured with
+    static constexpr int DEPTH = (M == ACM_MODEL_FOV || M == ACM_MODEL_RADTAN) ? 2 : LinStream<M>::DEPTH, PTS = LinStream<M>::PTS;
     static constexpr int MIN_BLOCKS = (M == ACM_MODEL_KANNALA_BRANDT || M == ACM_MODEL_RADTAN) ? 0 : (M == ACM_MODEL_DOUBLE_SPHERE ? 2 : 3);
     // from this many correspondences per GPU on, the solve runs one uncapped 256-thread block per SM instead (half the blocks to
     // reduce over, same warps): Double Sphere 68.3 -> 66.0 us per pass at 10 M, 37.8 -> 37.2 at 5 M, 22.1 -> 22.3 at 2.5 M, slower at 450; UCM and FOV lose
