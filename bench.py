@@ -276,7 +276,7 @@ def run_ours(args):
     extras = None
     if not args.no_extras:
         barrier()
-        mine = run_extras(acm, N, lib, ctx, X, UV, n)
+        mine = run_extras(acm, N, lib, ctx, X, UV, n, sampler if rank == 0 else None, barrier)
         if dist is not None:
             gathered = [None] * world
             dist.all_gather_object(gathered, mine)
@@ -441,6 +441,15 @@ def run_ours(args):
             line["roofline_by_kernel"] = {k: {"bound": "hbm", "achieved": v["gb_s"], "peak": peak, "unit": "GB/s", "frac": v["gb_s"] / peak,
                                               "frac_of_nominal_8TBs": v["gb_s"] / 8000.0, "ms": v["ms"]}
                                           for k, v in extras.get("linearize_100M", {}).items()}
+            # the FP64-bound ones also against the FP64 issue rate at the clock sampled during a ~0.4 s loop of that kernel
+            for k, ipp in FP64_INSTR_PER_POINT.items():
+                v = extras.get("linearize_100M", {}).get(k)
+                if v and v.get("sustained_ms") and v.get("sm_mhz"):
+                    rate = ipp * n / (v["sustained_ms"] * 1e-3)
+                    line["roofline_by_kernel"][k]["fp64"] = {
+                        "instr_per_point": ipp, "sustained_ms": v["sustained_ms"], "sustained_gb_s": n * 40 / v["sustained_ms"] / 1e6, "sm_mhz": v["sm_mhz"],
+                        "issue_frac_at_clock": rate / (FP64_LANES_PER_CLOCK * v["sm_mhz"] * 1e6),
+                        "note": "FP64 lane-instructions issued per second / (148 SMs x 64 lanes x sampled SM clock); ncu shows ~75 % as the practical ceiling (math-pipe throttle)"}
         if check is not None and not check.get("ok", False):
             line["check_failed"] = True
         print(json.dumps(line))
@@ -463,6 +472,8 @@ def merge_extras(per_rank, n, world):
             for key, val in row.items():
                 if key.endswith("ms"):
                     merged[key] = max(r[group][name][key] for r in per_rank)
+                elif key.startswith("_r0_"):
+                    merged[key[4:]] = val   # sampled on rank 0 only
             for key, val in row.items():
                 if key.endswith("_bytes_per_point"):
                     base = key[: -len("_bytes_per_point")]
@@ -510,7 +521,13 @@ def oracle_check(acm, N, lib, ctx, kb, cam, rank, world, dist):
     return out
 
 
-def run_extras(acm, N, lib, ctx, X, UV, n):
+# FP64 instructions per point in the streaming loop of the FP64-bound fused kernels (DFMA + DMUL + DADD + DSETP, counted in the
+# SASS with scripts/sass_loop_stats.py).  The B200 issues 148 SMs x 64 FP64 lane-instructions per clock.
+FP64_INSTR_PER_POINT = {"double_sphere/pixel": 77, "kannala_brandt/pixel": 102, "rad_tan/pixel": 99, "fov/pixel": 82}
+FP64_LANES_PER_CLOCK = 148 * 64
+
+
+def run_extras(acm, N, lib, ctx, X, UV, n, sampler=None, barrier=None):
     """Every other kernel of the path on this rank's 100 M points: the fused pass of every model / residual (config 3),
     project / unproject / fused round trip for all models in f64 and f32 I/O (config 2), project + Jacobians."""
     import ctypes as C
@@ -532,8 +549,27 @@ def run_extras(acm, N, lib, ctx, X, UV, n):
         for kind, kname in ((0, "pixel"), (1, "algebraic")):
             if kind == 1 and mid not in (3, 4, 5):
                 continue
-            ms = timeit(lambda: ctx.check(lib.acm_linearize_async(ctx.handle, C.byref(cam), kind, X.handle, UV.handle)))
-            lin[f"{names[mid]}/{kname}"] = {"ms": ms, "_bytes_per_point": 40}
+            fn = lambda: ctx.check(lib.acm_linearize_async(ctx.handle, C.byref(cam), kind, X.handle, UV.handle))
+            ms = timeit(fn)
+            row = {"ms": ms, "_bytes_per_point": 40}
+            if f"{names[mid]}/{kname}" in FP64_INSTR_PER_POINT:
+                # FP64-bound kernels: the same launch for ~0.4 s with the SM clock sampled next to it, so that the FP64 issue
+                # rate can be quoted at the clock the power cap actually allowed
+                reps = int(max(20, min(2000, 400.0 / max(ms, 1e-3))))
+                if barrier:
+                    barrier()
+                w0 = time.time()
+                ctx.sync(); ctx.timer_start()
+                for _ in range(reps):
+                    fn()
+                row["sustained_ms"] = ctx.timer_stop() / reps
+                if barrier:
+                    barrier()
+                w1 = time.time()
+                ck = sampler.summary(w0, w1) if sampler else None
+                if ck:
+                    row["_r0_sm_mhz"] = ck["sm_mhz"]
+            lin[f"{names[mid]}/{kname}"] = row
     out["linearize_100M"] = lin
     pu = {}
     UV2 = acm.Points(ctx, 2, n); X2 = acm.Points(ctx, 3, n)
