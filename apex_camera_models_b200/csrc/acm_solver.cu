@@ -453,8 +453,13 @@ template <> struct LinStream<ACM_EXP_MODEL> { static constexpr int DEPTH = ACM_E
 // 166 registers for Double Sphere but gain nothing (15.2 / 70.0).
 // -DACM_EXP_SOLVE_MODEL=<id> -DACM_EXP_SOLVE_DEPTH= -DACM_EXP_SOLVE_PTS= -DACM_EXP_SOLVE_MINB= overrides one model.
 template <int M> struct SolveStreamDefault {
-    // FOV, RadTan: the one-pass form runs deeper rings in 256-thread blocks; the solve keeps the depth it was measured with
-    static constexpr int DEPTH = (M == ACM_MODEL_FOV || M == ACM_MODEL_RADTAN) ? 2 : LinStream<M>::DEPTH, PTS = LinStream<M>::PTS;
+    // Ring depth / points per trip of the solve, measured on their own (us per pass at 10 M correspondences,
+    // profiles/r02_ab_lm_fov.log, r02_ab_lm_kb_rt.log): FOV with four points per trip spilled under the 170-register cap (20
+    // bytes): two points, 3 deep = 95.7 -> 80.0; KB two points 3 deep (238 registers) 102.8 -> 98.6; RadTan 3 deep 94.0 -> 90.9
+    // (capping either at 170 registers spills: RadTan 154.6).
+    static constexpr bool WIDE_MODEL = (M == ACM_MODEL_FOV || M == ACM_MODEL_KANNALA_BRANDT || M == ACM_MODEL_RADTAN);
+    static constexpr int DEPTH = WIDE_MODEL ? 3 : LinStream<M>::DEPTH;
+    static constexpr int PTS = WIDE_MODEL ? 2 : LinStream<M>::PTS;
     static constexpr int MIN_BLOCKS = (M == ACM_MODEL_KANNALA_BRANDT || M == ACM_MODEL_RADTAN) ? 0 : (M == ACM_MODEL_DOUBLE_SPHERE ? 2 : 3);
     // from this many correspondences per GPU on, the solve runs one uncapped 256-thread block per SM instead (half the blocks to
     // reduce over, same warps): Double Sphere 68.3 -> 66.0 us per pass at 10 M, 37.8 -> 37.2 at 5 M, 22.1 -> 22.3 at 2.5 M, slower at 450; UCM and FOV lose

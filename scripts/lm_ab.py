@@ -19,6 +19,12 @@ for n in [int(v) for v in os.environ.get("SIZES", "450,1250000,10000000").split(
     elif target == "eucm":
         ds = acm.EucmModel(acm.Intrinsics(*KB[:4]), acm.Resolution(512, 512), [0.6, 1.0], ctx=ctx)
         cost = acm.EucmOptimizationCost(ds, X, U)
+    elif target == "kb":
+        ds = acm.KannalaBrandtModel(acm.Intrinsics(*KB[:4]), acm.Resolution(512, 512), [0.0] * 4, ctx=ctx)
+        cost = acm.KannalaBrandtOptimizationCost(ds, X, U)
+    elif target == "radtan":
+        ds = acm.RadTanModel(acm.Intrinsics(*KB[:4]), acm.Resolution(512, 512), [0.0] * 5, ctx=ctx)
+        cost = acm.RadTanOptimizationCost(ds, X, U)
     elif target == "fov":
         ds = acm.FovModel(acm.Intrinsics(*KB[:4]), acm.Resolution(512, 512), [0.9], ctx=ctx)
         cost = acm.FovOptimizationCost(ds, X, U)
