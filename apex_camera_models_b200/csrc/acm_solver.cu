@@ -434,7 +434,8 @@ template <> struct LinStreamDefault<ACM_MODEL_RADTAN> { static constexpr int DEP
 // 96, two blocks per SM): 5365 -> 5667 GB/s 4 deep, 5535 2 deep (profiles/r02_ab_fov_occ*.log); capping the registers for more
 // warps loses (80 registers, 24 warps: 5144); KB in 256-thread blocks is unchanged (4761 -> 4781).  RadTan (198 registers, one
 // 256-thread block per SM, long_scoreboard 0.56 per issue with the ring 2 deep): 3 deep 5345 -> 5560, 4 deep 5561; two 128-thread
-// blocks 4876 (profiles/r02_ab_radtan_ring.log).
+// blocks 4876 (profiles/r02_ab_radtan_ring.log).  Double Sphere (the headline kernel) does not move: 3 deep x 2 points 5931-5939, 4 deep x 4
+// points 5941, 4 deep x 2 points 5926-5952 GB/s over 200 launches (profiles/r02_ab_ds_headline.log).
 template <> struct LinStreamDefault<ACM_MODEL_KANNALA_BRANDT> { static constexpr int DEPTH = 4, BLOCK = 128, MIN_BLOCKS = 0, PTS = 4; };
 template <int M> struct LinStream : LinStreamDefault<M> {};
 #ifdef ACM_EXP_MODEL  // tuning aid: -DACM_EXP_MODEL=<id> -DACM_EXP_DEPTH= -DACM_EXP_BLOCK= -DACM_EXP_MINB= overrides one model
