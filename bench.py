@@ -449,7 +449,8 @@ def run_ours(args):
                     line["roofline_by_kernel"][k]["fp64"] = {
                         "instr_per_point": ipp, "sustained_ms": v["sustained_ms"], "sustained_gb_s": n * 40 / v["sustained_ms"] / 1e6, "sm_mhz": v["sm_mhz"],
                         "issue_frac_at_clock": rate / (FP64_LANES_PER_CLOCK * v["sm_mhz"] * 1e6),
-                        "note": "FP64 lane-instructions issued per second / (148 SMs x 64 lanes x sampled SM clock); ncu shows ~75 % as the practical ceiling (math-pipe throttle)"}
+                        "note": "FP64 lane-instructions issued per second / (148 SMs x 64 lanes x sampled SM clock); ncu shows ~75 % as the practical ceiling (math-pipe throttle)"
+                                + ("" if world == 1 else "; N > 1: the time is the slowest rank's, the clock rank 0's, so the fraction is a lower bound")}
         if check is not None and not check.get("ok", False):
             line["check_failed"] = True
         print(json.dumps(line))
