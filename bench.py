@@ -545,6 +545,14 @@ def run_extras(acm, N, lib, ctx, X, UV, n, sampler=None, barrier=None):
         for _ in range(reps):
             fn()
         return ctx.timer_stop() / reps
+    def agree_max(v):
+        import torch
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
     intr = KB_SAMPLE[:4]
     dist_init = {0: [], 1: [0.01, 0.001, 0.0, 0.0, 0.0], 2: KB_SAMPLE[4:], 3: [0.6], 4: [0.6, 1.0], 5: [0.6, 0.1], 6: [0.9]}
     names = {0: "pinhole", 1: "rad_tan", 2: "kannala_brandt", 3: "ucm", 4: "eucm", 5: "double_sphere", 6: "fov"}
@@ -561,7 +569,8 @@ def run_extras(acm, N, lib, ctx, X, UV, n, sampler=None, barrier=None):
             # the same launch for ~0.4 s with the SM clock sampled next to it: the 10-launch burst above runs at whatever
             # clock the previous kernel left behind (the power cap reacts over ~100 ms), which flatters the HBM-bound
             # kernels and penalises the FP64-bound ones; the FP64 issue rate is quoted at the clock sampled here
-            reps = int(max(20, min(2000, 400.0 / max(ms, 1e-3))))
+            # every rank must issue the same number of launches (each one is an exchange): agree on the slowest rank's time
+            reps = int(max(20, min(2000, 400.0 / max(agree_max(ms), 1e-3))))
             if barrier:
                 barrier()
             w0 = time.time()
