@@ -293,10 +293,15 @@ int32_t acm_comm_size(const acm_ctx* ctx); /* 1 when no communicator is attached
 
 /* Fused exchange over NVLink peer memory (one process per GPU on one NVSwitch box).  Every rank
  * exports a small exchange buffer as a 64-byte CUDA IPC handle, the host gathers the handles of all
- * ranks (any transport) and attaches them.  From then on the last block of the linearisation kernel
- * stores its rank's normal equations straight into every peer's buffer, waits for the peers' and
- * adds them in rank order -- pass, all-reduce and LM step are ONE kernel per iteration and every
- * rank holds bit-identical sums.  Replaces the NCCL all-reduce of acm_linearize / acm_lm_solve. */
+ * ranks (any transport) and attaches them.  From then on the reducers of the linearisation kernel store
+ * their rank's sums straight into every peer's buffer as tagged cells, wait for the peers' and add them
+ * in rank order -- pass, all-reduce (and, for acm_lm_solve, every LM step of the solve) are ONE kernel
+ * and every rank holds bit-identical sums.  Replaces the NCCL all-reduce of acm_linearize / acm_lm_solve.
+ * Like any collective, the calls that carry an exchange (acm_linearize*, acm_lm_solve, and the
+ * all-reduced acm_linear_estimation / acm_reprojection_error) must be made in the same order and the
+ * same number of times on every rank: the exchanges are numbered per context.  A rank that waits ~2 s
+ * for a peer's cell aborts the exchange on EVERY rank; the calls return ACM_ERR_PEER and the context
+ * refuses further exchanges until acm_peer_detach + acm_peer_attach (which zero buffers and counters). */
 int32_t acm_peer_export(acm_ctx* ctx, uint8_t handle[64]);
 int32_t acm_peer_attach(acm_ctx* ctx, int32_t n_ranks, int32_t rank, const uint8_t* handles /* n_ranks * 64 bytes */);
 int32_t acm_peer_detach(acm_ctx* ctx);
