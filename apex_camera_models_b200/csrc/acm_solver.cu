@@ -958,6 +958,16 @@ static int32_t peer_failure(acm_ctx* ctx) {
 // Enqueue one pass (+ the cross-rank sum).  With peers attached the sum happens inside the kernel;
 // otherwise an NCCL all-reduce follows when a communicator is attached.  d_lm != nullptr: evaluate at
 // the trial point of the device-resident LM state (NCCL path of acm_lm_solve).
+
+// The exchange number that travels in the cells: the per-context counter in the low 48 bits (its parity picks the cell set) and a
+// signature of the call (model, residual kind, one pass / solve) in the upper 16.  Ranks whose call sequences have drifted apart
+// (one of them made a call the others did not) then wait for tags that never come and leave with ACM_ERR_PEER after the
+// time-out, instead of silently adding the sums of different kernels.
+static unsigned long long exchange_tag(unsigned long long seq, int model, int kind, int mode) {
+    const unsigned long long sig = 0x8000ULL | ((unsigned long long)(mode & 3) << 8) | ((unsigned long long)(kind & 1) << 4) | (unsigned long long)(model & 15);
+    return (seq & 0xFFFFFFFFFFFFULL) | (sig << 48);
+}
+
 static int32_t enqueue_linearize(acm_ctx* ctx, const acm_camera* cam, int32_t kind, LmState* d_lm, const acm_points* xyz,
                                  const acm_points* uv, double invalid_penalty, int* nacc) {
     LinKernelArgs a;
@@ -970,7 +980,7 @@ static int32_t enqueue_linearize(acm_ctx* ctx, const acm_camera* cam, int32_t ki
         int32_t rc = check_peer_state(ctx);
         if (rc) return rc;
         a.peer.bufs = ctx->d_peer_ptrs; a.peer.n_ranks = ctx->peer_n; a.peer.rank = ctx->peer_rank;
-        a.peer.seq = ++ctx->peer_seq;   // this launch executes exactly one exchange
+        a.peer.seq = exchange_tag(++ctx->peer_seq, cam->model, kind, 0);   // this launch executes exactly one exchange
     }
     ACM_DISPATCH_LIN(cam->model, kind, {
         int32_t rc = launch_lin<M, KIND>(ctx, a, xyz, uv);
@@ -1107,7 +1117,7 @@ extern "C" int32_t acm_lm_solve(acm_ctx* ctx, const acm_camera* init, int32_t re
         a.pen2x2 = 2.0 * cfg.invalid_penalty * cfg.invalid_penalty;
         if (use_peer) {
             a.peer.bufs = ctx->d_peer_ptrs; a.peer.n_ranks = ctx->peer_n; a.peer.rank = ctx->peer_rank;
-            a.peer.seq = ctx->peer_seq + 1;
+            a.peer.seq = exchange_tag(ctx->peer_seq + 1, init->model, residual_kind, 2);   // + pass inside the kernel
         }
         const bool want_trace = getenv("ACM_LM_TRACE") != nullptr;   // debug: per-phase clock64 stamps of block 0 -> stderr
         const size_t trace_words = (size_t)max_passes * 12 + (size_t)ctx->sm_count * 16 * 3;

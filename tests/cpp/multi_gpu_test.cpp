@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "acm.h"
@@ -211,6 +212,24 @@ int main(int argc, char** argv) {
         OK(ctx[0], acm_comm_init_all(ctx.data(), G));
         OK(ctx[0], acm_lm_solve_multi(ctx.data(), G, &ds1, ACM_RESIDUAL_ALGEBRAIC, Xs.data(), Us.data(), lo, hi, nullptr, pp, &rr));
         CHECK(rr.status == r1.status && rr.iterations == r1.iterations);
+        for (int i = 0; i < 6; ++i) CHECK(close_rel(pp[i], par1[i], 1e-11));
+    }
+    // Ranks whose call sequences drifted apart must not add the sums of different kernels: rank 0 linearises with the
+    // algebraic residual while rank 1 linearises with the pixel residual under the same exchange number.  The call signature
+    // travels in the cell tags, so neither accepts the other's cells; both give up after the time-out with ACM_ERR_PEER.
+    {
+        int32_t rc0 = 0, rc1 = 0;
+        acm_normal_equations ne0, ne1;
+        std::thread ta([&] { rc0 = acm_linearize(ctx[0], &ds1, ACM_RESIDUAL_ALGEBRAIC, Xs[0], Us[0], &ne0); });
+        std::thread tb([&] { rc1 = acm_linearize(ctx[1], &ds1, ACM_RESIDUAL_PIXEL, Xs[1], Us[1], &ne1); });
+        ta.join(); tb.join();
+        std::printf("MISMATCH_RC %d %d\n", rc0, rc1);
+        CHECK(rc0 == ACM_ERR_PEER && rc1 == ACM_ERR_PEER);
+        OK(ctx[0], acm_comm_destroy_all(ctx.data(), G));
+        OK(ctx[0], acm_comm_init_all(ctx.data(), G));
+        acm_lm_result rr;
+        double pp[ACM_MAX_PARAMS];
+        OK(ctx[0], acm_lm_solve_multi(ctx.data(), G, &ds1, ACM_RESIDUAL_ALGEBRAIC, Xs.data(), Us.data(), lo, hi, nullptr, pp, &rr));
         for (int i = 0; i < 6; ++i) CHECK(close_rel(pp[i], par1[i], 1e-11));
     }
     for (int g = 0; g < G; ++g) { acm_points_destroy(ctx[g], Xs[g]); acm_points_destroy(ctx[g], Us[g]); }

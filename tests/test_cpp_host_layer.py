@@ -12,7 +12,7 @@ LIBDIR = os.path.join(ROOT, "apex_camera_models_b200", "lib")
 
 def _build(tmp_path, name="host_test"):
     exe = str(tmp_path / name)
-    cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-pthread", "-I", os.path.join(ROOT, "include"),
            os.path.join(ROOT, "tests", "cpp", name + ".cpp"), "-o", exe, "-L", LIBDIR, "-lacm", f"-Wl,-rpath,{LIBDIR}"]
     subprocess.run(cmd, check=True)
     return exe
