@@ -1,4 +1,4 @@
-//! Raw bindings of `include/acm.h` (ABI version 1).  One `extern "C"` item per symbol of the header,
+//! Raw bindings of `include/acm.h` (ABI version 2).  One `extern "C"` item per symbol of the header,
 //! same order.  NOT compiled in this repository's environment (no Rust toolchain in the image); the
 //! ctypes table `apex_camera_models_b200/_native.py` is the tested twin of this file and
 //! `tests/test_abi_and_host_logic.py` checks that table against the header and the built library.
